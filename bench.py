@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of the hot path.
+
+A "step" is ONE pass of the hot path over one batch of synthetic input.  Workload =
+BASELINE.json configs[1]: NodeResourcesAllocatable, mode Most + NormalizeScore, 10k pending pods
+x 50k nodes per GPU (node axis sharded across GPUs => weak scaling), upstream feasibility mask of
+density 0.875, MATRIX output (every pod x node score, the layout the Go framework needs).
+
+  value     pod x node Score evals/s with inputs resident in HBM (int64 score matrix, 8 B/eval —
+            the SURVEY §8d contract layout), CUDA events on the engine's stream, max over ranks
+  roofline  the dominant kernel (alloc_norm_kernel) — algorithmic bytes / its mean launch time,
+            against the measured HBM copy peak of MEASURED_PEAKS.json
+  e2e       same metric through the C-ABI call the Go shim makes (b200s_score_batch): pinned HOST
+            buffers in, H2D of the step's inputs, kernels, D2H of the whole score matrix
+            (compact u8 transport, values identical to the int64 matrix; the int64 transport is
+            reported beside it as e2e_i64)
+  cpu_baseline  the CPU oracle (a port of the Go path; Go is not installed) on a bounded sample
+
+`--impl reference` times the CPU path alone (rank 0 only) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_PODS = 10_000
+N_NODES = 50_000  # per GPU
+MODE_MOST = 1
+WEIGHTS = [1 << 20, 1]
+CONFIG_NO = 2
+METRIC = "pod_x_node_score_evals_per_sec"
+UNIT = "evals/s"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(seed, P, N, npad, rank):
+    from scheduler_plugins_b200 import synth
+
+    nodes = synth.gen_nodes(seed + 1000 * rank, N)
+    feas = synth.gen_feasible_words(seed + 1000 * rank, P, N, npad)
+    return nodes, feas
+
+
+def cpu_sample(orc, cols, feas, sample_pods, threads):
+    """Times the oracle (port of allocatable.go Score + NormalizeScore) on sample_pods x N."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    N = len(cols[0])
+    chunks = np.array_split(np.arange(sample_pods), threads)
+    chunks = [c for c in chunks if len(c)]
+
+    def work(idx):
+        orc.alloc_batch(cols, WEIGHTS, MODE_MOST, len(idx), np.ascontiguousarray(feas[idx]), pitch=N)
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        work(chunks[0])
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, chunks))
+    dt = time.perf_counter() - t0
+    return sample_pods * N / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; the Go toolchain is absent) alone."""
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+
+    g.build()
+    from oracle import pyoracle as orc
+    from scheduler_plugins_b200 import engine as E
+
+    seed = 0xB2005EED + CONFIG_NO
+    N = N_NODES
+    npad = E.npad_of(N)
+    threads = os.cpu_count() or 1
+    sample = max(threads * 64, 256)
+    nodes, feas = make_inputs(seed, sample, N, npad, 0)
+    cols = [nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]]
+    for _ in range(args.warmup):
+        cpu_sample(orc, cols, feas, sample, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(orc, cols, feas, sample, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample * N / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "configs[1]: NodeResourcesAllocatable Most + NormalizeScore, 10k pods x 50k nodes/GPU",
+                   "note": f"each step = bounded sample of {sample} pods x {N} nodes of that workload"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} pods x {N} nodes per step, {threads} threads over pods; C port of "
+                                   "allocatable.go:63-168 (Go toolchain absent, reference not runnable)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pods", type=int, default=P_PODS)
+    ap.add_argument("--nodes", type=int, default=N_NODES)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    if rank == 0:
+        g.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from scheduler_plugins_b200 import engine as E
+
+    torch.cuda.set_device(local)
+    P, N = args.pods, args.nodes
+    seed = 0xB2005EED + CONFIG_NO
+    eng = E.Engine(local)
+    if world > 1:
+        uid = [eng.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
+    eng.snapshot_begin(N, generation=1, node_offset=rank * N, n_nodes_global=world * N)
+    npad = eng.Npad
+    nodes, feas_np = make_inputs(seed, P, N, npad, rank)
+    cols = [nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]]
+    eng.snapshot_allocatable(cols)
+    eng.snapshot_commit()
+    eng.config_allocatable(MODE_MOST, WEIGHTS)
+
+    words = npad // 64
+    # pinned host staging for the e2e leg (what the cgo shim would hold)
+    pin_feas = eng.pinned(P * words * 8)
+    feas_pin = pin_feas.view(np.uint64, (P, words))
+    feas_pin[:] = feas_np
+    pin_out8 = eng.pinned(P * npad)
+    out8 = pin_out8.view(np.uint8, (P, npad))
+
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM --------------------------------------
+    eng.pods_upload(P, feasible=feas_pin)
+    for _ in range(args.warmup):
+        eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_I64)
+    eng.sync()
+    eng.kernel_time(E.PLUGIN_ALLOCATABLE)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    eng.set_profiling(True)
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_I64)
+    e1.record(ext)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    k_ms, k_n = eng.kernel_time(E.PLUGIN_ALLOCATABLE)
+    eng.set_profiling(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    evals_per_step = P * N * world
+    value = evals_per_step / (ms_step * 1e-3)
+
+    # ---------------- e2e: host buffers through b200s_score_batch ---------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    batch, keep = eng.make_batch(P, feasible=feas_pin)
+
+    def e2e_leg(dtype, out):
+        for _ in range(2):
+            eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, dtype, out)
+        barrier()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ext)
+        for _ in range(e2e_steps):
+            eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, dtype, out)
+        b.record(ext)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        dev = a.elapsed_time(b)
+        tt = torch.tensor([max(wall, dev)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / e2e_steps
+
+    ms_e2e8 = e2e_leg(E.OUT_U8, out8)
+    chk8 = int(out8[:4].astype(np.int64).sum())
+    e2e_i64 = None
+    try:
+        pin_out64 = eng.pinned(P * npad * 8)
+        out64 = pin_out64.view(np.int64, (P, npad))
+        ms_e2e64 = e2e_leg(E.OUT_I64, out64)
+        assert int(out64[:4].sum()) == chk8, "u8 and int64 transports disagree"
+        e2e_i64 = {"value": evals_per_step / (ms_e2e64 * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": P * words * 8, "d2h_bytes_per_step": P * npad * 8}
+        pin_out64.free()
+    except MemoryError:
+        pass
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- roofline of the dominant kernel ------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # algorithmic bytes per launch: int64 score matrix + mask bits + raw + params
+    alg_bytes = P * N * 8 + P * ((N + 7) // 8) + N * 8 + P * 32
+    k_avg_ms = k_ms / max(k_n, 1)
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "alloc_norm_kernel<int64>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms,
+                "kernel_share_of_step": k_avg_ms / ms_step if ms_step else None}
+    ncu_traffic = os.path.join(ROOT, "profiles", "r01_alloc_norm_traffic.json")
+    if os.path.exists(ncu_traffic):
+        try:
+            roofline["traffic"] = json.load(open(ncu_traffic)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import pyoracle as orc
+
+        sample = 96
+        v1, dt1 = cpu_sample(orc, cols, feas_np, sample, 1)
+        # checker, not product: the sampled rows of the e2e result equal the oracle's
+        want = orc.alloc_batch(cols, WEIGHTS, MODE_MOST, 4, np.ascontiguousarray(feas_np[:4]), pitch=npad)
+        assert np.array_equal(out8[:4].astype(np.int64), want), "GPU result differs from the oracle"
+        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{sample} pods x {N} nodes, scalar single-thread C port of allocatable.go:63-168 "
+                         f"({dt1:.2f} s); Go toolchain absent so the reference itself cannot run",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "configs[1]: NodeResourcesAllocatable Most + NormalizeScore, "
+                                   f"{P} pods x {N} nodes/GPU, feasibility density 0.875, MATRIX output",
+                       "pods": P, "nodes_per_gpu": N, "parallelism": f"node-sharded x{world}",
+                       "value_out": "int64 [P][Npad] (8 B/eval)", "e2e_out": "u8 [P][Npad] (1 B/eval, same values)",
+                       "l2": f"score matrix {P * npad * 8 / 1e9:.2f} GB/step >> 126 MB L2: every step streams past L2"},
+            "e2e": {"value": evals_per_step / (ms_e2e8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": P * words * 8,
+                    "d2h_bytes_per_step": P * npad, "steps": e2e_steps, "ms_per_step": ms_e2e8},
+            "e2e_i64": e2e_i64,
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    pin_feas.free()
+    pin_out8.free()
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs — never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} missing: run `make -C oracle` (or __graft_entry__.build())")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_alloc_score.restype = C.c_int64
+        _lib.orc_tlp_score.restype = C.c_int64
+        _lib.orc_tlp_score.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64]
+        _lib.orc_lvrb_score.restype = C.c_int64
+        _lib.orc_lvrb_score.argtypes = [C.c_double] * 4 + [C.c_int64, C.c_int64, C.c_uint8, C.c_int64, C.c_int64,
+                                                           C.c_double, C.c_double]
+        _lib.orc_lvrb_compute_score.restype = C.c_double
+        _lib.orc_lvrb_compute_score.argtypes = [C.c_double] * 6
+    return _lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def alloc_score(alloc, weights, mode) -> int:
+    a = _c(alloc, np.int64); w = _c(weights, np.int64)
+    return int(lib().orc_alloc_score(_p(a), _p(w), C.c_int(len(a)), C.c_int(mode)))
+
+
+def alloc_normalize(scores):
+    s = _c(scores, np.int64).copy()
+    lib().orc_alloc_normalize(_p(s), C.c_int(len(s)))
+    return s
+
+
+def alloc_batch(cols, weights, mode, P, feasible_words=None, pitch=None):
+    cols = [_c(c, np.int64) for c in cols]
+    N = len(cols[0])
+    pitch = pitch or N
+    w = _c(weights, np.int64)
+    arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    out = np.zeros((P, pitch), dtype=np.int64)
+    fw = None if feasible_words is None else _c(feasible_words, np.uint64)
+    words = 0 if fw is None else fw.shape[1]
+    lib().orc_alloc_batch(arr, C.c_int(len(cols)), C.c_int(N), _p(w), C.c_int(mode), C.c_int(P), _p(fw),
+                          C.c_int(words), _p(out), C.c_int(pitch))
+    return out
+
+
+def tlp_score(util, cap, missing, flags, pod_cpu, target=40) -> int:
+    return int(lib().orc_tlp_score(util, cap, missing, flags, pod_cpu, target))
+
+
+def tlp_batch(util, cap, missing, flags, pod_cpu, target=40, pitch=None):
+    util = _c(util, np.float64); cap = _c(cap, np.int64); missing = _c(missing, np.int64)
+    flags = _c(flags, np.uint8); pod_cpu = _c(pod_cpu, np.int64)
+    N, P = len(util), len(pod_cpu)
+    pitch = pitch or N
+    out = np.zeros((P, pitch), dtype=np.int64)
+    lib().orc_tlp_batch(_p(util), _p(cap), _p(missing), _p(flags), C.c_int(N), _p(pod_cpu), C.c_int(P),
+                        C.c_int64(target), _p(out), C.c_int(pitch))
+    return out
+
+
+def lvrb_compute_score(used_avg, used_std, req, capacity, margin, sensitivity) -> float:
+    return float(lib().orc_lvrb_compute_score(used_avg, used_std, req, capacity, margin, sensitivity))
+
+
+def lvrb_mu_sigma(used_avg, used_std, req, capacity):
+    mu, sg = C.c_double(), C.c_double()
+    lib().orc_lvrb_mu_sigma(C.c_double(used_avg), C.c_double(used_std), C.c_double(req), C.c_double(capacity),
+                            C.byref(mu), C.byref(sg))
+    return mu.value, sg.value
+
+
+def lvrb_score(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, req_cpu, req_mem, margin=1.0,
+               sens=1.0) -> int:
+    return int(lib().orc_lvrb_score(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, req_cpu,
+                                    req_mem, margin, sens))
+
+
+def lvrb_batch(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, req_cpu, req_mem, margin=1.0,
+               sens=1.0, pitch=None):
+    f = [_c(x, np.float64) for x in (cpu_avg, cpu_std, mem_avg, mem_std)]
+    i = [_c(x, np.int64) for x in (alloc_cpu, alloc_mem)]
+    fl = _c(flags, np.uint8); rc = _c(req_cpu, np.int64); rm = _c(req_mem, np.int64)
+    N, P = len(fl), len(rc)
+    pitch = pitch or N
+    out = np.zeros((P, pitch), dtype=np.int64)
+    lib().orc_lvrb_batch(*[_p(x) for x in f], *[_p(x) for x in i], _p(fl), C.c_int(N), _p(rc), _p(rm), C.c_int(P),
+                         C.c_double(margin), C.c_double(sens), _p(out), C.c_int(pitch))
+    return out

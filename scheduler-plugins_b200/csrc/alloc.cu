@@ -1,0 +1,283 @@
+// NodeResourcesAllocatable: Score + NormalizeScore for all pods x all nodes.
+//
+// Reference semantics (pkg/noderesources):
+//   raw(n)   = ( sum_r sign * alloc_r(n) * w_r ) / sum_r w_r        allocatable.go:117-140
+//              int64 wrapping, Go truncating division; sign = -1 (Least) / +1 (Most), 0 otherwise.
+//              The scorer never reads `requested` (allocatable.go:122) => raw is POD-INDEPENDENT.
+//   norm(p,n)= (raw(n) - lo_p) * 100 / (hi_p - lo_p)                allocatable.go:143-168
+//              lo_p/hi_p = min/max of raw over the pod's FEASIBLE nodes; range 0 => 0.
+//
+// B200 design (not a translation):
+//   * raw[] is computed once per (snapshot, args) and radix-sorted (CUB, snapshot time, off the
+//     hot path).  Per pod, lo/hi are then the first/last FEASIBLE entries of the sorted order:
+//     one warp ballots 32 sorted positions at a time from each end — O(1/density) probes per pod
+//     instead of an O(N) reduction per pod.
+//   * The P x N pass is a pure streaming-store kernel: each thread keeps its nodes' raw values
+//     in registers, walks the pod tile, and divides with a per-pod 32-bit magic reciprocal
+//     (range*100 < 2^32; anything else takes the exact generic int64 path).  The only HBM
+//     traffic is the score matrix itself (8 B/eval for int64, 1 B/eval for u8), written with
+//     128-bit evict-first stores.  Inputs (raw 4-8 B/node, 32 B/pod, 1 bit/eval mask) stay in L2.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+struct AllocArgs {
+  int64_t w[16];
+  int R;
+  int mode;
+};
+
+__global__ void alloc_raw_kernel(const int64_t* __restrict__ cols, int N, int Npad, AllocArgs a,
+                                 int64_t* __restrict__ raw, int32_t* __restrict__ iota) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Npad) return;
+  int64_t node_score = 0, weight_sum = 0;
+  for (int r = 0; r < a.R; ++r) {
+    int64_t cap = cols[(size_t)r * Npad + n];
+    int64_t rs = a.mode == B200S_ALLOC_LEAST ? wrap_mul(-1, cap) : (a.mode == B200S_ALLOC_MOST ? cap : 0);
+    node_score = wrap_add(node_score, wrap_mul(rs, a.w[r]));
+    weight_sum = wrap_add(weight_sum, a.w[r]);
+  }
+  raw[n] = n < N ? go_div(node_score, weight_sum) : 0;
+  if (n < N) iota[n] = n;
+}
+
+// One warp per pod.  lo = raw of the first feasible node in ascending sorted order, hi = last.
+__global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, const int32_t* __restrict__ order,
+                                    const uint64_t* __restrict__ feasible, int words, int N, int P,
+                                    int64_t* __restrict__ lo, int64_t* __restrict__ hi) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const uint64_t* row = feasible ? feasible + (size_t)warp * words : nullptr;
+  int64_t vlo = INT64_MAX, vhi = -INT64_MAX;  // allocatable.go:145-146
+  if (N > 0) {
+    if (!row) {
+      vlo = sorted_raw[0];
+      vhi = sorted_raw[N - 1];
+    } else {
+      for (int base = 0; base < N; base += 32) {
+        int i = base + lane;
+        bool f = false;
+        if (i < N) {
+          int node = order[i];
+          f = (row[node >> 6] >> (node & 63)) & 1ull;
+        }
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        if (b) {
+          vlo = sorted_raw[base + __ffs(b) - 1];
+          break;
+        }
+      }
+      {
+        for (int top = N - 1; top >= 0; top -= 32) {
+          int i = top - lane;
+          bool f = false;
+          if (i >= 0) {
+            int node = order[i];
+            f = (row[node >> 6] >> (node & 63)) & 1ull;
+          }
+          unsigned b = __ballot_sync(0xffffffffu, f);
+          if (b) {
+            vhi = sorted_raw[top - (__ffs(b) - 1)];
+            break;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    lo[warp] = vlo;
+    hi[warp] = vhi;
+  }
+}
+
+__global__ void norm_params_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, int P,
+                                   NormParam* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  NormParam q;
+  q.lo = lo[p];
+  q.range = wrap_sub(hi[p], lo[p]);
+  q.magic = 0;
+  q.shift = 0;
+  q.pad = 0;
+  if (lo[p] > hi[p] || q.range == 0) {
+    q.mode = 0;  // empty feasible set, or oldRange == 0 => MinNodeScore (allocatable.go:158-160)
+  } else if (q.range > 0 && q.range <= (int64_t)(0xffffffffu / 100u)) {
+    // (raw-lo)*100 < 2^32 for every feasible node: exact 32-bit reciprocal division with one fix-up.
+    uint32_t r = (uint32_t)q.range;
+    uint32_t s = 31 - __clz(r);
+    uint64_t m = ((1ull << 32) << s) / r;  // floor(2^(32+s)/r) in (2^31, 2^32]
+    q.magic = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
+    q.shift = s;
+    q.mode = 1;
+  } else {
+    q.mode = 2;  // generic wrapping int64 path (Go semantics incl. overflow)
+  }
+  out[p] = q;
+}
+
+// Tile: (256 threads x NPT nodes) x PT pods.  Thread t owns nodes n0 + t*NPT .. +NPT-1.
+template <class OutT, int NPT, int PT>
+__global__ void __launch_bounds__(256)
+alloc_norm_kernel(const int64_t* __restrict__ raw, const NormParam* __restrict__ params,
+                  const uint64_t* __restrict__ feasible, int words, int N, int Npad, int P,
+                  OutT* __restrict__ out) {
+  constexpr int CHUNK = 256 * NPT;
+  __shared__ NormParam sp[PT];
+  __shared__ uint64_t sm[PT][CHUNK / 64];
+  const int n0 = blockIdx.x * CHUNK;
+  const int p0 = blockIdx.y * PT;
+  const int t = threadIdx.x;
+  const int nb = n0 + t * NPT;
+
+  for (int i = t; i < PT; i += 256)
+    if (p0 + i < P) sp[i] = params[p0 + i];
+  if (feasible) {
+    for (int i = t; i < PT * (CHUNK / 64); i += 256) {
+      int pp = i / (CHUNK / 64), w = i % (CHUNK / 64);
+      int gw = n0 / 64 + w;
+      sm[pp][w] = (p0 + pp < P && gw < words) ? feasible[(size_t)(p0 + pp) * words + gw] : 0ull;
+    }
+  }
+  uint32_t r32[NPT];
+  uint32_t valid = 0;
+  if (nb < Npad) {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      r32[j] = (uint32_t)(uint64_t)raw[nb + j];
+      if (nb + j < N) valid |= 1u << j;
+    }
+  }
+  __syncthreads();
+  if (nb >= Npad) return;
+  const int wi = (t * NPT) / 64, sh = (t * NPT) % 64;
+  const int pend = min(PT, P - p0);
+  OutT* orow = out + (size_t)p0 * Npad + nb;
+  for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+    const NormParam np = sp[pp];
+    uint32_t bits = valid;
+    if (feasible) bits &= (uint32_t)(sm[pp][wi] >> sh);
+    if (np.mode == 1) {
+      const uint32_t lo32 = (uint32_t)(uint64_t)np.lo, rg = (uint32_t)np.range;
+      uint32_t q[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        uint32_t n100 = (r32[j] - lo32) * 100u;
+        uint32_t q0 = __umulhi(n100, np.magic) >> np.shift;
+        uint32_t rem = n100 - q0 * rg;
+        q0 += rem >= rg ? 1u : 0u;
+        q[j] = ((bits >> j) & 1u) ? q0 : 0u;
+      }
+      Store<OutT, NPT>::put32(orow, q);
+    } else if (np.mode == 0) {
+      uint32_t q[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) q[j] = 0;
+      Store<OutT, NPT>::put32(orow, q);
+    } else {
+      int64_t q[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        int64_t v = go_div(wrap_mul(wrap_sub(raw[nb + j], np.lo), 100), np.range);
+        q[j] = ((bits >> j) & 1u) ? v : 0;
+      }
+      Store<OutT, NPT>::put64(orow, q);
+    }
+  }
+}
+
+}  // namespace
+
+int build_norm_params(b200s_ctx* c, int P) {
+  B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
+  if (P == 0) return B200S_OK;
+  norm_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P,
+                                                              c->norm_params.as<NormParam>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  return B200S_OK;
+}
+
+static int alloc_prepare(b200s_ctx* c) {
+  uint64_t key = c->snap_serial * 1000003ull + c->alloc_cfg_gen;
+  if (c->alloc_prepared_key == key) return B200S_OK;
+  const int N = c->N, Npad = c->Npad;
+  B200S_CUDA_TRY(c, c->alloc_raw.ensure((size_t)Npad * 8));
+  B200S_CUDA_TRY(c, c->alloc_sorted_raw.ensure((size_t)Npad * 8));
+  B200S_CUDA_TRY(c, c->alloc_order.ensure((size_t)Npad * 4));
+  B200S_CUDA_TRY(c, c->alloc_iota.ensure((size_t)Npad * 4));
+  AllocArgs a;
+  a.R = c->alloc_R;
+  a.mode = c->alloc_mode;
+  for (int r = 0; r < 16; ++r) a.w[r] = r < a.R ? c->alloc_w[r] : 0;
+  alloc_raw_kernel<<<(Npad + 255) / 256, 256, 0, c->stream>>>(c->alloc_cols.as<int64_t>(), N, Npad, a,
+                                                              c->alloc_raw.as<int64_t>(), c->alloc_iota.as<int32_t>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  if (N > 0) {
+    size_t tmp = 0;
+    B200S_CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->alloc_raw.as<int64_t>(),
+                                                      c->alloc_sorted_raw.as<int64_t>(), c->alloc_iota.as<int32_t>(),
+                                                      c->alloc_order.as<int32_t>(), N, 0, 64, c->stream));
+    B200S_CUDA_TRY(c, c->sort_tmp.ensure(tmp));
+    B200S_CUDA_TRY(c, cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp, c->alloc_raw.as<int64_t>(),
+                                                      c->alloc_sorted_raw.as<int64_t>(), c->alloc_iota.as<int32_t>(),
+                                                      c->alloc_order.as<int32_t>(), N, 0, 64, c->stream));
+  }
+  c->alloc_prepared_key = key;
+  return B200S_OK;
+}
+
+int alloc_eval(b200s_ctx* c, int dtype) {
+  if (!c->has_alloc) return c->set_err(B200S_ERR_STATE, "NodeResourcesAllocatable: snapshot has no allocatable columns");
+  if (!c->alloc_cfg) return c->set_err(B200S_ERR_STATE, "NodeResourcesAllocatable: args not configured");
+  if (c->alloc_cfg_R != c->alloc_R)
+    return c->set_err(B200S_ERR_INVALID, "NodeResourcesAllocatable: weights do not match the snapshot's resource columns");
+  const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
+  B200S_TRY(ensure_out(c, B200S_PLUGIN_ALLOCATABLE, dtype, false, false));
+  if (P == 0) {
+    c->out[B200S_PLUGIN_ALLOCATABLE].valid = true;
+    return B200S_OK;
+  }
+  B200S_TRY(alloc_prepare(c));
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
+  B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
+  const uint64_t* feas = c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr;
+  {
+    int threads = 128, warps_per_block = threads / 32;
+    alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
+        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, c->pod_lo.as<int64_t>(),
+        c->pod_hi.as<int64_t>());
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  B200S_TRY(comm_allreduce_minmax(c, c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P));
+  B200S_TRY(build_norm_params(c, P));
+  PluginOut& o = c->out[B200S_PLUGIN_ALLOCATABLE];
+  KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
+  if (dtype == B200S_OUT_I64) {
+    constexpr int NPT = 2, PT = 64;
+    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+    alloc_norm_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(),
+                                                                    c->norm_params.as<NormParam>(), feas, words, N,
+                                                                    Npad, P, o.scores.as<int64_t>());
+  } else {
+    constexpr int NPT = 8, PT = 64;
+    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+    alloc_norm_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(),
+                                                                    c->norm_params.as<NormParam>(), feas, words, N,
+                                                                    Npad, P, o.scores.as<uint8_t>());
+  }
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  o.valid = true;
+  return B200S_OK;
+}
+
+}  // namespace b200s

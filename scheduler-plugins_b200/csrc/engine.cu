@@ -1,0 +1,581 @@
+// libb200sched: lifecycle, snapshot columns, pod batches, result fetch — the C-ABI of
+// include/b200sched.h.  Kernels live in alloc.cu / trimaran.cu / nrt.cu / netoh.cu / combined.cu.
+#include "engine.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace b200s;
+
+namespace {
+
+thread_local std::string tl_err;
+
+struct Guard {
+  b200s_ctx* c;
+  std::unique_lock<std::mutex> lk;
+  explicit Guard(b200s_ctx* ctx) : c(ctx), lk(ctx->mu) { cudaSetDevice(ctx->device); }
+};
+
+// Copies a host column of n elements into a device buffer padded to npad elements (pad = 0).
+template <class T>
+int upload_col(b200s_ctx* c, DevBuf& dst, size_t dst_off_elems, const T* src, int n, int npad) {
+  T* d = dst.as<T>() + dst_off_elems;
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(d, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  if (npad > n) B200S_CUDA_TRY(c, cudaMemsetAsync(d + n, 0, sizeof(T) * (size_t)(npad - n), c->stream));
+  return B200S_OK;
+}
+
+int require_open(b200s_ctx* c) {
+  if (!c->snap_open) return c->set_err(B200S_ERR_STATE, "snapshot column set outside b200s_snapshot_begin/commit");
+  return B200S_OK;
+}
+
+}  // namespace
+
+namespace b200s {
+
+int ensure_out(b200s_ctx* c, int plugin, int dtype, bool feas, bool reasons) {
+  PluginOut& o = c->out[plugin];
+  size_t elems = (size_t)c->P * (size_t)c->Npad;
+  B200S_CUDA_TRY(c, o.scores.ensure(elems * (dtype == B200S_OUT_I64 ? 8 : 1)));
+  if (feas) B200S_CUDA_TRY(c, o.feas.ensure((size_t)c->P * (size_t)(c->Npad / 64) * 8));
+  if (reasons) B200S_CUDA_TRY(c, o.reasons.ensure(elems));
+  o.dtype = dtype;
+  o.P = c->P;
+  o.has_feas = feas;
+  o.has_reasons = reasons;
+  o.valid = false;
+  return B200S_OK;
+}
+
+}  // namespace b200s
+
+extern "C" {
+
+int b200s_version(void) { return B200S_VERSION; }
+
+int b200s_init(int device, b200s_ctx** out) {
+  if (!out) return B200S_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    tl_err = std::string("b200s_init: no CUDA device (") + cudaGetErrorString(e) +
+             "); the engine has no CPU fallback";
+    return B200S_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    tl_err = "b200s_init: device index out of range";
+    return B200S_ERR_INVALID;
+  }
+  b200s_ctx* c = new (std::nothrow) b200s_ctx();
+  if (!c) return B200S_ERR_NOMEM;
+  c->device = device;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    tl_err = std::string("b200s_init: ") + cudaGetErrorString(e);
+    delete c;
+    return B200S_ERR_CUDA;
+  }
+  *out = c;
+  return B200S_OK;
+}
+
+void b200s_shutdown(b200s_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
+                    &c->alloc_iota,      &c->sort_tmp,         &c->tlp_util,         &c->tlp_cap,
+                    &c->tlp_missing,     &c->tlp_flags,        &c->lvrb_f64,         &c->lvrb_i64,
+                    &c->lvrb_flags,      &c->nrt_node_flags,   &c->nrt_max_numa,     &c->nrt_nz,
+                    &c->nrt_node_res_mask, &c->nrt_zone_res_mask, &c->nrt_avail,     &c->nrt_cost,
+                    &c->netoh_region,    &c->netoh_zone,       &c->netoh_zone_cost,  &c->netoh_region_cost,
+                    &c->feasible_in,     &c->tlp_pod_cpu,      &c->lvrb_req_cpu,     &c->lvrb_req_mem,
+                    &c->nrt_pod_qos,     &c->nrt_pod_flags,    &c->nrt_pod_ninit,    &c->nrt_pod_napp,
+                    &c->nrt_pod_kind,    &c->nrt_pod_req_mask, &c->nrt_pod_req,      &c->netoh_equal,
+                    &c->netoh_dep_off,   &c->netoh_deps,       &c->pod_lo,           &c->pod_hi,
+                    &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
+                    &c->topk_local,      &c->topk_all,         &c->topk_final};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& o : c->out) {
+    o.scores.release();
+    o.feas.release();
+    o.reasons.release();
+  }
+  for (auto& v : c->prof_pending)
+    for (auto& pr : v) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* b200s_last_error(b200s_ctx* c) {
+  if (!c) return tl_err.c_str();
+  std::lock_guard<std::mutex> lk(c->mu);
+  tl_err = c->err;
+  return tl_err.c_str();
+}
+
+void* b200s_stream(b200s_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int b200s_sync(b200s_ctx* c) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200S_OK;
+}
+
+uint64_t b200s_launch_count(b200s_ctx* c) { return c ? c->launches : 0; }
+
+int32_t b200s_npad(b200s_ctx* c) { return c ? c->Npad : 0; }
+
+int b200s_set_profiling(b200s_ctx* c, int on) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->profiling = on != 0;
+  return B200S_OK;
+}
+
+int b200s_kernel_time(b200s_ctx* c, b200s_plugin plugin, double* total_ms, uint64_t* launches) {
+  if (!c || (int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT || !total_ms || !launches) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  double ms = 0;
+  uint64_t n = 0;
+  for (auto& pr : c->prof_pending[plugin]) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) {
+      ms += t;
+      n++;
+    }
+    c->prof_pool.push_back(pr.first);
+    c->prof_pool.push_back(pr.second);
+  }
+  c->prof_pending[plugin].clear();
+  *total_ms = ms;
+  *launches = n;
+  return B200S_OK;
+}
+
+void* b200s_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void b200s_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- snapshot
+int b200s_snapshot_begin(b200s_ctx* c, uint64_t generation, int32_t n_nodes, int32_t node_offset,
+                         int32_t n_nodes_global) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (n_nodes < 0 || node_offset < 0 || n_nodes_global < n_nodes + node_offset)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_begin: bad node counts");
+  c->snap_open = true;
+  c->snap_valid = false;
+  c->pods_valid = false;
+  c->gen = generation;
+  c->N = n_nodes;
+  c->Npad = round_up(n_nodes > 0 ? n_nodes : 1, B200S_NODE_ALIGN);
+  c->node_off = node_offset;
+  c->Nglobal = n_nodes_global;
+  c->has_alloc = c->has_tlp = c->has_lvrb = c->has_nrt = c->has_netoh = false;
+  for (auto& o : c->out) o.valid = false;
+  c->total_valid = c->topk_valid = false;
+  return B200S_OK;
+}
+
+int b200s_snapshot_allocatable(b200s_ctx* c, int32_t n_res, const int64_t* const* alloc) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (n_res < 1 || n_res > 16 || !alloc) return c->set_err(B200S_ERR_INVALID, "snapshot_allocatable: 1..16 resources");
+  B200S_CUDA_TRY(c, c->alloc_cols.ensure((size_t)n_res * c->Npad * 8));
+  for (int r = 0; r < n_res; ++r) {
+    if (!alloc[r]) return c->set_err(B200S_ERR_INVALID, "snapshot_allocatable: null column");
+    B200S_TRY(upload_col<int64_t>(c, c->alloc_cols, (size_t)r * c->Npad, alloc[r], c->N, c->Npad));
+  }
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->alloc_R = n_res;
+  c->has_alloc = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_tlp(b200s_ctx* c, const double* util, const int64_t* cap, const int64_t* missing,
+                       const uint8_t* flags) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!util || !cap || !missing || !flags) return c->set_err(B200S_ERR_INVALID, "snapshot_tlp: null column");
+  B200S_CUDA_TRY(c, c->tlp_util.ensure((size_t)c->Npad * 8));
+  B200S_CUDA_TRY(c, c->tlp_cap.ensure((size_t)c->Npad * 8));
+  B200S_CUDA_TRY(c, c->tlp_missing.ensure((size_t)c->Npad * 8));
+  B200S_CUDA_TRY(c, c->tlp_flags.ensure((size_t)c->Npad));
+  B200S_TRY(upload_col<double>(c, c->tlp_util, 0, util, c->N, c->Npad));
+  B200S_TRY(upload_col<int64_t>(c, c->tlp_cap, 0, cap, c->N, c->Npad));
+  B200S_TRY(upload_col<int64_t>(c, c->tlp_missing, 0, missing, c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->tlp_flags, 0, flags, c->N, c->Npad));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->has_tlp = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_lvrb(b200s_ctx* c, const double* cpu_avg, const double* cpu_std, const double* mem_avg,
+                        const double* mem_std, const int64_t* alloc_cpu, const int64_t* alloc_mem,
+                        const uint8_t* flags) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!cpu_avg || !cpu_std || !mem_avg || !mem_std || !alloc_cpu || !alloc_mem || !flags)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_lvrb: null column");
+  size_t np = c->Npad;
+  B200S_CUDA_TRY(c, c->lvrb_f64.ensure(4 * np * 8));
+  B200S_CUDA_TRY(c, c->lvrb_i64.ensure(2 * np * 8));
+  B200S_CUDA_TRY(c, c->lvrb_flags.ensure(np));
+  B200S_TRY(upload_col<double>(c, c->lvrb_f64, 0 * np, cpu_avg, c->N, c->Npad));
+  B200S_TRY(upload_col<double>(c, c->lvrb_f64, 1 * np, cpu_std, c->N, c->Npad));
+  B200S_TRY(upload_col<double>(c, c->lvrb_f64, 2 * np, mem_avg, c->N, c->Npad));
+  B200S_TRY(upload_col<double>(c, c->lvrb_f64, 3 * np, mem_std, c->N, c->Npad));
+  B200S_TRY(upload_col<int64_t>(c, c->lvrb_i64, 0 * np, alloc_cpu, c->N, c->Npad));
+  B200S_TRY(upload_col<int64_t>(c, c->lvrb_i64, 1 * np, alloc_mem, c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->lvrb_flags, 0, flags, c->N, c->Npad));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->has_lvrb = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_nrt(b200s_ctx* c, const b200s_nrt_nodes* nn) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!nn) return c->set_err(B200S_ERR_INVALID, "snapshot_nrt: null");
+  int Z = nn->n_zones, R = nn->n_res;
+  if (Z < 1 || Z > B200S_NRT_MAX_ZONES || R < 1 || R > B200S_NRT_MAX_RES)
+    return c->set_err(B200S_ERR_UNSUPPORTED, "snapshot_nrt: zones/resources outside 1..8");
+  if (!nn->res_flags || !nn->node_flags || !nn->max_numa || !nn->n_zones_node || !nn->node_res_mask ||
+      !nn->zone_res_mask || !nn->avail)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_nrt: null column");
+  size_t np = c->Npad;
+  memcpy(c->nrt_res_flags, nn->res_flags, R);
+  B200S_CUDA_TRY(c, c->nrt_node_flags.ensure(np));
+  B200S_CUDA_TRY(c, c->nrt_max_numa.ensure(np * 2));
+  B200S_CUDA_TRY(c, c->nrt_nz.ensure(np));
+  B200S_CUDA_TRY(c, c->nrt_node_res_mask.ensure(np));
+  B200S_CUDA_TRY(c, c->nrt_zone_res_mask.ensure((size_t)Z * np));
+  B200S_CUDA_TRY(c, c->nrt_avail.ensure((size_t)Z * R * np * 8));
+  B200S_TRY(upload_col<uint8_t>(c, c->nrt_node_flags, 0, nn->node_flags, c->N, c->Npad));
+  B200S_TRY(upload_col<uint16_t>(c, c->nrt_max_numa, 0, nn->max_numa, c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->nrt_nz, 0, nn->n_zones_node, c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->nrt_node_res_mask, 0, nn->node_res_mask, c->N, c->Npad));
+  for (int z = 0; z < Z; ++z)
+    B200S_TRY(upload_col<uint8_t>(c, c->nrt_zone_res_mask, (size_t)z * np, nn->zone_res_mask + (size_t)z * c->N,
+                                  c->N, c->Npad));
+  for (int i = 0; i < Z * R; ++i)
+    B200S_TRY(upload_col<int64_t>(c, c->nrt_avail, (size_t)i * np, nn->avail + (size_t)i * c->N, c->N, c->Npad));
+  c->nrt_has_cost = nn->cost != nullptr;
+  if (nn->cost) {
+    B200S_CUDA_TRY(c, c->nrt_cost.ensure((size_t)Z * Z * np * 4));
+    for (int i = 0; i < Z * Z; ++i)
+      B200S_TRY(upload_col<int32_t>(c, c->nrt_cost, (size_t)i * np, nn->cost + (size_t)i * c->N, c->N, c->Npad));
+  }
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->nrt_Z = Z;
+  c->nrt_R = R;
+  c->has_nrt = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_network_overhead(b200s_ctx* c, const uint16_t* region_id, const uint16_t* zone_id,
+                                    int32_t n_names, const int64_t* zone_cost, const int64_t* region_cost) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!region_id || !zone_id || !zone_cost || !region_cost || n_names < 1 || n_names > 4096)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_network_overhead: bad arguments");
+  size_t np = c->Npad, kk = (size_t)n_names * n_names;
+  B200S_CUDA_TRY(c, c->netoh_region.ensure(np * 2));
+  B200S_CUDA_TRY(c, c->netoh_zone.ensure(np * 2));
+  B200S_CUDA_TRY(c, c->netoh_zone_cost.ensure(kk * 8));
+  B200S_CUDA_TRY(c, c->netoh_region_cost.ensure(kk * 8));
+  B200S_TRY(upload_col<uint16_t>(c, c->netoh_region, 0, region_id, c->N, c->Npad));
+  B200S_TRY(upload_col<uint16_t>(c, c->netoh_zone, 0, zone_id, c->N, c->Npad));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_zone_cost.p, zone_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_region_cost.p, region_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->netoh_K = n_names;
+  c->has_netoh = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_commit(b200s_ctx* c) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->snap_open) return c->set_err(B200S_ERR_STATE, "snapshot_commit without begin");
+  c->snap_open = false;
+  c->snap_valid = true;
+  c->snap_serial++;
+  return B200S_OK;
+}
+
+// ---------------------------------------------------------------- plugin args
+int b200s_config_allocatable(b200s_ctx* c, int mode, int32_t n_res, const int64_t* weights) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (n_res < 1 || n_res > 16 || !weights) return c->set_err(B200S_ERR_INVALID, "config_allocatable: 1..16 resources");
+  // validateResources: allocatable.go:53-61 — weights must be positive.
+  for (int r = 0; r < n_res; ++r)
+    if (weights[r] <= 0) return c->set_err(B200S_ERR_INVALID, "resource Weight should be a positive value");
+  c->alloc_mode = mode;
+  c->alloc_cfg_R = n_res;
+  for (int r = 0; r < n_res; ++r) c->alloc_w[r] = weights[r];
+  c->alloc_cfg = true;
+  c->alloc_cfg_gen++;
+  return B200S_OK;
+}
+
+int b200s_config_tlp(b200s_ctx* c, int64_t target) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->tlp_target = target;
+  c->tlp_cfg = true;
+  return B200S_OK;
+}
+
+int b200s_config_lvrb(b200s_ctx* c, double margin, double sens) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->lvrb_margin = margin;
+  c->lvrb_sens = sens;
+  c->lvrb_cfg = true;
+  return B200S_OK;
+}
+
+int b200s_config_nrt(b200s_ctx* c, int strategy, int32_t n_res, const int64_t* weights) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (strategy < 0 || strategy > B200S_NRT_LEAST_NUMA_NODES)
+    return c->set_err(B200S_ERR_INVALID, "illegal scoring strategy found");  // score.go:138
+  if (n_res < 0 || n_res > B200S_NRT_MAX_RES) return c->set_err(B200S_ERR_UNSUPPORTED, "config_nrt: > 8 resources");
+  c->nrt_strategy = strategy;
+  for (int r = 0; r < B200S_NRT_MAX_RES; ++r) c->nrt_w[r] = 1;
+  for (int r = 0; r < n_res; ++r) c->nrt_w[r] = (weights && weights[r] >= 1) ? weights[r] : 1;  // score.go:49-60
+  c->nrt_cfg = true;
+  return B200S_OK;
+}
+
+// ---------------------------------------------------------------- pods
+static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
+  if (!c->snap_valid) return c->set_err(B200S_ERR_STATE, "pods_upload: no committed snapshot");
+  if (!b || b->n_pods < 0) return c->set_err(B200S_ERR_INVALID, "pods_upload: bad batch");
+  int P = b->n_pods;
+  c->pods_valid = false;
+  c->P = P;
+  size_t words = (size_t)(c->Npad / 64);
+  c->has_feasible = b->feasible != nullptr;
+  if (b->feasible && P > 0) {
+    B200S_CUDA_TRY(c, c->feasible_in.ensure((size_t)P * words * 8));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->feasible_in.p, b->feasible, (size_t)P * words * 8,
+                                      cudaMemcpyHostToDevice, c->stream));
+  }
+  c->has_tlp_pods = b->tlp_pod_cpu_milli != nullptr;
+  if (c->has_tlp_pods && P > 0) {
+    B200S_CUDA_TRY(c, c->tlp_pod_cpu.ensure((size_t)P * 8));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->tlp_pod_cpu.p, b->tlp_pod_cpu_milli, (size_t)P * 8,
+                                      cudaMemcpyHostToDevice, c->stream));
+  }
+  c->has_lvrb_pods = b->lvrb_req_cpu_milli && b->lvrb_req_mem_bytes;
+  if (c->has_lvrb_pods && P > 0) {
+    B200S_CUDA_TRY(c, c->lvrb_req_cpu.ensure((size_t)P * 8));
+    B200S_CUDA_TRY(c, c->lvrb_req_mem.ensure((size_t)P * 8));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->lvrb_req_cpu.p, b->lvrb_req_cpu_milli, (size_t)P * 8,
+                                      cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->lvrb_req_mem.p, b->lvrb_req_mem_bytes, (size_t)P * 8,
+                                      cudaMemcpyHostToDevice, c->stream));
+  }
+  c->has_nrt_pods = b->nrt != nullptr;
+  if (b->nrt && P > 0) {
+    const b200s_nrt_pods* q = b->nrt;
+    if (!c->has_nrt) return c->set_err(B200S_ERR_STATE, "pods_upload: NRT pods without NRT snapshot columns");
+    if (!q->qos || !q->flags || !q->n_init || !q->n_app || !q->cont_kind || !q->req_mask || !q->req)
+      return c->set_err(B200S_ERR_INVALID, "pods_upload: null NRT pod column");
+    const int C = B200S_NRT_MAX_CONT, R = c->nrt_R;
+    struct {
+      DevBuf* d;
+      const void* s;
+      size_t bytes;
+    } cols[] = {{&c->nrt_pod_qos, q->qos, (size_t)P},
+                {&c->nrt_pod_flags, q->flags, (size_t)P},
+                {&c->nrt_pod_ninit, q->n_init, (size_t)P},
+                {&c->nrt_pod_napp, q->n_app, (size_t)P},
+                {&c->nrt_pod_kind, q->cont_kind, (size_t)P * C},
+                {&c->nrt_pod_req_mask, q->req_mask, (size_t)P * (C + 1)},
+                {&c->nrt_pod_req, q->req, (size_t)P * (C + 1) * R * 8}};
+    for (auto& col : cols) {
+      B200S_CUDA_TRY(c, col.d->ensure(col.bytes));
+      B200S_CUDA_TRY(c, cudaMemcpyAsync(col.d->p, col.s, col.bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  c->has_netoh_pods = b->netoh != nullptr;
+  if (b->netoh && P > 0) {
+    const b200s_netoh_pods* q = b->netoh;
+    if (!q->score_equally || !q->dep_offset) return c->set_err(B200S_ERR_INVALID, "pods_upload: null NetworkOverhead column");
+    int total = q->dep_offset[P];
+    if (total < 0 || (total > 0 && !q->deps)) return c->set_err(B200S_ERR_INVALID, "pods_upload: bad dependency CSR");
+    B200S_CUDA_TRY(c, c->netoh_equal.ensure((size_t)P));
+    B200S_CUDA_TRY(c, c->netoh_dep_off.ensure((size_t)(P + 1) * 4));
+    B200S_CUDA_TRY(c, c->netoh_deps.ensure((size_t)(total > 0 ? total : 1) * sizeof(b200s_netoh_dep)));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_equal.p, q->score_equally, (size_t)P, cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_dep_off.p, q->dep_offset, (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (total > 0)
+      B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_deps.p, q->deps, (size_t)total * sizeof(b200s_netoh_dep),
+                                        cudaMemcpyHostToDevice, c->stream));
+    c->netoh_total_deps = total;
+  }
+  // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (auto& o : c->out) o.valid = false;
+  c->total_valid = c->topk_valid = false;
+  c->pods_valid = true;
+  return B200S_OK;
+}
+
+int b200s_pods_upload(b200s_ctx* c, const b200s_pod_batch* b) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  return pods_upload_locked(c, b);
+}
+
+// ---------------------------------------------------------------- eval
+static int eval_locked(b200s_ctx* c, b200s_plugin plugin, b200s_out_dtype dtype) {
+  if (!c->snap_valid) return c->set_err(B200S_ERR_STATE, "eval: no committed snapshot");
+  if (!c->pods_valid) return c->set_err(B200S_ERR_STATE, "eval: no pod batch uploaded");
+  if (dtype != B200S_OUT_I64 && dtype != B200S_OUT_U8) return c->set_err(B200S_ERR_INVALID, "eval: bad dtype");
+  switch (plugin) {
+    case B200S_PLUGIN_ALLOCATABLE: return alloc_eval(c, dtype);
+    case B200S_PLUGIN_TLP: return tlp_eval(c, dtype);
+    case B200S_PLUGIN_LVRB: return lvrb_eval(c, dtype);
+    case B200S_PLUGIN_NRT: return nrt_eval(c, dtype);
+    case B200S_PLUGIN_NETWORK_OVERHEAD: return netoh_eval(c, dtype);
+    default: return c->set_err(B200S_ERR_INVALID, "eval: unknown plugin");
+  }
+}
+
+int b200s_eval(b200s_ctx* c, b200s_plugin plugin, b200s_out_dtype dtype) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  return eval_locked(c, plugin, dtype);
+}
+
+static int fetch(b200s_ctx* c, const DevBuf& src, void* out, size_t bytes, size_t want, const char* what) {
+  if (!out) return c->set_err(B200S_ERR_INVALID, std::string(what) + ": null output");
+  if (bytes < want) return c->set_err(B200S_ERR_INVALID, std::string(what) + ": output buffer too small");
+  if (want == 0) return B200S_OK;
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(out, src.p, want, cudaMemcpyDeviceToHost, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return B200S_OK;
+}
+
+static int fetch_scores_locked(b200s_ctx* c, b200s_plugin plugin, void* out, size_t bytes) {
+  if ((int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT) return c->set_err(B200S_ERR_INVALID, "fetch: unknown plugin");
+  PluginOut& o = c->out[plugin];
+  if (!o.valid) return c->set_err(B200S_ERR_STATE, "fetch_scores: plugin not evaluated");
+  size_t want = (size_t)o.P * c->Npad * (o.dtype == B200S_OUT_I64 ? 8 : 1);
+  return fetch(c, o.scores, out, bytes, want, "fetch_scores");
+}
+
+int b200s_fetch_scores(b200s_ctx* c, b200s_plugin plugin, void* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  return fetch_scores_locked(c, plugin, out, bytes);
+}
+
+static int fetch_feasible_locked(b200s_ctx* c, b200s_plugin plugin, uint64_t* out, size_t bytes) {
+  if ((int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT) return c->set_err(B200S_ERR_INVALID, "fetch: unknown plugin");
+  PluginOut& o = c->out[plugin];
+  if (!o.valid || !o.has_feas) return c->set_err(B200S_ERR_STATE, "fetch_feasible: no feasibility words for plugin");
+  return fetch(c, o.feas, out, bytes, (size_t)o.P * (c->Npad / 64) * 8, "fetch_feasible");
+}
+
+int b200s_fetch_feasible(b200s_ctx* c, b200s_plugin plugin, uint64_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  return fetch_feasible_locked(c, plugin, out, bytes);
+}
+
+static int fetch_reasons_locked(b200s_ctx* c, b200s_plugin plugin, uint8_t* out, size_t bytes) {
+  if ((int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT) return c->set_err(B200S_ERR_INVALID, "fetch: unknown plugin");
+  PluginOut& o = c->out[plugin];
+  if (!o.valid || !o.has_reasons) return c->set_err(B200S_ERR_STATE, "fetch_reasons: no reason codes for plugin");
+  return fetch(c, o.reasons, out, bytes, (size_t)o.P * c->Npad, "fetch_reasons");
+}
+
+int b200s_fetch_reasons(b200s_ctx* c, b200s_plugin plugin, uint8_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  return fetch_reasons_locked(c, plugin, out, bytes);
+}
+
+void* b200s_device_scores(b200s_ctx* c, b200s_plugin plugin) {
+  if (!c || (int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT || !c->out[plugin].valid) return nullptr;
+  return c->out[plugin].scores.p;
+}
+uint64_t* b200s_device_feasible(b200s_ctx* c, b200s_plugin plugin) {
+  if (!c || (int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT || !c->out[plugin].valid || !c->out[plugin].has_feas)
+    return nullptr;
+  return c->out[plugin].feas.as<uint64_t>();
+}
+
+int b200s_eval_combined(b200s_ctx* c, uint32_t plugin_mask, const int64_t* weights, int32_t k, int write_total) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->snap_valid) return c->set_err(B200S_ERR_STATE, "eval_combined: no committed snapshot");
+  if (!c->pods_valid) return c->set_err(B200S_ERR_STATE, "eval_combined: no pod batch uploaded");
+  return combined_eval(c, plugin_mask, weights, k, write_total);
+}
+
+int b200s_fetch_topk(b200s_ctx* c, b200s_topk_entry* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->topk_valid) return c->set_err(B200S_ERR_STATE, "fetch_topk: eval_combined not run");
+  return fetch(c, c->topk_final, out, bytes, (size_t)c->P * c->topk_k * sizeof(b200s_topk_entry), "fetch_topk");
+}
+
+int b200s_fetch_total(b200s_ctx* c, int64_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->total_valid) return c->set_err(B200S_ERR_STATE, "fetch_total: total matrix not written");
+  return fetch(c, c->total, out, bytes, (size_t)c->P * c->Npad * 8, "fetch_total");
+}
+
+int b200s_fetch_total_feasible(b200s_ctx* c, uint64_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->topk_valid) return c->set_err(B200S_ERR_STATE, "fetch_total_feasible: eval_combined not run");
+  return fetch(c, c->total_feas, out, bytes, (size_t)c->P * (c->Npad / 64) * 8, "fetch_total_feasible");
+}
+
+int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,
+                      void* scores_out, uint64_t* feasible_out, uint8_t* reasons_out) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(pods_upload_locked(c, batch));
+  B200S_TRY(eval_locked(c, plugin, dtype));
+  size_t elems = (size_t)c->P * c->Npad;
+  B200S_TRY(fetch_scores_locked(c, plugin, scores_out, elems * (dtype == B200S_OUT_I64 ? 8 : 1)));
+  if (feasible_out && c->out[plugin].has_feas)
+    B200S_TRY(fetch_feasible_locked(c, plugin, feasible_out, (size_t)c->P * (c->Npad / 64) * 8));
+  if (reasons_out && c->out[plugin].has_reasons) B200S_TRY(fetch_reasons_locked(c, plugin, reasons_out, elems));
+  return B200S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// Engine context of libb200sched (internal; the public surface is include/b200sched.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200s {
+
+// Grow-only device buffer: a scheduling cycle re-uses the previous cycle's allocation.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;  // slack so a slightly larger next cycle does not realloc
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct PluginOut {
+  DevBuf scores;   // [P][Npad] int64 or u8
+  DevBuf feas;     // [P][Npad/64] u64 (own filter AND upstream mask)
+  DevBuf reasons;  // [P][Npad] u8 (filter plugins)
+  int dtype = 0;
+  int P = 0;
+  bool valid = false;
+  bool has_feas = false;
+  bool has_reasons = false;
+};
+
+// Per-pod normalisation parameters of NormalizeScore (allocatable.go:143, networkoverhead.go:389)
+struct alignas(16) NormParam {
+  int64_t lo;      // min over the feasible set
+  int64_t range;   // hi - lo (wrapping, as Go computes it)
+  uint32_t magic;  // fast path: floor(2^(32+shift)/range) (or 2^32-1 for powers of two)
+  uint32_t shift;  // fast path: floor(log2(range))
+  uint32_t mode;   // 0: all zero (range == 0 or empty set); 1: 32-bit fast path; 2: generic int64 path
+  uint32_t pad;
+};
+
+struct Comm;  // NCCL communicator wrapper (comm.cu)
+
+}  // namespace b200s
+
+struct b200s_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  uint64_t launches = 0;
+  b200s::Comm* comm = nullptr;
+
+  // ---- snapshot ----
+  bool snap_open = false, snap_valid = false;
+  uint64_t gen = 0;
+  int N = 0, Npad = 0, node_off = 0, Nglobal = 0;
+
+  // NodeResourcesAllocatable
+  bool has_alloc = false;
+  int alloc_R = 0;
+  b200s::DevBuf alloc_cols;  // [R][Npad] int64
+  bool alloc_cfg = false;
+  int alloc_mode = 0;
+  int alloc_cfg_R = 0;
+  int64_t alloc_w[16] = {0};
+  uint64_t alloc_cfg_gen = 0;        // bumped on every config change
+  uint64_t alloc_prepared_key = ~0ull;  // (snapshot gen, cfg gen) the raw/sorted arrays belong to
+  b200s::DevBuf alloc_raw;         // [Npad] int64   raw score (pod independent, allocatable.go:117-127)
+  b200s::DevBuf alloc_sorted_raw;  // [N] int64      raw sorted ascending
+  b200s::DevBuf alloc_order;       // [N] int32      node index of sorted position
+  b200s::DevBuf alloc_iota;        // [N] int32
+  b200s::DevBuf sort_tmp;
+  uint64_t snap_serial = 0;        // bumped on every commit
+
+  // TargetLoadPacking
+  bool has_tlp = false;
+  b200s::DevBuf tlp_util, tlp_cap, tlp_missing, tlp_flags;
+  bool tlp_cfg = false;
+  int64_t tlp_target = 40;
+
+  // LoadVariationRiskBalancing
+  bool has_lvrb = false;
+  b200s::DevBuf lvrb_f64;  // [4][Npad] cpuAvg cpuStd memAvg memStd
+  b200s::DevBuf lvrb_i64;  // [2][Npad] allocCpuMilli allocMemBytes
+  b200s::DevBuf lvrb_flags;
+  bool lvrb_cfg = false;
+  double lvrb_margin = 1.0, lvrb_sens = 1.0;
+
+  // NodeResourceTopologyMatch
+  bool has_nrt = false;
+  int nrt_Z = 0, nrt_R = 0;
+  bool nrt_has_cost = false;
+  uint8_t nrt_res_flags[B200S_NRT_MAX_RES] = {0};
+  b200s::DevBuf nrt_node_flags, nrt_max_numa, nrt_nz, nrt_node_res_mask, nrt_zone_res_mask, nrt_avail,
+      nrt_cost;
+  bool nrt_cfg = false;
+  int nrt_strategy = B200S_NRT_LEAST_ALLOCATED;
+  int64_t nrt_w[B200S_NRT_MAX_RES] = {1, 1, 1, 1, 1, 1, 1, 1};
+
+  // NetworkOverhead
+  bool has_netoh = false;
+  int netoh_K = 0;
+  b200s::DevBuf netoh_region, netoh_zone, netoh_zone_cost, netoh_region_cost;
+
+  // ---- pods ----
+  bool pods_valid = false;
+  int P = 0;
+  bool has_feasible = false;
+  b200s::DevBuf feasible_in;  // [P][Npad/64]
+  bool has_tlp_pods = false, has_lvrb_pods = false, has_nrt_pods = false, has_netoh_pods = false;
+  b200s::DevBuf tlp_pod_cpu, lvrb_req_cpu, lvrb_req_mem;
+  b200s::DevBuf nrt_pod_qos, nrt_pod_flags, nrt_pod_ninit, nrt_pod_napp, nrt_pod_kind, nrt_pod_req_mask,
+      nrt_pod_req;
+  b200s::DevBuf netoh_equal, netoh_dep_off, netoh_deps;
+  int netoh_total_deps = 0;
+
+  // ---- per-pod scratch ----
+  b200s::DevBuf pod_lo, pod_hi;  // [P] int64
+  b200s::DevBuf norm_params;     // [P] NormParam
+  b200s::DevBuf raw_scores;      // [P][Npad] int64 scratch (NetworkOverhead raw cost)
+
+  // ---- outputs ----
+  b200s::PluginOut out[B200S_PLUGIN_COUNT];
+  b200s::DevBuf total;       // [P][Npad] int64
+  b200s::DevBuf total_feas;  // [P][Npad/64]
+  b200s::DevBuf topk_local;  // [P][k] entries of this shard
+  b200s::DevBuf topk_all;    // [world][P][k]
+  b200s::DevBuf topk_final;  // [P][k]
+  int topk_k = 0;
+  bool total_valid = false, topk_valid = false;
+
+  // ---- harness profiling: event pairs around the dominant kernel of each eval ----
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending[B200S_PLUGIN_COUNT];
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_get() {
+    cudaEvent_t e = nullptr;
+    if (!prof_pool.empty()) {
+      e = prof_pool.back();
+      prof_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+
+  int set_err(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+};
+
+namespace b200s {
+
+#define B200S_CUDA_TRY(ctx, expr)                                                               \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return (ctx)->set_err(B200S_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define B200S_TRY(expr)     \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc != B200S_OK) return _rc; \
+  } while (0)
+
+// per-plugin launchers (each in its own .cu)
+int alloc_eval(b200s_ctx* c, int dtype);
+int tlp_eval(b200s_ctx* c, int dtype);
+int lvrb_eval(b200s_ctx* c, int dtype);
+int nrt_eval(b200s_ctx* c, int dtype);
+int netoh_eval(b200s_ctx* c, int dtype);
+int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
+
+// comm.cu
+int comm_allreduce_minmax(b200s_ctx* c, int64_t* lo, int64_t* hi, int count);  // in place, device
+int comm_allgather(b200s_ctx* c, const void* send, void* recv, size_t bytes_per_rank);
+int comm_rank(b200s_ctx* c);
+int comm_world(b200s_ctx* c);
+void comm_destroy(b200s_ctx* c);
+
+// shared small kernels (norm.cu)
+int build_norm_params(b200s_ctx* c, int P);  // pod_lo/pod_hi -> norm_params
+
+int ensure_out(b200s_ctx* c, int plugin, int dtype, bool feas, bool reasons);
+
+// Brackets the dominant kernel of an eval with events when profiling is on.
+struct KernelTimer {
+  b200s_ctx* c;
+  int plugin;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(b200s_ctx* ctx, int pl) : c(ctx), plugin(pl) {
+    if (c->profiling) {
+      e0 = c->prof_get();
+      e1 = c->prof_get();
+      cudaEventRecord(e0, c->stream);
+    }
+  }
+  ~KernelTimer() {
+    if (e0) {
+      cudaEventRecord(e1, c->stream);
+      c->prof_pending[plugin].push_back({e0, e1});
+    }
+  }
+};
+
+}  // namespace b200s

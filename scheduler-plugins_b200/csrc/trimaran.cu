@@ -1,0 +1,253 @@
+// Trimaran: TargetLoadPacking.Score and LoadVariationRiskBalancing.Score, all pods x all nodes.
+//
+// Reference semantics: float64 end to end, never fused (Go/amd64), result int64 via math.Round
+//   TLP   pkg/trimaran/targetloadpacking/targetloadpacking.go:107-187
+//   LVRB  pkg/trimaran/loadvariationriskbalancing/loadvariationriskbalancing.go:84-122,
+//         analysis.go:34-60, pkg/trimaran/resourcestats.go:45-86
+// The translation unit is compiled with -fmad=false so that a*b+c stays two roundings, and uses
+// IEEE division (nvcc default -prec-div=true) — scores are bit-identical to the Go path.
+//
+// B200 design: the node-only sub-expressions are hoisted out of the P x N loop and live in
+// registers for the whole pod tile (TLP: util%/100*cap and float(missing); LVRB: clamped
+// usedAvg, capacity and the complete sigma term incl. Pow — sigma does not depend on the pod).
+// Per eval what remains is one (TLP) or two (LVRB) fp64 divisions plus compares; the only HBM
+// traffic is the streaming store of the score matrix.
+#include <math_constants.h>
+
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+// Go float64 -> int64 (CVTTSD2SI): NaN / out of range -> MinInt64.
+__device__ __forceinline__ int64_t go_f2i(double x) {
+  if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
+  return (int64_t)x;
+}
+// math.Round: half away from zero.  floor + exact remainder test (Sterbenz) instead of libdevice round().
+__device__ __forceinline__ double go_round(double x) {
+  double a = fabs(x);
+  if (!(a < 4503599627370496.0)) return x;  // already integral, Inf or NaN
+  double f = floor(a);
+  if (a - f >= 0.5) f += 1.0;
+  return copysign(f, x);
+}
+// Go builtin min/max: NaN-propagating (signed zeros cannot change a rounded score).
+__device__ __forceinline__ double go_min(double a, double b) {
+  if (a != a || b != b) return CUDART_NAN;
+  return a < b ? a : b;
+}
+__device__ __forceinline__ double go_max(double a, double b) {
+  if (a != a || b != b) return CUDART_NAN;
+  return a > b ? a : b;
+}
+// math.Pow as Go resolves it for the exponents 1/sensitivity (special cases first; see oracle).
+__device__ double go_pow(double x, double y) {
+  if (y == 0 || x == 1) return 1;
+  if (y == 1) return x;
+  if (x != x || y != y) return CUDART_NAN;
+  if (isinf(y) && x != 0) {
+    if (x == -1) return 1;
+    if ((fabs(x) < 1) == (y > 0)) return 0;
+    return CUDART_INF;
+  }
+  if (y == 0.5 && !isinf(x) && x != 0) return sqrt(x);
+  if (y == -0.5 && !isinf(x) && x != 0) return 1 / sqrt(x);
+  return pow(x, y);  // general exponent: <= 2 ulp from Go's software Pow; tolerance rule SURVEY §8c(ii)
+}
+
+template <class OutT, int NPT, int PT>
+__global__ void __launch_bounds__(256)
+tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, const int64_t* __restrict__ missing,
+           const uint8_t* __restrict__ flags, const int64_t* __restrict__ pod_cpu, int64_t target, int N, int Npad,
+           int P, OutT* __restrict__ out) {
+  constexpr int CHUNK = 256 * NPT;
+  __shared__ double s_pod[PT];
+  const int nb = blockIdx.x * CHUNK + threadIdx.x * NPT;
+  const int p0 = blockIdx.y * PT;
+  for (int i = threadIdx.x; i < PT; i += 256)
+    if (p0 + i < P) s_pod[i] = (double)pod_cpu[p0 + i];
+  double ncap[NPT], base[NPT], miss[NPT];
+  uint32_t ok = 0;
+  if (nb < Npad) {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      int n = nb + j;
+      ncap[j] = (double)cap[n];
+      base[j] = (util[n] / 100) * ncap[j];  // nodeCPUUtilMillis, :147
+      miss[j] = (double)missing[n];
+      uint8_t f = flags[n];
+      if (n < N && (f & B200S_TLP_HAS_METRICS) && (f & B200S_TLP_CPU_FOUND)) ok |= 1u << j;
+    }
+  }
+  __syncthreads();
+  if (nb >= Npad) return;
+  const double t = (double)target;
+  const double hundred_minus_t = 100 - t;
+  const int pend = min(PT, P - p0);
+  OutT* orow = out + (size_t)p0 * Npad + nb;
+  for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+    const double pc = s_pod[pp];
+    int64_t q[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      double predicted = 0;
+      if (ncap[j] != 0) predicted = 100 * (base[j] + pc + miss[j]) / ncap[j];  // :170-173
+      double s;
+      if (predicted > t) {
+        s = predicted > 100 ? 0.0 : go_round(t * (100 - predicted) / hundred_minus_t);  // :174-181
+      } else {
+        s = go_round(hundred_minus_t * predicted / t + t);  // :183-184
+      }
+      q[j] = ((ok >> j) & 1u) ? go_f2i(s) : 0;
+    }
+    Store<OutT, NPT>::put64(orow, q);
+  }
+}
+
+struct LvrbNode {
+  double avg, cap, sigma;  // clamped usedAvg, capacity, final sigma (after Pow, margin, clamp)
+};
+
+// Node-only part of computeScore (analysis.go:34-54) for one resource.
+__device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, double cap, double margin,
+                                              double sens) {
+  LvrbNode r;
+  r.cap = cap;
+  double used_avg = util_avg * cap / 100;  // resourcestats.go:68
+  double used_std = util_std * cap / 100;  // :69
+  r.avg = go_max(go_min(used_avg, cap), 0);
+  used_std = go_max(go_min(used_std, cap), 0);
+  double sigma = 0;
+  if (cap > 0) {
+    sigma = used_std / cap;
+    sigma = go_max(go_min(sigma, 1), 0);
+    if (sens >= 0) sigma = go_pow(sigma, 1 / sens);
+    sigma *= margin;
+    sigma = go_max(go_min(sigma, 1), 0);
+  }
+  r.sigma = sigma;
+  return r;
+}
+
+__device__ __forceinline__ double lvrb_res_score(const LvrbNode& nd, double req) {
+  if (nd.cap <= 0) return 0;  // analysis.go:35-38
+  double mu = (nd.avg + req) / nd.cap;
+  mu = go_max(go_min(mu, 1), 0);
+  double risk = (mu + nd.sigma) / 2;
+  return (1. - risk) * 100.0;
+}
+
+template <class OutT, int NPT, int PT>
+__global__ void __launch_bounds__(256)
+lvrb_kernel(const double* __restrict__ f64, const int64_t* __restrict__ i64, const uint8_t* __restrict__ flags,
+            const int64_t* __restrict__ req_cpu, const int64_t* __restrict__ req_mem, double margin, double sens,
+            int N, int Npad, int P, OutT* __restrict__ out) {
+  constexpr int CHUNK = 256 * NPT;
+  constexpr double MEGA = 1. / 1024. / 1024.;  // resourcestats.go:29
+  __shared__ double s_cpu[PT], s_mem[PT];
+  const int nb = blockIdx.x * CHUNK + threadIdx.x * NPT;
+  const int p0 = blockIdx.y * PT;
+  for (int i = threadIdx.x; i < PT; i += 256)
+    if (p0 + i < P) {
+      s_cpu[i] = go_max((double)req_cpu[p0 + i], 0);         // analysis.go:41 on resourcestats.go:60
+      s_mem[i] = go_max((double)req_mem[p0 + i] * MEGA, 0);  // resourcestats.go:64
+    }
+  LvrbNode cpu[NPT], mem[NPT];
+  uint32_t fl[NPT];
+  if (nb < Npad) {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      int n = nb + j;
+      cpu[j] = lvrb_node(f64[n], f64[(size_t)Npad + n], (double)i64[n], margin, sens);
+      double mcap = (double)i64[(size_t)Npad + n];
+      mcap *= MEGA;  // resourcestats.go:62-63
+      mem[j] = lvrb_node(f64[2 * (size_t)Npad + n], f64[3 * (size_t)Npad + n], mcap, margin, sens);
+      fl[j] = n < N ? flags[n] : 0;
+    }
+  }
+  __syncthreads();
+  if (nb >= Npad) return;
+  const int pend = min(PT, P - p0);
+  OutT* orow = out + (size_t)p0 * Npad + nb;
+  for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+    const double rc = s_cpu[pp], rm = s_mem[pp];
+    int64_t q[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const bool cpu_ok = fl[j] & B200S_LVRB_CPU_OK, mem_ok = fl[j] & B200S_LVRB_MEM_OK;
+      double cs = cpu_ok ? lvrb_res_score(cpu[j], rc) : 0.0;
+      double ms = mem_ok ? lvrb_res_score(mem[j], rm) : 0.0;
+      double total = (mem_ok && cpu_ok) ? go_min(ms, cs) : go_max(ms, cs);  // :113-118
+      q[j] = (fl[j] & B200S_LVRB_HAS_METRICS) ? go_f2i(go_round(total)) : 0;
+    }
+    Store<OutT, NPT>::put64(orow, q);
+  }
+}
+
+}  // namespace
+
+int tlp_eval(b200s_ctx* c, int dtype) {
+  if (!c->has_tlp) return c->set_err(B200S_ERR_STATE, "TargetLoadPacking: snapshot has no TLP columns");
+  if (!c->has_tlp_pods) return c->set_err(B200S_ERR_STATE, "TargetLoadPacking: pod batch has no tlp_pod_cpu_milli");
+  const int P = c->P, N = c->N, Npad = c->Npad;
+  B200S_TRY(ensure_out(c, B200S_PLUGIN_TLP, dtype, false, false));
+  PluginOut& o = c->out[B200S_PLUGIN_TLP];
+  if (P > 0) {
+    constexpr int PT = 64;
+    KernelTimer kt(c, B200S_PLUGIN_TLP);
+    if (dtype == B200S_OUT_I64) {
+      constexpr int NPT = 2;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+      tlp_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(
+          c->tlp_util.as<double>(), c->tlp_cap.as<int64_t>(), c->tlp_missing.as<int64_t>(),
+          c->tlp_flags.as<uint8_t>(), c->tlp_pod_cpu.as<int64_t>(), c->tlp_target, N, Npad, P,
+          o.scores.as<int64_t>());
+    } else {
+      constexpr int NPT = 4;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+      tlp_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(
+          c->tlp_util.as<double>(), c->tlp_cap.as<int64_t>(), c->tlp_missing.as<int64_t>(),
+          c->tlp_flags.as<uint8_t>(), c->tlp_pod_cpu.as<int64_t>(), c->tlp_target, N, Npad, P,
+          o.scores.as<uint8_t>());
+    }
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  o.valid = true;
+  return B200S_OK;
+}
+
+int lvrb_eval(b200s_ctx* c, int dtype) {
+  if (!c->has_lvrb) return c->set_err(B200S_ERR_STATE, "LoadVariationRiskBalancing: snapshot has no LVRB columns");
+  if (!c->has_lvrb_pods) return c->set_err(B200S_ERR_STATE, "LoadVariationRiskBalancing: pod batch has no lvrb_req_*");
+  const int P = c->P, N = c->N, Npad = c->Npad;
+  B200S_TRY(ensure_out(c, B200S_PLUGIN_LVRB, dtype, false, false));
+  PluginOut& o = c->out[B200S_PLUGIN_LVRB];
+  if (P > 0) {
+    constexpr int PT = 64;
+    KernelTimer kt(c, B200S_PLUGIN_LVRB);
+    if (dtype == B200S_OUT_I64) {
+      constexpr int NPT = 2;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+      lvrb_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(
+          c->lvrb_f64.as<double>(), c->lvrb_i64.as<int64_t>(), c->lvrb_flags.as<uint8_t>(),
+          c->lvrb_req_cpu.as<int64_t>(), c->lvrb_req_mem.as<int64_t>(), c->lvrb_margin, c->lvrb_sens, N, Npad, P,
+          o.scores.as<int64_t>());
+    } else {
+      constexpr int NPT = 4;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+      lvrb_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(
+          c->lvrb_f64.as<double>(), c->lvrb_i64.as<int64_t>(), c->lvrb_flags.as<uint8_t>(),
+          c->lvrb_req_cpu.as<int64_t>(), c->lvrb_req_mem.as<int64_t>(), c->lvrb_margin, c->lvrb_sens, N, Npad, P,
+          o.scores.as<uint8_t>());
+    }
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  o.valid = true;
+  return B200S_OK;
+}
+
+}  // namespace b200s

@@ -1,0 +1,279 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the CPU
+oracle on the same seeded inputs.  Bit-exact for every int64 score and every mask word."""
+import numpy as np
+import pytest
+
+from scheduler_plugins_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+W_DEFAULT = [1 << 20, 1]  # cpu, memory (resource_allocation.go:36)
+
+
+def setup_alloc(eng, E, nodes, mode, weights=W_DEFAULT, extra_cols=()):
+    cols = [nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"], *extra_cols]
+    eng.snapshot_begin(nodes["N"])
+    eng.snapshot_allocatable(cols)
+    eng.snapshot_commit()
+    eng.config_allocatable(mode, weights)
+    return cols
+
+
+@pytest.mark.parametrize("P,N,mode,masked", [
+    (128, 1000, 0, False),   # config c1: 128 x 1000, Least
+    (128, 1000, 0, True),
+    (37, 4097, 1, True),     # ragged: N not a multiple of 128, odd P
+    (257, 513, 1, False),
+    (1, 1, 0, True),         # single node
+    (3, 130, 1, True),
+])
+def test_allocatable_matches_oracle(eng, engine_mod, oracle, P, N, mode, masked):
+    E = engine_mod
+    seed = synth.BASE_SEED + 1 + mode
+    nodes = synth.gen_nodes(seed, N)
+    cols = setup_alloc(eng, E, nodes, mode)
+    feas = synth.gen_feasible_words(seed, P, N, eng.Npad) if masked else None
+    eng.pods_upload(P, feasible=feas)
+    eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_I64)
+    got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE)
+    want = oracle.alloc_batch(cols, W_DEFAULT, mode, P, feas, pitch=eng.Npad)
+    assert np.array_equal(got, want)
+    assert got.min() >= 0 and got.max() <= 100
+    # compact u8 transport carries the same values
+    eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+    got8 = eng.fetch_scores(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+    assert np.array_equal(got8.astype(np.int64), want)
+
+
+def test_allocatable_golden_through_cuda(eng, engine_mod):
+    """The reference's own table (allocatable_test.go:114-221) through the CUDA path."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    E = engine_mod
+    g = json.load(open(os.path.join(GOLDEN, "allocatable.json")))
+    for case in g["cases"]:
+        nodes = case["nodes"]
+        eng.snapshot_begin(len(nodes))
+        eng.snapshot_allocatable([[n[0] for n in nodes], [n[1] for n in nodes]])
+        eng.snapshot_commit()
+        eng.config_allocatable({"Least": 0, "Most": 1}[case["mode"]], case["weights"])
+        eng.pods_upload(1)
+        eng.eval(E.PLUGIN_ALLOCATABLE)
+        got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE)[0, :len(nodes)]
+        assert list(got) == case["expected"], case["name"]
+    for bad in g["invalid_args"]:
+        with pytest.raises(E.B200SError):
+            eng.config_allocatable(0, bad["weights"])
+
+
+def test_allocatable_edge_feasibility(eng, engine_mod, oracle):
+    E = engine_mod
+    N, P = 700, 6
+    nodes = synth.gen_nodes(7, N)
+    cols = setup_alloc(eng, E, nodes, 1)
+    feas_b = np.zeros((P, N), dtype=bool)
+    feas_b[1, :] = True                 # all feasible
+    feas_b[2, 5] = True                 # one feasible node -> range 0 -> score 0
+    feas_b[3, [10, 11]] = True          # two nodes
+    feas_b[4, ::7] = True
+    feas_b[5, N - 1] = feas_b[5, 0] = True
+    # pod 0: nothing feasible
+    feas = E.pack_bits(feas_b, eng.Npad)
+    eng.pods_upload(P, feasible=feas)
+    eng.eval(E.PLUGIN_ALLOCATABLE)
+    got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE)
+    want = oracle.alloc_batch(cols, W_DEFAULT, 1, P, feas, pitch=eng.Npad)
+    assert np.array_equal(got, want)
+    assert not got[0].any() and not got[2].any()
+
+
+def test_allocatable_generic_int64_path(eng, engine_mod, oracle):
+    """Huge weights / wrapping ranges take the exact generic path (Go wraps, allocatable.go:126,163)."""
+    E = engine_mod
+    N, P = 300, 4
+    rng = np.random.default_rng(5)
+    cpu = rng.integers(1, 1 << 40, N).astype(np.int64)
+    mem = rng.integers(1, 1 << 62, N).astype(np.int64)
+    w = [(1 << 40) + 12345, 3]
+    eng.snapshot_begin(N)
+    eng.snapshot_allocatable([cpu, mem])
+    eng.snapshot_commit()
+    for mode in (0, 1):
+        eng.config_allocatable(mode, w)
+        feas = synth.gen_feasible_words(11, P, N, eng.Npad)
+        eng.pods_upload(P, feasible=feas)
+        eng.eval(E.PLUGIN_ALLOCATABLE)
+        got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE)
+        want = oracle.alloc_batch([cpu, mem], w, mode, P, feas, pitch=eng.Npad)
+        assert np.array_equal(got, want)
+
+
+def test_allocatable_three_resources_and_reconfig(eng, engine_mod, oracle):
+    E = engine_mod
+    N, P = 1000, 16
+    nodes = synth.gen_nodes(3, N)
+    w = [1 << 20, 1, 7]
+    cols = setup_alloc(eng, E, nodes, 0, w, extra_cols=[nodes["alloc_ephemeral_bytes"]])
+    eng.pods_upload(P)
+    eng.eval(E.PLUGIN_ALLOCATABLE)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_ALLOCATABLE), oracle.alloc_batch(cols, w, 0, P, pitch=eng.Npad))
+    eng.config_allocatable(1, [5, 1, 1])  # args change without a new snapshot
+    eng.eval(E.PLUGIN_ALLOCATABLE)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_ALLOCATABLE),
+                          oracle.alloc_batch(cols, [5, 1, 1], 1, P, pitch=eng.Npad))
+    with pytest.raises(E.B200SError):  # weights must match the snapshot's resource columns
+        eng.config_allocatable(1, [1, 1])
+        eng.eval(E.PLUGIN_ALLOCATABLE)
+
+
+def test_empty_batch_and_state_errors(eng, engine_mod):
+    E = engine_mod
+    with pytest.raises(E.B200SError):
+        eng.pods_upload(1)  # no snapshot
+    nodes = synth.gen_nodes(1, 10)
+    setup_alloc(eng, E, nodes, 0)
+    with pytest.raises(E.B200SError):
+        eng.eval(E.PLUGIN_ALLOCATABLE)  # no pods
+    eng.pods_upload(0)
+    eng.eval(E.PLUGIN_ALLOCATABLE)
+    assert eng.fetch_scores(E.PLUGIN_ALLOCATABLE).shape == (0, eng.Npad)
+    with pytest.raises(E.B200SError):
+        eng.eval(E.PLUGIN_TLP)  # no TLP columns in this snapshot
+
+
+def trimaran_snapshot(eng, nodes, tri):
+    eng.snapshot_begin(nodes["N"])
+    eng.snapshot_tlp(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"])
+    eng.snapshot_lvrb(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"], nodes["alloc_cpu_milli"],
+                      nodes["alloc_mem_bytes"], tri["lvrb_flags"])
+    eng.snapshot_commit()
+
+
+@pytest.mark.parametrize("P,N,target", [(128, 1000, 40), (33, 2049, 40), (64, 777, 70), (5, 129, 100), (5, 129, 1)])
+def test_tlp_matches_oracle(eng, engine_mod, oracle, P, N, target):
+    E = engine_mod
+    seed = synth.BASE_SEED + 3
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    nodes["cap_cpu_milli"][::97] = 0  # cap == 0 branch (targetloadpacking.go:170)
+    trimaran_snapshot(eng, nodes, tri)
+    eng.config_tlp(target)
+    eng.pods_upload(P, tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"])
+    eng.eval(E.PLUGIN_TLP)
+    got = eng.fetch_scores(E.PLUGIN_TLP)
+    want = oracle.tlp_batch(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"],
+                            pods["tlp_pod_cpu_milli"], target, pitch=eng.Npad)
+    assert np.array_equal(got, want)
+    eng.eval(E.PLUGIN_TLP, E.OUT_U8)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_TLP, E.OUT_U8).astype(np.int64), want)
+
+
+@pytest.mark.parametrize("margin,sens", [(1.0, 1.0), (1.0, 2.0), (2.0, 0.0), (1.0, -1.0), (-1.0, 1.0), (0.5, 2.0)])
+def test_lvrb_matches_oracle(eng, engine_mod, oracle, margin, sens):
+    E = engine_mod
+    P, N = 96, 1537
+    seed = synth.BASE_SEED + 3
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    nodes["alloc_cpu_milli"][::101] = 0  # capacity <= 0 (analysis.go:35)
+    trimaran_snapshot(eng, nodes, tri)
+    eng.config_lvrb(margin, sens)
+    eng.pods_upload(P, lvrb_req_cpu_milli=pods["req_cpu_milli"], lvrb_req_mem_bytes=pods["req_mem_bytes"])
+    eng.eval(E.PLUGIN_LVRB)
+    got = eng.fetch_scores(E.PLUGIN_LVRB)
+    want = oracle.lvrb_batch(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"],
+                             nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"], tri["lvrb_flags"],
+                             pods["req_cpu_milli"], pods["req_mem_bytes"], margin, sens, pitch=eng.Npad)
+    assert np.array_equal(got, want)
+
+
+def test_lvrb_general_pow_tolerance(eng, engine_mod, oracle):
+    """Non-special sensitivities go through pow(): equal, or off by one only at a rounding boundary
+    (SURVEY §8c rule ii) — and reported, never silently accepted."""
+    E = engine_mod
+    P, N = 64, 2000
+    seed = synth.BASE_SEED + 3
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    trimaran_snapshot(eng, nodes, tri)
+    eng.config_lvrb(1.0, 3.0)
+    eng.pods_upload(P, lvrb_req_cpu_milli=pods["req_cpu_milli"], lvrb_req_mem_bytes=pods["req_mem_bytes"])
+    eng.eval(E.PLUGIN_LVRB)
+    got = eng.fetch_scores(E.PLUGIN_LVRB)
+    want = oracle.lvrb_batch(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"],
+                             nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"], tri["lvrb_flags"],
+                             pods["req_cpu_milli"], pods["req_mem_bytes"], 1.0, 3.0, pitch=eng.Npad)
+    diff = np.abs(got - want)
+    assert diff.max() <= 1
+    print(f"general pow: {int((diff != 0).sum())} of {diff.size} scores differ by 1 (boundary cases)")
+    assert (diff != 0).mean() < 1e-6
+
+
+def test_trimaran_golden_through_cuda(eng, engine_mod):
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    E = engine_mod
+    for case in json.load(open(os.path.join(GOLDEN, "tlp.json")))["cases"]:
+        eng.snapshot_begin(1)
+        eng.snapshot_tlp([case["util"]], [case["cap_milli"]], [case["missing_milli"]], [case["flags"]])
+        eng.snapshot_commit()
+        eng.config_tlp(case["target"])
+        eng.pods_upload(1, tlp_pod_cpu_milli=[case["pod_cpu_milli"]])
+        eng.eval(E.PLUGIN_TLP)
+        assert eng.fetch_scores(E.PLUGIN_TLP)[0, 0] == case["expected"], case["name"]
+    g = json.load(open(os.path.join(GOLDEN, "lvrb.json")))["score"]
+    for case in g["cases"]:
+        eng.snapshot_begin(1)
+        eng.snapshot_lvrb([case["cpu_avg"]], [case["cpu_std"]], [case["mem_avg"]], [case["mem_std"]],
+                          [g["alloc_cpu_milli"]], [g["alloc_mem_bytes"]], [case["flags"]])
+        eng.snapshot_commit()
+        eng.config_lvrb(g["margin"], g["sensitivity"])
+        eng.pods_upload(1, lvrb_req_cpu_milli=[case["req_cpu_milli"]], lvrb_req_mem_bytes=[case["req_mem_bytes"]])
+        eng.eval(E.PLUGIN_LVRB)
+        assert eng.fetch_scores(E.PLUGIN_LVRB)[0, 0] == case["expected"], case["name"]
+
+
+def test_full_size_properties_config2(eng, engine_mod, oracle):
+    """BASELINE config 2 at full size (10k pods x 50k nodes, Most + NormalizeScore): the oracle
+    checks a sample of rows bit-exactly, size-independent properties cover the whole matrix."""
+    E = engine_mod
+    import torch
+
+    P, N = 10_000, 50_000
+    seed = synth.BASE_SEED + 2
+    nodes = synth.gen_nodes(seed, N)
+    cols = setup_alloc(eng, E, nodes, 1)
+    feas = synth.gen_feasible_words(seed, P, N, eng.Npad)
+    eng.pods_upload(P, feasible=feas)
+    eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+    got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+    rows = np.r_[0:8, P // 2:P // 2 + 8, P - 8:P]
+    want = oracle.alloc_batch(cols, W_DEFAULT, 1, len(rows), feas[rows], pitch=eng.Npad)
+    assert np.array_equal(got[rows].astype(np.int64), want)
+    # properties over the full matrix: range, infeasible -> 0, every row with >= 2 distinct
+    # feasible raw values reaches both 0 and 100, monotone in raw score
+    assert got.max() <= 100
+    fb = E.unpack_bits(feas[:64], N)
+    g64 = got[:64, :N]
+    assert not g64[~fb].any()
+    raw = np.array([oracle.alloc_score([cols[0][n], cols[1][n]], W_DEFAULT, 1) for n in range(0, N, 97)])
+    sub = g64[:, ::97]
+    order = np.argsort(raw, kind="stable")
+    for p in range(64):
+        f = fb[p, ::97][order]
+        s = sub[p][order][f]
+        assert np.all(np.diff(s.astype(np.int64)) >= 0)
+    assert (got[:, :N].max(axis=1) == 100).all()
+    # i64 layout == u8 layout
+    eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_I64)
+    t = torch.empty(0)  # noqa: F841 (torch is only the device plumbing here)
+    got64 = eng.fetch_scores(E.PLUGIN_ALLOCATABLE, E.OUT_I64)
+    assert np.array_equal(got64[rows], want)
+    # checksum of checksums: both transports agree on the whole matrix
+    assert int(got64.sum()) == int(got.astype(np.int64).sum())
