@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--pods", type=int, default=P_PODS)
     ap.add_argument("--nodes", type=int, default=N_NODES)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip the e2e and CPU legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -272,6 +273,12 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()) / e2e_steps
 
+    if args.kernel_only:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"kernel_only": True, "value": value, "ms_per_step": ms_step}), flush=True)
+        eng.close()
+        return
     ms_e2e8 = e2e_leg(E.OUT_U8, out8)
     chk8 = int(out8[:4].astype(np.int64).sum())
     e2e_i64 = None
