@@ -58,6 +58,26 @@ void orc_lvrb_batch(const double* cpu_avg, const double* cpu_std, const double* 
                     const int64_t* req_cpu, const int64_t* req_mem, int P, double margin, double sens,
                     int64_t* out, int pitch);
 
+/* ---- NetworkOverhead (pkg/networkaware/networkoverhead) ---- */
+#define ORC_NETOH_MISSING INT64_MIN
+typedef struct {
+  int32_t host_node;
+  uint16_t host_region, host_zone;
+  int64_t max_network_cost;
+} orc_netoh_dep;
+typedef struct {
+  int n_names;
+  const int64_t* zone_cost;   /* [K][K] */
+  const int64_t* region_cost; /* [K][K] */
+} orc_netoh_topology;
+void orc_netoh_node(const orc_netoh_topology* t, int node_global, int region, int zone, const orc_netoh_dep* deps,
+                    int n_deps, int64_t* satisfied, int64_t* violated, int64_t* cost_out);
+void orc_netoh_normalize(int64_t* scores, int n);
+void orc_netoh_batch(const orc_netoh_topology* t, const uint16_t* region_id, const uint16_t* zone_id, int N,
+                     int node_offset, const uint8_t* score_equally, const int32_t* dep_offset,
+                     const orc_netoh_dep* deps, int P, const uint64_t* feasible, int words, int64_t* out_scores,
+                     uint64_t* out_feasible, uint8_t* out_reasons, int pitch);
+
 #ifdef __cplusplus
 }
 #endif

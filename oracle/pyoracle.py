@@ -108,3 +108,52 @@ def lvrb_batch(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, 
     lib().orc_lvrb_batch(*[_p(x) for x in f], *[_p(x) for x in i], _p(fl), C.c_int(N), _p(rc), _p(rm), C.c_int(P),
                          C.c_double(margin), C.c_double(sens), _p(out), C.c_int(pitch))
     return out
+
+
+# ---- NetworkOverhead -------------------------------------------------------------------------
+NETOH_DEP_DTYPE = np.dtype([("host_node", "<i4"), ("host_region", "<u2"), ("host_zone", "<u2"),
+                            ("max_network_cost", "<i8")])
+NETOH_MISSING = -(2**63)
+
+
+class _NetohTopo(C.Structure):
+    _fields_ = [("n_names", C.c_int), ("zone_cost", C.c_void_p), ("region_cost", C.c_void_p)]
+
+
+def _topo(zone_cost, region_cost):
+    zc = _c(zone_cost, np.int64); rc = _c(region_cost, np.int64)
+    return _NetohTopo(zc.shape[0], zc.ctypes.data, rc.ctypes.data), (zc, rc)
+
+
+def netoh_node(zone_cost, region_cost, node_global, region, zone, deps):
+    t, keep = _topo(zone_cost, region_cost)
+    d = np.ascontiguousarray(deps, dtype=NETOH_DEP_DTYPE)
+    s, v, c = C.c_int64(), C.c_int64(), C.c_int64()
+    lib().orc_netoh_node(C.byref(t), C.c_int(node_global), C.c_int(region), C.c_int(zone), _p(d) if len(d) else None,
+                         C.c_int(len(d)), C.byref(s), C.byref(v), C.byref(c))
+    return s.value, v.value, c.value
+
+
+def netoh_normalize(scores):
+    s = _c(scores, np.int64).copy()
+    lib().orc_netoh_normalize(_p(s), C.c_int(len(s)))
+    return s
+
+
+def netoh_batch(zone_cost, region_cost, region_id, zone_id, score_equally, dep_offset, deps, feasible_words=None,
+                pitch=None, node_offset=0):
+    t, keep = _topo(zone_cost, region_cost)
+    rid = _c(region_id, np.uint16); zid = _c(zone_id, np.uint16)
+    eq = _c(score_equally, np.uint8); off = _c(dep_offset, np.int32)
+    d = np.ascontiguousarray(deps, dtype=NETOH_DEP_DTYPE)
+    N, P = len(rid), len(eq)
+    pitch = pitch or (N + 127) // 128 * 128
+    fw = None if feasible_words is None else _c(feasible_words, np.uint64)
+    words = 0 if fw is None else fw.shape[1]
+    scores = np.zeros((P, pitch), dtype=np.int64)
+    feas = np.zeros((P, pitch // 64), dtype=np.uint64)
+    reasons = np.zeros((P, pitch), dtype=np.uint8)
+    lib().orc_netoh_batch(C.byref(t), _p(rid), _p(zid), C.c_int(N), C.c_int(node_offset), _p(eq), _p(off),
+                          _p(d) if len(d) else None, C.c_int(P), _p(fw), C.c_int(words), _p(scores), _p(feas),
+                          _p(reasons), C.c_int(pitch))
+    return scores, feas, reasons

@@ -1,0 +1,285 @@
+// NetworkOverhead: PreFilter node loop + Filter + Score + NormalizeScore, all pods x all nodes.
+//
+// Reference semantics (pkg/networkaware/networkoverhead/networkoverhead.go):
+//   per node: (satisfied, violated) = checkMaxNetworkCostRequirements :500-573
+//             cost                  = getAccumulatedCost              :576-638
+//   Filter  : !scoreEqually && violated > satisfied -> Unschedulable   :326-359
+//   Score   : scoreEqually ? 0 : cost                                  :362-386
+//   Normalize over the feasible list: 100 - int64(100.0*float64(s-min)/float64(max-min)) :389-418
+// The reference keeps the per-node cost map in a Go map keyed by (origin,destination) strings and
+// rebuilds (and re-sorts) it for every node; here region/zone labels are dictionary ids and the
+// two cost lists are dense [K][K] int64 matrices with a MISSING sentinel (L2/L1 resident).
+//
+// Kernels: (1) raw pass: cost + own filter -> raw int64 matrix, feasibility words, reason codes;
+//          (2) per-pod min/max over the feasible bits; [NCCL min/max all-reduce when sharded]
+//          (3) normalise pass -> score matrix (int64 or u8).
+// Warp layout of the P x N passes: a warp covers 64 consecutive nodes, lane l owns nodes l and
+// l+32, so the warp's two ballots ARE the 64-bit feasibility word and every store is a fully
+// used 256 B segment.
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+constexpr int64_t MAX_COST = 100;  // :52
+constexpr int64_t SAME_ZONE = 1;   // :58
+
+struct Topo {
+  const int64_t* zc;
+  const int64_t* rc;
+  int K;
+};
+
+__device__ __forceinline__ bool lookup_zone(const Topo& t, int r, int z, int d, int64_t& c) {
+  if (z != 0) {
+    c = __ldg(&t.zc[(size_t)z * t.K + d]);
+    if (c != B200S_NETOH_MISSING) return true;
+    if (r == z) {
+      c = __ldg(&t.rc[(size_t)r * t.K + d]);
+      if (c != B200S_NETOH_MISSING) return true;
+    }
+  }
+  return false;
+}
+__device__ __forceinline__ bool lookup_region(const Topo& t, int r, int z, int d, int64_t& c) {
+  if (r != 0) {
+    if (z == r) {
+      c = __ldg(&t.zc[(size_t)z * t.K + d]);
+      if (c != B200S_NETOH_MISSING) return true;
+    }
+    c = __ldg(&t.rc[(size_t)r * t.K + d]);
+    if (c != B200S_NETOH_MISSING) return true;
+  }
+  return false;
+}
+
+// One (pod, node): the two reference loops fused (same traversal, :500-573 and :576-638).
+__device__ __forceinline__ void eval_node(const Topo& t, int node_global, int r, int z,
+                                          const b200s_netoh_dep* __restrict__ deps, int nd, int64_t& sat,
+                                          int64_t& viol, int64_t& cost) {
+  sat = viol = cost = 0;
+  for (int i = 0; i < nd; ++i) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(deps + i));  // 16 B entry, warp-uniform address
+    const int host = raw.x;
+    const int hr = raw.y & 0xffff, hz = (raw.y >> 16) & 0xffff;
+    const int64_t maxc = (int64_t)(((uint64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z);
+    int64_t c;
+    if (host == node_global) {
+      sat += 1;  // cost += SameHostname (0)
+    } else if (hr == 0 && hz == 0) {
+      viol += 1;
+      cost = wrap_add(cost, MAX_COST);
+    } else if (r == hr) {
+      if (z == hz) {
+        sat += 1;
+        cost = wrap_add(cost, SAME_ZONE);
+      } else if (lookup_zone(t, r, z, hz, c)) {
+        if (c <= maxc) sat += 1; else viol += 1;
+        cost = wrap_add(cost, c);
+      } else {
+        cost = wrap_add(cost, MAX_COST);  // missing: Filter counts neither, Score adds MaxCost
+      }
+    } else if (lookup_region(t, r, z, hr, c)) {
+      if (c <= maxc) sat += 1; else viol += 1;
+      cost = wrap_add(cost, c);
+    } else {
+      cost = wrap_add(cost, MAX_COST);
+    }
+  }
+}
+
+template <int PT>
+__global__ void __launch_bounds__(256)
+netoh_raw_kernel(Topo t, const uint16_t* __restrict__ region, const uint16_t* __restrict__ zone, int node_off,
+                 const uint8_t* __restrict__ equal, const int32_t* __restrict__ dep_off,
+                 const b200s_netoh_dep* __restrict__ deps, const uint64_t* __restrict__ upstream, int words, int N,
+                 int Npad, int P, int64_t* __restrict__ raw, uint64_t* __restrict__ feas_out,
+                 uint8_t* __restrict__ reasons) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbase = (blockIdx.x * 8 + warp) * 64;  // this warp's 64-node group
+  if (nbase >= Npad) return;
+  const int p0 = blockIdx.y * PT;
+  const int pend = min(p0 + PT, P);
+  const int n0 = nbase + lane, n1 = nbase + lane + 32;
+  const int r0 = region[n0], z0 = zone[n0], r1 = region[n1], z1 = zone[n1];
+  const bool v0 = n0 < N, v1 = n1 < N;
+  const int word = nbase >> 6;
+  for (int p = p0; p < pend; ++p) {
+    const bool eq = equal[p] != 0;
+    const int d0 = dep_off[p], nd = dep_off[p + 1] - d0;
+    int64_t s0 = 0, w0 = 0, c0 = 0, s1 = 0, w1 = 0, c1 = 0;
+    if (!eq) {
+      eval_node(t, node_off + n0, r0, z0, deps + d0, nd, s0, w0, c0);
+      eval_node(t, node_off + n1, r1, z1, deps + d0, nd, s1, w1, c1);
+    }
+    const bool pass0 = v0 && (eq || !(w0 > s0)), pass1 = v1 && (eq || !(w1 > s1));
+    uint64_t up = upstream ? upstream[(size_t)p * words + word] : ~0ull;
+    const bool f0 = pass0 && ((up >> lane) & 1ull), f1 = pass1 && ((up >> (lane + 32)) & 1ull);
+    const uint64_t fw = (uint64_t)__ballot_sync(0xffffffffu, f0) | ((uint64_t)__ballot_sync(0xffffffffu, f1) << 32);
+    if (lane == 0) feas_out[(size_t)p * words + word] = fw;
+    int64_t* row = raw + (size_t)p * Npad;
+    row[n0] = f0 ? (eq ? 0 : c0) : 0;
+    row[n1] = f1 ? (eq ? 0 : c1) : 0;
+    if (reasons) {
+      uint8_t* rr = reasons + (size_t)p * Npad;
+      rr[n0] = !v0 ? 0 : (!pass0 ? B200S_REASON_NETOH_VIOLATED : (f0 ? B200S_REASON_OK : B200S_REASON_UPSTREAM));
+      rr[n1] = !v1 ? 0 : (!pass1 ? B200S_REASON_NETOH_VIOLATED : (f1 ? B200S_REASON_OK : B200S_REASON_UPSTREAM));
+    }
+  }
+}
+
+// One CTA per pod: min/max of raw over the feasible bits (getMinMaxScores :421-435).
+__global__ void __launch_bounds__(256)
+row_minmax_kernel(const int64_t* __restrict__ raw, const uint64_t* __restrict__ feas, int words, int Npad,
+                  int64_t* __restrict__ lo, int64_t* __restrict__ hi) {
+  const int p = blockIdx.x;
+  const int64_t* row = raw + (size_t)p * Npad;
+  const uint64_t* fr = feas + (size_t)p * words;
+  int64_t mn = INT64_MAX, mx = INT64_MIN;
+  for (int n = threadIdx.x; n < Npad; n += 256) {
+    if ((fr[n >> 6] >> (n & 63)) & 1ull) {
+      int64_t v = row[n];
+      mn = v < mn ? v : mn;
+      mx = v > mx ? v : mx;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    int64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+  }
+  __shared__ int64_t smn[8], smx[8];
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      mn = smn[i] < mn ? smn[i] : mn;
+      mx = smx[i] > mx ? smx[i] : mx;
+    }
+    lo[p] = mn;
+    hi[p] = mx;
+  }
+}
+
+// mode 0: all 0 (min == max == 0, or nothing feasible)       :400-402
+// mode 1: 100 - floor((s-min)*100/range) with the 32-bit reciprocal (== the float64 formula: for
+//         range*100 < 2^32 the fp64 quotient cannot round across an integer)
+// mode 2: the float64 formula verbatim                        :406-410
+// mode 3: max == min != 0 -> 100 - int64(float64(0)) = 100    :411-413
+__global__ void netoh_params_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, int P,
+                                    NormParam* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  NormParam q;
+  q.lo = lo[p];
+  q.range = wrap_sub(hi[p], lo[p]);
+  q.magic = q.shift = q.pad = 0;
+  if (lo[p] > hi[p] || (lo[p] == 0 && hi[p] == 0)) {
+    q.mode = 0;
+  } else if (lo[p] == hi[p]) {
+    q.mode = 3;
+  } else if (q.range > 0 && q.range <= (int64_t)(0xffffffffu / 100u)) {
+    uint32_t r = (uint32_t)q.range, s = 31 - __clz(r);
+    uint64_t m = ((1ull << 32) << s) / r;
+    q.magic = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
+    q.shift = s;
+    q.mode = 1;
+  } else {
+    q.mode = 2;
+  }
+  out[p] = q;
+}
+
+__device__ __forceinline__ int64_t netoh_norm_one(const NormParam& np, int64_t s) {
+  if (np.mode == 1) {
+    uint32_t n100 = ((uint32_t)(uint64_t)s - (uint32_t)(uint64_t)np.lo) * 100u;
+    uint32_t q0 = __umulhi(n100, np.magic) >> np.shift;
+    uint32_t rem = n100 - q0 * (uint32_t)np.range;
+    q0 += rem >= (uint32_t)np.range ? 1u : 0u;
+    return 100 - (int64_t)q0;
+  }
+  if (np.mode == 0) return 0;
+  if (np.mode == 3) return 100;
+  double norm = 100.0 * (double)wrap_sub(s, np.lo) / (double)np.range;
+  int64_t tr = (norm >= -9223372036854775808.0 && norm < 9223372036854775808.0) ? (int64_t)norm : INT64_MIN;
+  return wrap_sub(100, tr);
+}
+
+template <class OutT, int PT>
+__global__ void __launch_bounds__(256)
+netoh_norm_kernel(const int64_t* __restrict__ raw, const uint64_t* __restrict__ feas, const NormParam* __restrict__ params,
+                  int words, int Npad, int P, OutT* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbase = (blockIdx.x * 8 + warp) * 64;
+  if (nbase >= Npad) return;
+  const int p0 = blockIdx.y * PT, pend = min(p0 + PT, P);
+  const int n0 = nbase + lane, n1 = n0 + 32, word = nbase >> 6;
+  for (int p = p0; p < pend; ++p) {
+    const NormParam np = params[p];
+    const uint64_t fw = feas[(size_t)p * words + word];
+    const int64_t* row = raw + (size_t)p * Npad;
+    int64_t a = ((fw >> lane) & 1ull) ? netoh_norm_one(np, row[n0]) : 0;
+    int64_t b = ((fw >> (lane + 32)) & 1ull) ? netoh_norm_one(np, row[n1]) : 0;
+    OutT* orow = out + (size_t)p * Npad;
+    orow[n0] = (OutT)a;
+    orow[n1] = (OutT)b;
+  }
+}
+
+}  // namespace
+
+int netoh_eval(b200s_ctx* c, int dtype) {
+  if (!c->has_netoh) return c->set_err(B200S_ERR_STATE, "NetworkOverhead: snapshot has no region/zone columns");
+  if (!c->has_netoh_pods) return c->set_err(B200S_ERR_STATE, "NetworkOverhead: pod batch has no dependency lists");
+  const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
+  B200S_TRY(ensure_out(c, B200S_PLUGIN_NETWORK_OVERHEAD, dtype, true, true));
+  PluginOut& o = c->out[B200S_PLUGIN_NETWORK_OVERHEAD];
+  if (P == 0) {
+    o.valid = true;
+    return B200S_OK;
+  }
+  B200S_CUDA_TRY(c, c->raw_scores.ensure((size_t)P * Npad * 8));
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
+  B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
+  B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
+  Topo t{c->netoh_zone_cost.as<int64_t>(), c->netoh_region_cost.as<int64_t>(), c->netoh_K};
+  constexpr int PT = 32;
+  dim3 grid((Npad / 64 + 7) / 8, (P + PT - 1) / PT);
+  {
+    KernelTimer kt(c, B200S_PLUGIN_NETWORK_OVERHEAD);
+    netoh_raw_kernel<PT><<<grid, 256, 0, c->stream>>>(
+        t, c->netoh_region.as<uint16_t>(), c->netoh_zone.as<uint16_t>(), c->node_off, c->netoh_equal.as<uint8_t>(),
+        c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(),
+        c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr, words, N, Npad, P, c->raw_scores.as<int64_t>(),
+        o.feas.as<uint64_t>(), o.reasons.as<uint8_t>());
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  row_minmax_kernel<<<P, 256, 0, c->stream>>>(c->raw_scores.as<int64_t>(), o.feas.as<uint64_t>(), words, Npad,
+                                              c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  B200S_TRY(comm_allreduce_minmax(c, c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P));
+  netoh_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P,
+                                                               c->norm_params.as<NormParam>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  if (dtype == B200S_OUT_I64)
+    netoh_norm_kernel<int64_t, PT><<<grid, 256, 0, c->stream>>>(c->raw_scores.as<int64_t>(), o.feas.as<uint64_t>(),
+                                                                c->norm_params.as<NormParam>(), words, Npad, P,
+                                                                o.scores.as<int64_t>());
+  else
+    netoh_norm_kernel<uint8_t, PT><<<grid, 256, 0, c->stream>>>(c->raw_scores.as<int64_t>(), o.feas.as<uint64_t>(),
+                                                                c->norm_params.as<NormParam>(), words, Npad, P,
+                                                                o.scores.as<uint8_t>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  o.valid = true;
+  return B200S_OK;
+}
+
+}  // namespace b200s

@@ -86,3 +86,49 @@ def gen_feasible_words(seed: int, P: int, N: int, npad: int, k_or: int = 3) -> n
     else:
         m[:, full:] = 0
     return m
+
+
+def gen_netoh(seed: int, N: int, P: int, n_regions: int = 8, zones_per_region: int = 8, n_global: int | None = None,
+              max_deps: int = 8) -> dict:
+    """NetworkOverhead inputs: 3-tier topology (same host 0 / same zone 1 / zone matrix inside a
+    region / region matrix / MaxCost 100), AppGroup dependencies already matched against the
+    placed pods.  Name dictionary: id 0 = empty label, 1..R = regions, R+1.. = zones."""
+    g = _streams(seed)[5]
+    n_global = n_global or N
+    R, Z = n_regions, n_regions * zones_per_region
+    K = 1 + R + Z
+    MISSING = -(2**63)
+    region_cost = np.full((K, K), MISSING, dtype=np.int64)
+    zone_cost = np.full((K, K), MISSING, dtype=np.int64)
+    rc = g.integers(20, 101, size=(R, R))
+    miss = g.random((R, R)) < 0.05
+    for a in range(R):
+        for b in range(R):
+            if a != b and not miss[a, b]:
+                region_cost[1 + a, 1 + b] = rc[a, b]
+    zc = g.integers(2, 20, size=(Z, Z))
+    for a in range(Z):
+        for b in range(Z):
+            if a != b and a // zones_per_region == b // zones_per_region:
+                zone_cost[1 + R + a, 1 + R + b] = zc[a, b]
+    zone_of = g.integers(0, Z, size=n_global)
+    unl = g.random(n_global) < 0.005
+    region_all = np.where(unl, 0, 1 + zone_of // zones_per_region).astype(np.uint16)
+    zone_all = np.where(unl, 0, 1 + R + zone_of).astype(np.uint16)
+    # a few nodes with a zone label but no region label ("same region" incl. the empty string, :540)
+    odd = g.random(n_global) < 0.002
+    region_all = np.where(odd, 0, region_all).astype(np.uint16)
+    score_equally = (g.random(P) < 0.2).astype(np.uint8)
+    nd = np.where(score_equally == 1, 0, g.integers(1, max_deps + 1, size=P))
+    off = np.zeros(P + 1, dtype=np.int32)
+    off[1:] = np.cumsum(nd)
+    total = int(off[-1])
+    deps = np.zeros(total, dtype=[("host_node", "<i4"), ("host_region", "<u2"), ("host_zone", "<u2"),
+                                  ("max_network_cost", "<i8")])
+    hosts = g.integers(0, n_global, size=total)
+    deps["host_node"] = hosts
+    deps["host_region"] = region_all[hosts]
+    deps["host_zone"] = zone_all[hosts]
+    deps["max_network_cost"] = g.choice(np.array([0, 10, 30, 100]), size=total)
+    return dict(K=K, zone_cost=zone_cost, region_cost=region_cost, region_all=region_all, zone_all=zone_all,
+                score_equally=score_equally, dep_offset=off, deps=deps)

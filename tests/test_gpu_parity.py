@@ -277,3 +277,52 @@ def test_full_size_properties_config2(eng, engine_mod, oracle):
     assert np.array_equal(got64[rows], want)
     # checksum of checksums: both transports agree on the whole matrix
     assert int(got64.sum()) == int(got.astype(np.int64).sum())
+
+
+# ---------------------------------------------------------------- NetworkOverhead
+def netoh_setup(eng, E, net, N, node_offset=0, n_global=None):
+    eng.snapshot_begin(N, node_offset=node_offset, n_nodes_global=n_global or (node_offset + N))
+    eng.snapshot_network_overhead(net["region_all"][node_offset:node_offset + N],
+                                  net["zone_all"][node_offset:node_offset + N], net["zone_cost"], net["region_cost"])
+    eng.snapshot_commit()
+
+
+@pytest.mark.parametrize("P,N,masked", [(64, 1000, False), (97, 3001, True), (8, 64, True)])
+def test_network_overhead_matches_oracle(eng, engine_mod, oracle, P, N, masked):
+    E = engine_mod
+    seed = synth.BASE_SEED + 5
+    net = synth.gen_netoh(seed, N, P)
+    netoh_setup(eng, E, net, N)
+    feas = synth.gen_feasible_words(seed, P, N, eng.Npad) if masked else None
+    eng.pods_upload(P, feasible=feas, netoh=net)
+    eng.eval(E.PLUGIN_NETWORK_OVERHEAD)
+    got = eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD)
+    gf = eng.fetch_feasible(E.PLUGIN_NETWORK_OVERHEAD)
+    gr = eng.fetch_reasons(E.PLUGIN_NETWORK_OVERHEAD)
+    ws, wf, wr = oracle.netoh_batch(net["zone_cost"], net["region_cost"], net["region_all"], net["zone_all"],
+                                    net["score_equally"], net["dep_offset"], net["deps"], feas, pitch=eng.Npad)
+    assert np.array_equal(gf, wf)
+    assert np.array_equal(gr, wr)
+    assert np.array_equal(got, ws)
+    assert (gr == 7).any() and (got == 100).any()  # the fixture exercises rejects and best nodes
+    eng.eval(E.PLUGIN_NETWORK_OVERHEAD, E.OUT_U8)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD, E.OUT_U8).astype(np.int64), ws)
+
+
+def test_network_overhead_generic_normalize(eng, engine_mod, oracle):
+    """Huge costs: the float64 NormalizeScore formula verbatim (networkoverhead.go:406-410)."""
+    E = engine_mod
+    P, N = 16, 500
+    net = synth.gen_netoh(99, N, P)
+    zc = net["zone_cost"]
+    zc[zc != -(2**63)] *= 10**9 + 7
+    rc = net["region_cost"]
+    rc[rc != -(2**63)] *= 3 * 10**15 + 1
+    net["deps"]["max_network_cost"] = 2**62
+    netoh_setup(eng, E, net, N)
+    eng.pods_upload(P, netoh=net)
+    eng.eval(E.PLUGIN_NETWORK_OVERHEAD)
+    ws, wf, _ = oracle.netoh_batch(net["zone_cost"], net["region_cost"], net["region_all"], net["zone_all"],
+                                   net["score_equally"], net["dep_offset"], net["deps"], None, pitch=eng.Npad)
+    assert np.array_equal(eng.fetch_feasible(E.PLUGIN_NETWORK_OVERHEAD), wf)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD), ws)
