@@ -78,6 +78,78 @@ void orc_netoh_batch(const orc_netoh_topology* t, const uint16_t* region_id, con
                      const orc_netoh_dep* deps, int P, const uint64_t* feasible, int words, int64_t* out_scores,
                      uint64_t* out_feasible, uint8_t* out_reasons, int pitch);
 
+/* ---- NodeResourceTopologyMatch (pkg/noderesourcetopology) ---- */
+#define ORC_QOS_GUARANTEED 0
+#define ORC_QOS_BURSTABLE 1
+#define ORC_QOS_BEST_EFFORT 2
+#define ORC_NRT_NODE_HAS_NRT 1u
+#define ORC_NRT_NODE_FRESH 2u
+#define ORC_NRT_NODE_SINGLE_NUMA 4u
+#define ORC_NRT_NODE_SCOPE_POD 8u
+#define ORC_NRT_NODE_UNSUPPORTED 16u
+#define ORC_NRT_RES_AFFINE 1u
+#define ORC_NRT_RES_HOST_LEVEL 2u
+#define ORC_NRT_POD_FILTER_BYPASS 1u
+#define ORC_NRT_POD_UNSUPPORTED 2u
+#define ORC_CONT_APP 0
+#define ORC_CONT_INIT 1
+#define ORC_CONT_SIDECAR 2
+#define ORC_NRT_MOST_ALLOCATED 0
+#define ORC_NRT_BALANCED_ALLOCATION 1
+#define ORC_NRT_LEAST_ALLOCATED 2
+#define ORC_NRT_LEAST_NUMA_NODES 3
+#define ORC_REASON_OK 0
+#define ORC_REASON_NRT_INVALID_TOPOLOGY 1
+#define ORC_REASON_NRT_ALIGN_POD 2
+#define ORC_REASON_NRT_ALIGN_CONTAINER 3
+#define ORC_REASON_NRT_ALIGN_INIT 4
+#define ORC_REASON_NRT_ALIGN_SIDECAR 5
+#define ORC_REASON_NRT_ACCOUNTING 6
+#define ORC_REASON_UPSTREAM 8
+#define ORC_REASON_UNSUPPORTED 9
+typedef struct {
+  uint8_t flags;
+  uint16_t max_numa;
+  uint8_t n_zones;
+  uint8_t node_res_mask;
+  uint8_t zone_res_mask[8];
+  int64_t avail[8][8]; /* [zone][resource slot], milli-units */
+  int32_t cost[8][8];  /* -1 = missing */
+} orc_nrt_node;
+typedef struct {
+  uint8_t qos, flags, n_init, n_app;
+  uint8_t cont_kind[8];
+  uint8_t req_mask[9]; /* slot 8 = pod effective request */
+  int64_t req[9][8];
+} orc_nrt_pod;
+/* returns an ORC_REASON_* code (0 = pass) */
+int orc_nrt_filter(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R);
+int64_t orc_nrt_score(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R, int strategy,
+                      const int64_t* weights);
+typedef struct {
+  int32_t n_zones, n_res;
+  const uint8_t* res_flags;     /* [R] */
+  const uint8_t* node_flags;    /* [N] */
+  const uint16_t* max_numa;     /* [N] */
+  const uint8_t* n_zones_node;  /* [N] */
+  const uint8_t* node_res_mask; /* [N] */
+  const uint8_t* zone_res_mask; /* [Z][N] */
+  const int64_t* avail;         /* [Z][R][N] */
+  const int32_t* cost;          /* [Z][Z][N] or NULL */
+} orc_nrt_nodes_soa;
+typedef struct {
+  const uint8_t* qos;
+  const uint8_t* flags;
+  const uint8_t* n_init;
+  const uint8_t* n_app;
+  const uint8_t* cont_kind; /* [P][8] */
+  const uint8_t* req_mask;  /* [P][9] */
+  const int64_t* req;       /* [P][9][R] */
+} orc_nrt_pods_soa;
+void orc_nrt_batch(const orc_nrt_nodes_soa* ns, int N, const orc_nrt_pods_soa* ps, int P, int strategy,
+                   const int64_t* weights, const uint64_t* feasible, int words, int64_t* out_scores,
+                   uint64_t* out_feasible, uint8_t* out_reasons, int pitch);
+
 #ifdef __cplusplus
 }
 #endif
