@@ -1,0 +1,517 @@
+// NodeResourceTopologyMatch: Filter (single-numa-node, pod/container scope) + Score (Least/Most/
+// Balanced/LeastNUMANodes), all pods x all nodes on the dense encoding of include/b200sched.h.
+//
+// Reference semantics (pkg/noderesourcetopology):
+//   Filter   filter.go:176-225, handlers :39-78 / :162-173, resourcesAvailableInAnyNUMANodes :90-160,
+//            isResourceSetSuitable numaresources.go:137-142, subtractResourcesFromNUMANodeList :145-182
+//   Score    score.go:62-102, scoreForEachNUMANode :110-124, pod/container scope :142-165,
+//            least_allocated.go:25-55, most_allocated.go:25-54, balanced_allocation.go:27-54,
+//            least_numa.go:35-233, subtractFromNUMAs numaresources.go:184-215
+// The reference re-parses zone names and deep-copies every Quantity map per (pod,node) call; here
+// a node's zones x resources block (exact milli-units) is loaded ONCE into registers and reused
+// for the whole pod tile.  One thread owns one node; a warp's ballot is half a feasibility word.
+// Kernels are instantiated for the common shapes (<=2 zones x <=4 resources, <=4 x <=4, <=8 x <=8)
+// so the zone/resource loops unroll and the working copy used by the container-scope state
+// machine stays in registers.
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+constexpr int C_MAX = B200S_NRT_MAX_CONT;
+
+// Combination tables for LeastNUMANodes: for n zones, all non-empty subsets ordered by size then
+// lexicographically by index tuple (gonum combin.Combinations order, least_numa.go:161).
+__constant__ uint8_t c_combo_mask[8][255];
+__constant__ uint8_t c_combo_off[8][10];  // [n-1][k] = first index of size-k subsets; [n-1][n+1] = end
+bool g_combo_ready = false;
+
+int ensure_combos() {
+  if (g_combo_ready) return 0;
+  static uint8_t mask[8][255];
+  static uint8_t off[8][10];
+  for (int n = 1; n <= 8; ++n) {
+    int cnt = 0;
+    for (int k = 1; k <= n; ++k) {
+      off[n - 1][k] = (uint8_t)cnt;
+      int idx[8];
+      for (int i = 0; i < k; ++i) idx[i] = i;
+      while (true) {
+        uint8_t m = 0;
+        for (int i = 0; i < k; ++i) m |= (uint8_t)(1u << idx[i]);
+        mask[n - 1][cnt++] = m;
+        int i = k - 1;
+        while (i >= 0 && idx[i] == n - k + i) --i;
+        if (i < 0) break;
+        ++idx[i];
+        for (int j = i + 1; j < k; ++j) idx[j] = idx[j - 1] + 1;
+      }
+    }
+    off[n - 1][n + 1] = (uint8_t)cnt;
+    off[n - 1][0] = 0;
+  }
+  if (cudaMemcpyToSymbol(c_combo_mask, mask, sizeof(mask)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(c_combo_off, off, sizeof(off)) != cudaSuccess) return -1;
+  g_combo_ready = true;
+  return 0;
+}
+
+template <int R>
+struct PodS {  // one pod of the tile, in shared memory
+  int64_t req[C_MAX + 1][R];
+  uint8_t req_mask[C_MAX + 1];
+  uint8_t kind[C_MAX];
+  uint8_t qos, flags, n_init, n_app;
+};
+
+template <int Z, int R>
+struct Zones {
+  int64_t avail[Z][R];
+  uint32_t zmask[Z];
+  int nz;
+};
+
+struct NrtCfg {
+  int strategy;
+  int64_t w[B200S_NRT_MAX_RES];
+  uint8_t res_flags[B200S_NRT_MAX_RES];
+};
+
+__device__ __forceinline__ int64_t qty_value(int64_t milli) { return (milli + 999) / 1000; }  // Quantity.Value(), >= 0
+__device__ __forceinline__ int64_t f2i(double x) {
+  if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
+  return (int64_t)x;
+}
+__device__ __forceinline__ bool suitable(int qos, uint32_t rflags, int64_t qty, int64_t numa_qty) {
+  if (qos != B200S_QOS_GUARANTEED && (rflags & B200S_NRT_RES_AFFINE)) return true;
+  return numa_qty >= qty;
+}
+
+// resourcesAvailableInAnyNUMANodes (filter.go:90-160)
+template <int Z, int R>
+__device__ __forceinline__ bool available_in_any(const Zones<Z, R>& zs, uint32_t node_res_mask, const NrtCfg& cfg,
+                                                 int qos, uint32_t req_mask, const int64_t* req, int& numa_id) {
+  uint32_t bitmask = 0xffffffffu;  // only bits < nz <= 8 can be cleared; all-ones <=> untouched
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!((req_mask >> r) & 1u)) continue;
+    const int64_t q = req[r];
+    if (q == 0) continue;
+    if (!((node_res_mask >> r) & 1u)) return false;
+    bool has_affinity = false;
+    uint32_t res_bits = 0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      if (z < zs.nz && ((zs.zmask[z] >> r) & 1u)) {
+        has_affinity = true;
+        if (suitable(qos, cfg.res_flags[r], q, zs.avail[z][r])) res_bits |= 1u << z;
+      }
+    }
+    if (!has_affinity && (cfg.res_flags[r] & B200S_NRT_RES_HOST_LEVEL)) continue;
+    bitmask &= res_bits;
+    if (bitmask == 0) return false;
+  }
+  numa_id = __ffs(bitmask) - 1;
+  return true;
+}
+
+// TopologyMatch.Filter -> reason code
+template <int Z, int R>
+__device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t node_res_mask, const NrtCfg& cfg,
+                          const PodS<R>& pod) {
+  if (pod.flags & B200S_NRT_POD_FILTER_BYPASS) return B200S_REASON_OK;
+  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return B200S_REASON_UNSUPPORTED;
+  if (!(nflags & B200S_NRT_NODE_FRESH)) return B200S_REASON_NRT_INVALID_TOPOLOGY;
+  if (!(nflags & B200S_NRT_NODE_HAS_NRT)) return B200S_REASON_OK;
+  if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return B200S_REASON_OK;
+  int numa_id = 0;
+  if (nflags & B200S_NRT_NODE_SCOPE_POD) {
+    return available_in_any<Z, R>(node_zs, node_res_mask, cfg, pod.qos, pod.req_mask[C_MAX], pod.req[C_MAX], numa_id)
+               ? B200S_REASON_OK
+               : B200S_REASON_NRT_ALIGN_POD;
+  }
+  Zones<Z, R> zs = node_zs;  // working copy: app containers subtract what they take
+  for (int c = 0; c < pod.n_init; ++c) {
+    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, pod.req_mask[c], pod.req[c], numa_id))
+      return pod.kind[c] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT;
+  }
+  const int nc = pod.n_init + pod.n_app;
+  for (int c = pod.n_init; c < nc; ++c) {
+    const uint32_t rm = pod.req_mask[c];
+    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, rm, pod.req[c], numa_id))
+      return B200S_REASON_NRT_ALIGN_CONTAINER;
+    // subtractResourcesFromNUMANodeList (numaresources.go:145-182)
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      if (z != numa_id || z >= zs.nz) continue;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!((rm >> r) & 1u)) continue;
+        if (pod.qos != B200S_QOS_GUARANTEED && (cfg.res_flags[r] & B200S_NRT_RES_AFFINE)) continue;
+        const int64_t q = pod.req[c][r];
+        if (q == 0) continue;
+        if (!((zs.zmask[z] >> r) & 1u)) continue;
+        const int64_t left = zs.avail[z][r] - q;
+        if (left < 0) return B200S_REASON_NRT_ACCOUNTING;
+        zs.avail[z][r] = left;
+      }
+    }
+  }
+  return B200S_REASON_OK;
+}
+
+// one zone, Least/Most/Balanced strategies
+template <int Z, int R>
+__device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, const NrtCfg& cfg, uint32_t req_mask,
+                                                  const int64_t* req) {
+  if (cfg.strategy == B200S_NRT_BALANCED_ALLOCATION) {
+    double fr[R];
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!((req_mask >> r) & 1u)) continue;
+      const int64_t cap = ((zs.zmask[z] >> r) & 1u) ? zs.avail[z][r] : 0;
+      const int64_t cv = qty_value(cap);
+      const double f = cv == 0 ? 1.0 : (double)qty_value(req[r]) / (double)cv;
+      if (f > 1) return 0;
+      fr[n++] = f;
+    }
+    double sum = 0;
+    for (int i = 0; i < n; ++i) sum += fr[i];
+    const double mean = sum / (double)n;
+    double ss = 0, comp = 0;
+    for (int i = 0; i < n; ++i) {
+      const double d = fr[i] - mean;
+      ss += d * d;
+      comp += d;
+    }
+    const double variance = (ss - comp * comp / (double)n) / ((double)n - 1);
+    return f2i((1 - variance) * 100.0);
+  }
+  const bool most = cfg.strategy == B200S_NRT_MOST_ALLOCATED;
+  int64_t node_score = 0, weight_sum = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!((req_mask >> r) & 1u)) continue;
+    const int64_t cap = ((zs.zmask[z] >> r) & 1u) ? zs.avail[z][r] : 0;
+    int64_t s;
+    if (cap == 0 || req[r] > cap) {
+      s = 0;
+    } else {
+      const int64_t cv = qty_value(cap), rv = qty_value(req[r]);
+      s = most ? go_div(wrap_mul(rv, 100), cv) : go_div(wrap_mul(cv - rv, 100), cv);
+    }
+    node_score = wrap_add(node_score, wrap_mul(s, cfg.w[r]));
+    weight_sum = wrap_add(weight_sum, cfg.w[r]);
+  }
+  if (weight_sum == 0) return 0;
+  return go_div(node_score, weight_sum);
+}
+
+template <int Z, int R>
+__device__ __forceinline__ int64_t score_each_numa(const Zones<Z, R>& zs, const NrtCfg& cfg, uint32_t req_mask,
+                                                   const int64_t* req) {
+  int64_t min_score = 0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z) {
+    if (z >= zs.nz) continue;
+    const int64_t s = strategy_score<Z, R>(zs, z, cfg, req_mask, req);
+    if (min_score == 0 || (s != 0 && s < min_score)) min_score = s;
+  }
+  return min_score;
+}
+
+template <int Z, int R>
+__device__ __forceinline__ bool only_non_numa(const Zones<Z, R>& zs, uint32_t req_mask) {
+  uint32_t any = 0;
+#pragma unroll
+  for (int z = 0; z < Z; ++z)
+    if (z < zs.nz) any |= zs.zmask[z];
+  return (any & req_mask) == 0;
+}
+
+template <int Z>
+__device__ __forceinline__ float avg_distance(const int32_t (&cost)[Z][Z], uint32_t m, int k) {
+  int accu = 0;
+#pragma unroll
+  for (int i = 0; i < Z; ++i) {
+    if (!((m >> i) & 1u)) continue;
+#pragma unroll
+    for (int j = 0; j < Z; ++j) {
+      if (!((m >> j) & 1u)) continue;
+      const int c = cost[i][j];
+      accu += c < 0 ? 255 : c;
+    }
+  }
+  return (float)accu / (float)(k * k);
+}
+
+// numaNodesRequired + findSuitableCombination (least_numa.go:159-208); returns k (0 = cannot fit)
+template <int Z, int R>
+__device__ int numa_nodes_required(const Zones<Z, R>& zs, const int32_t (&cost)[Z][Z], const NrtCfg& cfg, int qos,
+                                   uint32_t req_mask, const int64_t* req, uint32_t& mask_out, bool& is_min) {
+  const int n = zs.nz;
+  if (n == 0) return 0;
+  for (int k = 1; k <= n; ++k) {
+    const int lo = c_combo_off[n - 1][k], hi = c_combo_off[n - 1][k + 1];
+    float min_avg = 255.0f;
+    for (int i = lo; i < hi; ++i) {
+      const float d = avg_distance<Z>(cost, c_combo_mask[n - 1][i], k);
+      if (d < min_avg) min_avg = d;
+    }
+    bool have = false;
+    uint32_t best = 0;
+    float min_dist = 256.0f;
+    for (int i = lo; i < hi; ++i) {
+      const uint32_t m = c_combo_mask[n - 1][i];
+      bool valid = true;
+      int64_t sum[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) sum[r] = 0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        if (!((m >> z) & 1u)) continue;
+        if ((zs.zmask[z] & req_mask) != req_mask) valid = false;  // isValidCombineResources
+#pragma unroll
+        for (int r = 0; r < R; ++r) sum[r] += zs.avail[z][r];
+      }
+      if (!valid) continue;
+      bool fit = true;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!((req_mask >> r) & 1u) || req[r] == 0) continue;
+        if (!suitable(qos, cfg.res_flags[r], req[r], sum[r])) fit = false;
+      }
+      if (!fit) continue;
+      const float dist = avg_distance<Z>(cost, m, k);
+      if (dist == min_avg) {
+        mask_out = m;
+        is_min = true;
+        return k;
+      }
+      if (dist < min_dist) {
+        min_dist = dist;
+        best = m;
+        have = true;
+      }
+    }
+    if (have) {
+      mask_out = best;
+      is_min = false;
+      return k;
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ int64_t normalize_least_numa(int count, bool is_min, int max_numa) {
+  const int64_t unit = 100 / (int64_t)max_numa;
+  const int64_t s = 100 - (int64_t)count * unit;
+  return is_min ? s + unit / 2 : s;
+}
+
+template <int Z, int R>
+__device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z][Z], uint32_t nflags, int max_numa,
+                             const NrtCfg& cfg, const PodS<R>& pod) {
+  if (pod.qos != B200S_QOS_GUARANTEED) return 100;
+  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return 0;
+  if (!(nflags & B200S_NRT_NODE_FRESH) || !(nflags & B200S_NRT_NODE_HAS_NRT)) return 0;
+  const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
+  const int nc = pod.n_init + pod.n_app;
+  if (cfg.strategy == B200S_NRT_LEAST_NUMA_NODES) {
+    uint32_t mask = 0;
+    bool is_min = false;
+    if (scope_pod) {
+      if (only_non_numa<Z, R>(node_zs, pod.req_mask[C_MAX])) return 100;
+      const int k = numa_nodes_required<Z, R>(node_zs, cost, cfg, pod.qos, pod.req_mask[C_MAX], pod.req[C_MAX], mask, is_min);
+      return k == 0 ? 0 : normalize_least_numa(k, is_min, max_numa);
+    }
+    Zones<Z, R> zs = node_zs;
+    int max_count = 0;
+    bool all_min = true;
+    for (int c = 0; c < nc; ++c) {
+      const uint32_t rm = pod.req_mask[c];
+      if (only_non_numa<Z, R>(zs, rm)) continue;
+      const int k = numa_nodes_required<Z, R>(zs, cost, cfg, pod.qos, rm, pod.req[c], mask, is_min);
+      if (k == 0) return 0;
+      if (!is_min) all_min = false;
+      if (k > max_count) max_count = k;
+      // subtractFromNUMAs (numaresources.go:184-215)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!((rm >> r) & 1u)) continue;
+        int64_t q = pod.req[c][r];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          if (z >= zs.nz || !((mask >> z) & 1u) || q == 0) continue;
+          if (!((zs.zmask[z] >> r) & 1u)) continue;
+          const int64_t av = zs.avail[z][r];
+          if (q >= av) {
+            q -= av;
+            zs.avail[z][r] = 0;
+          } else {
+            zs.avail[z][r] = av - q;
+            q = 0;
+          }
+        }
+      }
+    }
+    return max_count == 0 ? 100 : normalize_least_numa(max_count, all_min, max_numa);
+  }
+  if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return 0;
+  if (scope_pod) return score_each_numa<Z, R>(node_zs, cfg, pod.req_mask[C_MAX], pod.req[C_MAX]);
+  double sum = 0;
+  for (int c = 0; c < nc; ++c) sum += (double)score_each_numa<Z, R>(node_zs, cfg, pod.req_mask[c], pod.req[c]);
+  return f2i(sum / (double)nc);
+}
+
+struct NrtNodeCols {
+  const uint8_t* node_flags;
+  const uint16_t* max_numa;
+  const uint8_t* nz;
+  const uint8_t* node_res_mask;
+  const uint8_t* zone_res_mask;  // [Zs][Npad]
+  const int64_t* avail;          // [Zs][Rs][Npad]
+  const int32_t* cost;           // [Zs][Zs][Npad] or null
+  int Zs, Rs;
+};
+struct NrtPodCols {
+  const uint8_t* qos;
+  const uint8_t* flags;
+  const uint8_t* n_init;
+  const uint8_t* n_app;
+  const uint8_t* kind;      // [P][8]
+  const uint8_t* req_mask;  // [P][9]
+  const int64_t* req;       // [P][9][Rs]
+};
+
+template <int Z, int R, class OutT, int PT>
+__global__ void __launch_bounds__(128)
+nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict__ upstream, int words, int N,
+           int Npad, int P, OutT* __restrict__ out, uint32_t* __restrict__ feas_out32, uint8_t* __restrict__ reasons) {
+  __shared__ PodS<R> sp[PT];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int p0 = blockIdx.y * PT, pend = min(PT, P - p0);
+  // stage the pod tile
+  for (int i = threadIdx.x; i < pend * (C_MAX + 1) * R; i += 128) {
+    const int pp = i / ((C_MAX + 1) * R), rest = i % ((C_MAX + 1) * R), c = rest / R, r = rest % R;
+    sp[pp].req[c][r] = r < nc.Rs ? pc.req[((size_t)(p0 + pp) * (C_MAX + 1) + c) * nc.Rs + r] : 0;
+  }
+  for (int i = threadIdx.x; i < pend; i += 128) {
+    const int p = p0 + i;
+    sp[i].qos = pc.qos[p];
+    sp[i].flags = pc.flags[p];
+    sp[i].n_init = pc.n_init[p];
+    sp[i].n_app = pc.n_app[p];
+    for (int c = 0; c < C_MAX; ++c) sp[i].kind[c] = pc.kind[(size_t)p * C_MAX + c];
+    for (int c = 0; c <= C_MAX; ++c) sp[i].req_mask[c] = pc.req_mask[(size_t)p * (C_MAX + 1) + c];
+  }
+  // this thread's node: zones x resources block into registers, once for the whole pod tile
+  Zones<Z, R> zs;
+  int32_t cost[Z][Z];
+  uint32_t nflags = 0, node_res_mask = 0;
+  int max_numa = 8;
+  zs.nz = 0;
+  const bool in = n < Npad;
+  if (in) {
+    nflags = n < N ? nc.node_flags[n] : 0;
+    node_res_mask = nc.node_res_mask[n];
+    max_numa = nc.max_numa[n];
+    if (max_numa < 1) max_numa = 1;
+    zs.nz = min((int)nc.nz[n], Z);
+  }
+#pragma unroll
+  for (int z = 0; z < Z; ++z) {
+    zs.zmask[z] = (in && z < nc.Zs) ? nc.zone_res_mask[(size_t)z * Npad + n] : 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      zs.avail[z][r] = (in && z < nc.Zs && r < nc.Rs) ? nc.avail[((size_t)z * nc.Rs + r) * Npad + n] : 0;
+#pragma unroll
+    for (int z2 = 0; z2 < Z; ++z2)
+      cost[z][z2] = (in && nc.cost && z < nc.Zs && z2 < nc.Zs) ? nc.cost[((size_t)z * nc.Zs + z2) * Npad + n] : -1;
+  }
+  __syncthreads();
+  if (!in) return;
+  const int lane = threadIdx.x & 31;
+  const int word = n >> 6, half = (n >> 5) & 1;
+  for (int pp = 0; pp < pend; ++pp) {
+    const int p = p0 + pp;
+    const PodS<R>& pod = sp[pp];
+    int reason = 0;
+    bool feasible = false;
+    int64_t score = 0;
+    if (n < N) {
+      reason = nrt_filter<Z, R>(zs, nflags, node_res_mask, cfg, pod);
+      const bool up = upstream ? ((upstream[(size_t)p * words + word] >> (n & 63)) & 1ull) : true;
+      feasible = reason == 0 && up;
+      if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
+      if (feasible) score = nrt_score<Z, R>(zs, cost, nflags, max_numa, cfg, pod);
+    }
+    const uint32_t fw = __ballot_sync(0xffffffffu, feasible);
+    if (lane == 0) feas_out32[((size_t)p * words + word) * 2 + half] = fw;
+    out[(size_t)p * Npad + n] = (OutT)score;
+    reasons[(size_t)p * Npad + n] = (uint8_t)reason;
+  }
+}
+
+template <int Z, int R>
+int launch(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc, const NrtCfg& cfg) {
+  constexpr int PT = 16;
+  const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
+  PluginOut& o = c->out[B200S_PLUGIN_NRT];
+  const uint64_t* up = c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr;
+  dim3 grid((Npad + 127) / 128, (P + PT - 1) / PT);
+  if (dtype == B200S_OUT_I64)
+    nrt_kernel<Z, R, int64_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
+                                                               o.scores.as<int64_t>(), o.feas.as<uint32_t>(),
+                                                               o.reasons.as<uint8_t>());
+  else
+    nrt_kernel<Z, R, uint8_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
+                                                               o.scores.as<uint8_t>(), o.feas.as<uint32_t>(),
+                                                               o.reasons.as<uint8_t>());
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  return B200S_OK;
+}
+
+}  // namespace
+
+int nrt_eval(b200s_ctx* c, int dtype) {
+  if (!c->has_nrt) return c->set_err(B200S_ERR_STATE, "NodeResourceTopologyMatch: snapshot has no NRT columns");
+  if (!c->has_nrt_pods) return c->set_err(B200S_ERR_STATE, "NodeResourceTopologyMatch: pod batch has no NRT columns");
+  if (c->nrt_strategy == B200S_NRT_LEAST_NUMA_NODES && !c->nrt_has_cost)
+    return c->set_err(B200S_ERR_STATE, "NodeResourceTopologyMatch: LeastNUMANodes needs the zone cost columns");
+  if (ensure_combos() != 0) return c->set_err(B200S_ERR_CUDA, "NodeResourceTopologyMatch: combination table upload failed");
+  B200S_TRY(ensure_out(c, B200S_PLUGIN_NRT, dtype, true, true));
+  PluginOut& o = c->out[B200S_PLUGIN_NRT];
+  if (c->P == 0) {
+    o.valid = true;
+    return B200S_OK;
+  }
+  NrtNodeCols nc{c->nrt_node_flags.as<uint8_t>(), c->nrt_max_numa.as<uint16_t>(), c->nrt_nz.as<uint8_t>(),
+                 c->nrt_node_res_mask.as<uint8_t>(), c->nrt_zone_res_mask.as<uint8_t>(), c->nrt_avail.as<int64_t>(),
+                 c->nrt_has_cost ? c->nrt_cost.as<int32_t>() : nullptr, c->nrt_Z, c->nrt_R};
+  NrtPodCols pc{c->nrt_pod_qos.as<uint8_t>(), c->nrt_pod_flags.as<uint8_t>(), c->nrt_pod_ninit.as<uint8_t>(),
+                c->nrt_pod_napp.as<uint8_t>(), c->nrt_pod_kind.as<uint8_t>(), c->nrt_pod_req_mask.as<uint8_t>(),
+                c->nrt_pod_req.as<int64_t>()};
+  NrtCfg cfg;
+  cfg.strategy = c->nrt_strategy;
+  for (int r = 0; r < B200S_NRT_MAX_RES; ++r) {
+    cfg.w[r] = c->nrt_w[r];
+    cfg.res_flags[r] = c->nrt_res_flags[r];
+  }
+  KernelTimer kt(c, B200S_PLUGIN_NRT);
+  int rc;
+  if (c->nrt_Z <= 2 && c->nrt_R <= 4)
+    rc = launch<2, 4>(c, dtype, nc, pc, cfg);
+  else if (c->nrt_Z <= 4 && c->nrt_R <= 4)
+    rc = launch<4, 4>(c, dtype, nc, pc, cfg);
+  else
+    rc = launch<8, 8>(c, dtype, nc, pc, cfg);
+  if (rc != B200S_OK) return rc;
+  o.valid = true;
+  return B200S_OK;
+}
+
+}  // namespace b200s

@@ -132,3 +132,92 @@ def gen_netoh(seed: int, N: int, P: int, n_regions: int = 8, zones_per_region: i
     deps["max_network_cost"] = g.choice(np.array([0, 10, 30, 100]), size=total)
     return dict(K=K, zone_cost=zone_cost, region_cost=region_cost, region_all=region_all, zone_all=zone_all,
                 score_equally=score_equally, dep_offset=off, deps=deps)
+
+
+def gen_nrt(seed: int, N: int, P: int, Z: int = 4, with_cost: bool = True) -> tuple:
+    """NodeResourceTopologyMatch inputs directly in the dense encoding (include/b200sched.h):
+    resource slots 0 cpu, 1 memory, 2 hugepages-2Mi, 3 vendor/nic1 (device).  Returns (nodes, pods)."""
+    g = _streams(seed)[4]
+    R, C = 4, 8
+    base = gen_nodes(seed, N)
+    cores = base["alloc_cpu_milli"] // 1000
+    res_flags = np.array([1, 1, 1, 2], dtype=np.uint8)  # affine, affine, affine, host-level (non-native)
+    node_flags = np.full(N, 1 | 2 | 4, dtype=np.uint8)  # hasNRT | fresh | single-numa-node
+    node_flags |= (g.random(N) < 0.5).astype(np.uint8) * 8  # scope pod for half of the nodes
+    u = g.random(N)
+    node_flags[u < 0.01] &= ~np.uint8(1)       # 1 %: no NRT object
+    node_flags[(u >= 0.01) & (u < 0.015)] &= ~np.uint8(2)  # 0.5 %: stale
+    node_flags[(u >= 0.015) & (u < 0.02)] &= ~np.uint8(4)  # 0.5 %: policy none
+    node_flags[(u >= 0.02) & (u < 0.022)] |= 16  # unsupported shape -> host fallback
+    nz = np.full(N, Z, dtype=np.uint8)
+    nz[g.random(N) < 0.05] = max(1, Z // 2)
+    avail = np.zeros((Z, R, N), dtype=np.int64)
+    zmask = np.zeros((Z, N), dtype=np.uint8)
+    for z in range(Z):
+        has = z < nz
+        cpu = np.maximum(cores // Z - g.integers(0, 5, N), 0) * 1000
+        frac = g.random(N) < 0.10
+        cpu = np.where(frac, cpu + g.integers(1, 1000, N), cpu)
+        mem = np.maximum(base["alloc_mem_bytes"] // Z - g.integers(0, 4, N) * GiB, 0) * 1000
+        hp = g.choice(np.array([0, 512 * MiB, GiB]), size=N) * 1000
+        dev = np.where((z % 2) == 0, g.integers(0, 9, N), 0) * 1000
+        avail[z, 0], avail[z, 1], avail[z, 2], avail[z, 3] = cpu, mem, hp, dev
+        m = np.full(N, 1 | 2 | 4, dtype=np.uint8)
+        m |= np.where((z % 2) == 0, 8, 0).astype(np.uint8)  # device listed by 2 of 4 zones
+        zmask[z] = np.where(has, m, 0)
+        avail[z][:, ~has] = 0
+    node_res_mask = np.full(N, 1 | 2 | 4 | 8, dtype=np.uint8)
+    node_res_mask[g.random(N) < 0.02] &= ~np.uint8(8)  # device missing at node level
+    cost = np.full((Z, Z, N), -1, dtype=np.int32)
+    for a in range(Z):
+        for b in range(Z):
+            cost[a, b] = 10 if a == b else (12 if a // 2 == b // 2 else 20)
+    cost[:, :, g.random(N) < 0.01] = -1  # no SLIT data
+    nodes = dict(n_zones=Z, n_res=R, res_flags=res_flags, node_flags=node_flags,
+                 max_numa=np.where(g.random(N) < 0.9, 8, 4).astype(np.uint16), n_zones_node=nz,
+                 node_res_mask=node_res_mask, zone_res_mask=zmask, avail=avail, cost=cost if with_cost else None)
+
+    qos = g.choice(np.array([0, 1, 2]), size=P, p=[0.6, 0.3, 0.1]).astype(np.uint8)
+    n_app = g.integers(1, 5, P).astype(np.uint8)
+    n_init = g.integers(0, 3, P).astype(np.uint8)
+    kind = np.zeros((P, C), dtype=np.uint8)
+    req = np.zeros((P, C + 1, R), dtype=np.int64)
+    rmask = np.zeros((P, C + 1), dtype=np.uint8)
+    flags = np.zeros(P, dtype=np.uint8)
+    cpu_ch = np.array([100, 250, 500, 1000, 2000, 4000, 8000])
+    for p in range(P):
+        ni, na = int(n_init[p]), int(n_app[p])
+        non_native = False
+        for c in range(ni + na):
+            if c < ni:
+                kind[p, c] = 2 if g.random() < 0.3 else 1
+            if qos[p] != 2:
+                cpu = int(g.choice(cpu_ch)) if qos[p] == 1 or g.random() < 0.1 else int(g.integers(1, 9)) * 1000
+                req[p, c, 0], req[p, c, 1] = cpu, int(128 << g.integers(0, 8)) * MiB * 1000
+                rmask[p, c] |= 3
+                if g.random() < 0.2:
+                    req[p, c, 2] = int(g.choice([0, 64, 256, 512])) * MiB * 1000
+                    rmask[p, c] |= 4
+            if g.random() < (0.25 if qos[p] != 2 else 0.5):
+                req[p, c, 3] = int(g.integers(0, 5)) * 1000
+                rmask[p, c] |= 8
+                non_native = True
+        if qos[p] == 2 and not non_native:
+            flags[p] |= 1  # BestEffort with only native resources: Filter passes (filter.go:181)
+        # GetPodEffectiveRequest: max(sum app, max init) per resource (pkg/util/resource.go:51-85)
+        app_sum = req[p, ni:ni + na].sum(axis=0)
+        app_mask = np.bitwise_or.reduce(rmask[p, ni:ni + na]) if na else 0
+        init_max = req[p, :ni].max(axis=0) if ni else np.zeros(R, dtype=np.int64)
+        init_mask = np.bitwise_or.reduce(rmask[p, :ni]) if ni else 0
+        for r in range(R):
+            in_app, in_init = (app_mask >> r) & 1, (init_mask >> r) & 1
+            if in_app and in_init:
+                req[p, C, r] = max(app_sum[r], init_max[r])
+            elif in_app:
+                req[p, C, r] = app_sum[r]
+            elif in_init:
+                req[p, C, r] = init_max[r]
+        rmask[p, C] = app_mask | init_mask
+    flags[g.random(P) < 0.002] |= 2  # unsupported pods
+    pods = dict(qos=qos, flags=flags, n_init=n_init, n_app=n_app, cont_kind=kind, req_mask=rmask, req=req)
+    return nodes, pods

@@ -273,5 +273,54 @@ def main():
               "rejects", sum(1 for c in s["cases"] if c["want"]))
 
 
+def fixture_func(text, name):
+    k = text.index("func " + name + "(")
+    i = text.index("{", text.index("NodeResourceTopology {", k) + len("NodeResourceTopology"))
+    body = text[i:match_brace(text, i)]
+    nrts = parse_nrts(body)
+    for n in nrts:
+        n.pop("_span")
+        n["node_extra"] = {}
+    return nrts
+
+
+def main_scores():
+    src = open(os.path.join(REF, "score_test.go")).read()
+    CONST["gpu"] = "gpu"
+    default_nodes = fixture_func(src, "defaultNUMANodes")
+    four_nodes = fixture_func(src, "fourNUMANodes")
+    out = {"source": "pkg/noderesourcetopology/score_test.go — TestNodeResourceScorePlugin :87-194 (fixtures "
+                     "defaultNUMANodes :643-714 with policy SingleNUMANodeContainerLevel; only the arg-max node and its "
+                     "score are asserted), TestNodeResourceScorePluginLeastNUMA :196-480 (fixtures defaultNUMANodes / "
+                     "fourNUMANodes :716-947; every node's score asserted). Pods are makePodByResourceList(s): "
+                     "requests == limits (Guaranteed).",
+           "generated_by": "tests/golden/extract_nrt_golden.py", "suites": []}
+    pod = {"init": [], "containers": [cont({"cpu": "2", "memory": str(20 * 1024 * 1024)})]}
+    out["suites"].append({
+        "suite": "TestNodeResourceScorePlugin", "nodes": default_nodes, "policy_override": "SingleNUMANodeContainerLevel",
+        "cases": [{"name": "MostAllocated strategy", "strategy": "MostAllocated", "pod": pod, "want_max": {"Node2": 70}},
+                  {"name": "BalancedAllocation strategy", "strategy": "BalancedAllocation", "pod": pod, "want_max": {"Node3": 100}},
+                  {"name": "LeastAllocated strategy", "strategy": "LeastAllocated", "pod": pod, "want_max": {"Node1": 73}}]})
+    body = func_body(src, "TestNodeResourceScorePluginLeastNUMA")
+    cases = []
+    for ct in split_cases(table_after(body, "testCases := []struct")):
+        name = re.search(r'name:\s*"((?:[^"\\]|\\.)*)"', ct).group(1)
+        k = ct.index("podRequests:")
+        i = ct.index("{", k)
+        conts = [cont(parse_resource_list(g)) for g in top_level_groups(ct[i + 1:match_brace(ct, i) - 1])]
+        k = ct.index("wantedRes:")
+        i = ct.index("{", k)
+        want = {m.group(1): int(m.group(2)) for m in re.finditer(r'"(\w+)":\s*(\d+)', ct[i:match_brace(ct, i)])}
+        nm = re.search(r"nodes:\s*(\w+)\((?:withPolicy\(topologyv1alpha2\.(\w+)\))?\)", ct)
+        cases.append({"name": name, "strategy": "LeastNUMANodes", "pod": {"init": [], "containers": conts},
+                      "fixture": nm.group(1), "policy_override": nm.group(2), "want": want})
+    out["suites"].append({"suite": "TestNodeResourceScorePluginLeastNUMA",
+                          "fixtures": {"defaultNUMANodes": default_nodes, "fourNUMANodes": four_nodes}, "cases": cases})
+    with open(os.path.join(OUT, "nrt_score.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("score: default nodes", len(default_nodes), "four-NUMA nodes", len(four_nodes), "LeastNUMA cases", len(cases))
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    main()
+    main_scores()

@@ -1,0 +1,128 @@
+"""GPU parity: NodeResourceTopologyMatch Filter + Score through the C-ABI vs the oracle, on seeded
+dense inputs and on the reference's own unit-test fixtures (tests/golden/nrt_*.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from scheduler_plugins_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REASON_MSG = {0: None, 1: "invalid node topology data", 2: "cannot align pod", 3: "cannot align container",
+              4: "cannot align init container", 5: "cannot align sidecar container"}
+STRATEGY = {"MostAllocated": 0, "BalancedAllocation": 1, "LeastAllocated": 2, "LeastNUMANodes": 3}
+
+
+def run_nrt(eng, E, nodes, pods, strategy, weights=None, feas=None):
+    N, P = len(nodes["node_flags"]), len(pods["qos"])
+    eng.snapshot_begin(N)
+    eng.snapshot_nrt(nodes)
+    eng.snapshot_commit()
+    eng.config_nrt(strategy, weights)
+    eng.pods_upload(P, feasible=feas, nrt=pods)
+    eng.eval(E.PLUGIN_NRT)
+    return (eng.fetch_scores(E.PLUGIN_NRT), eng.fetch_feasible(E.PLUGIN_NRT), eng.fetch_reasons(E.PLUGIN_NRT))
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3])
+@pytest.mark.parametrize("P,N,Z,masked", [(96, 1500, 4, True), (33, 257, 2, False), (40, 640, 8, True)])
+def test_nrt_matches_oracle(eng, engine_mod, strategy, P, N, Z, masked):
+    from oracle import pyoracle_nrt
+
+    E = engine_mod
+    seed = synth.BASE_SEED + 4
+    nodes, pods = synth.gen_nrt(seed, N, P, Z=Z)
+    feas = synth.gen_feasible_words(seed, P, N, E.npad_of(N)) if masked else None
+    w = [3, 1, 2, 1] if strategy != 1 else None
+    gs, gf, gr = run_nrt(eng, E, nodes, pods, strategy, w, feas)
+    ws, wf, wr = pyoracle_nrt.nrt_batch(nodes, pods, strategy, w, feas, pitch=eng.Npad)
+    assert np.array_equal(gr, wr)
+    assert np.array_equal(gf, wf)
+    assert np.array_equal(gs, ws)
+    assert {2, 3}.issubset(set(np.unique(gr)))  # the fixture exercises pod- and container-scope rejects
+    eng.eval(E.PLUGIN_NRT, E.OUT_U8)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_NRT, E.OUT_U8).astype(np.int64), ws)
+
+
+def test_nrt_wide_resources(eng, engine_mod):
+    """R = 8 resource slots (the <8,8> instantiation) with 2 zones."""
+    from oracle import pyoracle_nrt
+
+    E = engine_mod
+    nodes, pods = synth.gen_nrt(21, 300, 24, Z=2)
+    R = 8
+    def widen(a, axis):
+        pad = [(0, 0)] * a.ndim
+        pad[axis] = (0, R - a.shape[axis])
+        return np.pad(a, pad)
+    nodes = dict(nodes, n_res=R, res_flags=widen(nodes["res_flags"], 0), avail=widen(nodes["avail"], 1))
+    nodes["avail"][:, 6] = nodes["avail"][:, 3]
+    nodes["zone_res_mask"] = nodes["zone_res_mask"] | ((nodes["zone_res_mask"] & 8) << 3)
+    nodes["node_res_mask"] = nodes["node_res_mask"] | ((nodes["node_res_mask"] & 8) << 3)
+    nodes["res_flags"][6] = 2
+    pods = dict(pods, req=widen(pods["req"], 2))
+    pods["req"][:, :, 6] = pods["req"][:, :, 3]
+    pods["req_mask"] = pods["req_mask"] | ((pods["req_mask"] & 8) << 3)
+    for strategy in (2, 3):
+        gs, gf, gr = run_nrt(eng, E, nodes, pods, strategy)
+        ws, wf, wr = pyoracle_nrt.nrt_batch(nodes, pods, strategy, None, None, pitch=eng.Npad)
+        assert np.array_equal(gr, wr) and np.array_equal(gf, wf) and np.array_equal(gs, ws)
+
+
+def _node_objects(suite_nodes):
+    from test_oracle_golden_nrt import node_objects
+
+    return node_objects({"nodes": suite_nodes})
+
+
+def test_nrt_filter_golden_through_cuda(eng, engine_mod):
+    """filter_test.go's 71 cases through flatten -> C-ABI -> CUDA."""
+    from oracle import flatten as F
+
+    E = engine_mod
+    g = json.load(open(os.path.join(GOLDEN, "nrt_filter.json")))
+    checked = 0
+    for suite in g["suites"]:
+        nodes, nrts = _node_objects(suite["nodes"])
+        pods = [c["pod"] for c in suite["cases"]]
+        names = F.build_dictionary(pods)
+        assert len(names) <= 8
+        ns, ps = F.flatten_nrt_nodes(nodes, nrts, names), F.flatten_nrt_pods(pods, names)
+        _, gf, gr = run_nrt(eng, E, ns, ps, E.NRT_LEAST_ALLOCATED)
+        for p, case in enumerate(suite["cases"]):
+            want = case["want"]["message"] if case["want"] else None
+            assert REASON_MSG[int(gr[p, case["node"]])] == want, (suite["suite"], case["name"])
+            assert bool((int(gf[p, 0]) >> case["node"]) & 1) == (want is None)
+            checked += 1
+    assert checked == 71
+
+
+def test_nrt_score_golden_through_cuda(eng, engine_mod):
+    from oracle import flatten as F
+
+    E = engine_mod
+    g = json.load(open(os.path.join(GOLDEN, "nrt_score.json")))
+    s0 = g["suites"][0]
+    fixture = [dict(n, policies=[s0["policy_override"]]) for n in s0["nodes"]]
+    nodes, nrts = _node_objects(fixture)
+    for case in s0["cases"]:
+        names = F.build_dictionary([case["pod"]])
+        gs, _, _ = run_nrt(eng, E, F.flatten_nrt_nodes(nodes, nrts, names), F.flatten_nrt_pods([case["pod"]], names),
+                           STRATEGY[case["strategy"]])
+        (wn, wsc), = case["want_max"].items()
+        idx = [n["name"] for n in fixture].index(wn)
+        assert gs[0, idx] == wsc and gs[0, :len(fixture)].max() == wsc, case["name"]
+    s1 = g["suites"][1]
+    for case in s1["cases"]:
+        fx = s1["fixtures"][case["fixture"]]
+        if case["policy_override"]:
+            fx = [dict(n, policies=[case["policy_override"]]) for n in fx]
+        nodes, nrts = _node_objects(fx)
+        names = F.build_dictionary([case["pod"]])
+        gs, _, _ = run_nrt(eng, E, F.flatten_nrt_nodes(nodes, nrts, names), F.flatten_nrt_pods([case["pod"]], names),
+                           E.NRT_LEAST_NUMA_NODES)
+        got = {n["name"]: int(gs[0, i]) for i, n in enumerate(fx)}
+        assert got == case["want"], case["name"]
