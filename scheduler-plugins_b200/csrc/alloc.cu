@@ -248,7 +248,7 @@ int alloc_eval(b200s_ctx* c, int dtype) {
   B200S_TRY(alloc_prepare(c));
   B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
   B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
-  const uint64_t* feas = c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr;
+  const uint64_t* feas = c->upstream_mask();
   {
     int threads = 128, warps_per_block = threads / 32;
     alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(

@@ -1,0 +1,262 @@
+// Combined profile: the upstream scheduling cycle over the engine's plugins, all pods at once.
+//
+// Restated from the upstream framework runtime (k8s.io/kubernetes pkg/scheduler, NOT in the
+// reference tree; SURVEY App. B "Upstream combination"):
+//   feasible(n) = AND over the enabled Filter plugins (NodeResourceTopologyMatch, NetworkOverhead)
+//                 and the caller's upstream mask;
+//   Score plugins run on the feasible nodes only, NormalizeScore over exactly that set;
+//   total(n)    = sum_p weight_p * score_p(n);
+//   selectHost  = arg-max; ties are random upstream — here deterministic: (total desc, node asc).
+// The filters are chained (each plugin's "upstream" set is what the previous filters left) so
+// NodeResourcesAllocatable / NetworkOverhead normalise over the final feasible set, as upstream.
+// Per-plugin scores travel as u8 (0..100); the weighted sum, the optional int64 total matrix and
+// the per-pod top-k are produced by one kernel.  Sharded: ONE ncclAllGather of the [P][k]
+// winners, then a fold — every rank ends up with the global top-k.
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+constexpr int K_MAX = 16;
+
+struct Cand {
+  int64_t score;
+  int32_t node;
+};
+__device__ __forceinline__ bool better(int64_t s1, int32_t n1, int64_t s2, int32_t n2) {
+  return s1 > s2 || (s1 == s2 && n1 < n2);
+}
+
+struct PluginPtrs {
+  const uint8_t* s[B200S_PLUGIN_COUNT];
+  int64_t w[B200S_PLUGIN_COUNT];
+  int n;
+};
+
+// One CTA per pod.
+template <int K>
+__global__ void __launch_bounds__(256)
+combine_topk_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words, int N, int Npad, int node_off, int k,
+                    int64_t* __restrict__ total, b200s_topk_entry* __restrict__ out) {
+  const int p = blockIdx.x, t = threadIdx.x;
+  int64_t bs[K];
+  int32_t bn[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    bs[i] = INT64_MIN;
+    bn[i] = INT32_MAX;
+  }
+  const size_t rowoff = (size_t)p * Npad;
+  for (int n4 = t * 4; n4 < Npad; n4 += 256 * 4) {
+    uint32_t packed[B200S_PLUGIN_COUNT];
+    for (int j = 0; j < pl.n; ++j) packed[j] = *reinterpret_cast<const uint32_t*>(pl.s[j] + rowoff + n4);
+    const uint64_t fw = feas ? feas[(size_t)p * words + (n4 >> 6)] : ~0ull;
+    int64_t tot[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n4 + e;
+      const bool f = n < N && ((fw >> (n & 63)) & 1ull);
+      int64_t s = 0;
+      for (int j = 0; j < pl.n; ++j) s = wrap_add(s, wrap_mul(pl.w[j], (int64_t)((packed[j] >> (8 * e)) & 255u)));
+      tot[e] = f ? s : 0;
+      if (f) {
+        const int32_t g = node_off + n;
+        if (better(s, g, bs[K - 1], bn[K - 1])) {  // insertion into the sorted per-thread list
+          bs[K - 1] = s;
+          bn[K - 1] = g;
+#pragma unroll
+          for (int i = K - 1; i > 0; --i) {
+            if (better(bs[i], bn[i], bs[i - 1], bn[i - 1])) {
+              int64_t ts = bs[i]; bs[i] = bs[i - 1]; bs[i - 1] = ts;
+              int32_t tn = bn[i]; bn[i] = bn[i - 1]; bn[i - 1] = tn;
+            }
+          }
+        }
+      }
+    }
+    if (total) {
+      st_stream_v2(total + rowoff + n4, tot[0], tot[1]);
+      st_stream_v2(total + rowoff + n4 + 2, tot[2], tot[3]);
+    }
+  }
+  // k rounds of block arg-max over the heads of the per-thread lists
+  __shared__ int64_t ss[8];
+  __shared__ int32_t sn[8];
+  __shared__ int64_t win_s;
+  __shared__ int32_t win_n;
+  for (int round = 0; round < k; ++round) {
+    int64_t s = bs[0];
+    int32_t n = bn[0];
+    for (int o = 16; o; o >>= 1) {
+      const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
+      const int32_t on = __shfl_xor_sync(0xffffffffu, n, o);
+      if (better(os, on, s, n)) {
+        s = os;
+        n = on;
+      }
+    }
+    if ((t & 31) == 0) {
+      ss[t >> 5] = s;
+      sn[t >> 5] = n;
+    }
+    __syncthreads();
+    if (t == 0) {
+      for (int i = 1; i < 8; ++i)
+        if (better(ss[i], sn[i], s, n)) {
+          s = ss[i];
+          n = sn[i];
+        }
+      win_s = s;
+      win_n = n;
+      b200s_topk_entry e;
+      e.score = n == INT32_MAX ? 0 : s;
+      e.node = n == INT32_MAX ? -1 : n;
+      e.pad = 0;
+      out[(size_t)p * k + round] = e;
+    }
+    __syncthreads();
+    if (bn[0] == win_n && win_n != INT32_MAX) {  // the owner pops its head
+#pragma unroll
+      for (int i = 0; i < K - 1; ++i) {
+        bs[i] = bs[i + 1];
+        bn[i] = bn[i + 1];
+      }
+      bs[K - 1] = INT64_MIN;
+      bn[K - 1] = INT32_MAX;
+    }
+    __syncthreads();
+  }
+}
+
+// Fold the gathered [world][P][k] winners: one thread per pod, k rounds of arg-max.
+__global__ void fold_topk_kernel(const b200s_topk_entry* __restrict__ all, int world, int P, int k,
+                                 b200s_topk_entry* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int64_t last_s = 0;
+  int32_t last_n = -1;
+  bool have_last = false;
+  for (int round = 0; round < k; ++round) {
+    int64_t bsx = INT64_MIN;
+    int32_t bnx = INT32_MAX;
+    for (int r = 0; r < world; ++r)
+      for (int i = 0; i < k; ++i) {
+        const b200s_topk_entry e = all[((size_t)r * P + p) * k + i];
+        if (e.node < 0) continue;
+        // strictly after the previous winner in (score desc, node asc) order
+        if (have_last && !better(last_s, last_n, e.score, e.node)) continue;
+        if (better(e.score, e.node, bsx, bnx)) {
+          bsx = e.score;
+          bnx = e.node;
+        }
+      }
+    b200s_topk_entry o;
+    o.score = bnx == INT32_MAX ? 0 : bsx;
+    o.node = bnx == INT32_MAX ? -1 : bnx;
+    o.pad = 0;
+    out[(size_t)p * k + round] = o;
+    if (bnx == INT32_MAX) {
+      for (int j = round + 1; j < k; ++j) out[(size_t)p * k + j] = o;
+      return;
+    }
+    last_s = bsx;
+    last_n = bnx;
+    have_last = true;
+  }
+}
+
+__global__ void fill_feasible_kernel(uint64_t* __restrict__ dst, int words, int N, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * words) return;
+  const int w = i % words;
+  const int base = w * 64;
+  uint64_t v = 0;
+  if (base + 64 <= N) v = ~0ull;
+  else if (base < N) v = (1ull << (N - base)) - 1ull;
+  dst[i] = v;
+}
+
+}  // namespace
+
+int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total) {
+  if (k < 1 || k > K_MAX) return c->set_err(B200S_ERR_INVALID, "eval_combined: k must be 1..16");
+  if (!weights) return c->set_err(B200S_ERR_INVALID, "eval_combined: null weights");
+  if ((mask & ((1u << B200S_PLUGIN_COUNT) - 1)) == 0) return c->set_err(B200S_ERR_INVALID, "eval_combined: no plugin enabled");
+  const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
+  c->total_valid = c->topk_valid = false;
+  c->mask_override = nullptr;
+  const uint64_t* cur = c->upstream_mask();
+  struct Reset {
+    b200s_ctx* c;
+    ~Reset() { c->mask_override = nullptr; }
+  } reset{c};
+  // filters first, chained
+  if (mask & (1u << B200S_PLUGIN_NRT)) {
+    c->mask_override = cur;
+    B200S_TRY(nrt_eval(c, B200S_OUT_U8));
+    cur = c->out[B200S_PLUGIN_NRT].feas.as<uint64_t>();
+  }
+  if (mask & (1u << B200S_PLUGIN_NETWORK_OVERHEAD)) {
+    c->mask_override = cur;
+    B200S_TRY(netoh_eval(c, B200S_OUT_U8));
+    cur = c->out[B200S_PLUGIN_NETWORK_OVERHEAD].feas.as<uint64_t>();
+  }
+  if (mask & (1u << B200S_PLUGIN_ALLOCATABLE)) {
+    c->mask_override = cur;
+    B200S_TRY(alloc_eval(c, B200S_OUT_U8));
+  }
+  c->mask_override = nullptr;
+  if (mask & (1u << B200S_PLUGIN_TLP)) B200S_TRY(tlp_eval(c, B200S_OUT_U8));
+  if (mask & (1u << B200S_PLUGIN_LVRB)) B200S_TRY(lvrb_eval(c, B200S_OUT_U8));
+
+  B200S_CUDA_TRY(c, c->total_feas.ensure((size_t)(P > 0 ? P : 1) * words * 8));
+  B200S_CUDA_TRY(c, c->topk_local.ensure((size_t)(P > 0 ? P : 1) * k * sizeof(b200s_topk_entry)));
+  B200S_CUDA_TRY(c, c->topk_final.ensure((size_t)(P > 0 ? P : 1) * k * sizeof(b200s_topk_entry)));
+  if (write_total) B200S_CUDA_TRY(c, c->total.ensure((size_t)(P > 0 ? P : 1) * Npad * 8));
+  c->topk_k = k;
+  if (P == 0) {
+    c->topk_valid = true;
+    c->total_valid = write_total != 0;
+    return B200S_OK;
+  }
+  if (cur)
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->total_feas.p, cur, (size_t)P * words * 8, cudaMemcpyDeviceToDevice, c->stream));
+  else {
+    fill_feasible_kernel<<<(P * words + 255) / 256, 256, 0, c->stream>>>(c->total_feas.as<uint64_t>(), words, N, P);
+    c->launches++;
+  }
+  PluginPtrs pl;
+  pl.n = 0;
+  for (int j = 0; j < B200S_PLUGIN_COUNT; ++j)
+    if (mask & (1u << j)) {
+      pl.s[pl.n] = c->out[j].scores.as<uint8_t>();
+      pl.w[pl.n] = weights[j];
+      pl.n++;
+    }
+  const int world = comm_world(c);
+  b200s_topk_entry* local = world > 1 ? c->topk_local.as<b200s_topk_entry>() : c->topk_final.as<b200s_topk_entry>();
+  int64_t* tot = write_total ? c->total.as<int64_t>() : nullptr;
+  if (k == 1)
+    combine_topk_kernel<1><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+  else if (k <= 4)
+    combine_topk_kernel<4><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+  else
+    combine_topk_kernel<K_MAX><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  if (world > 1) {
+    const size_t bytes = (size_t)P * k * sizeof(b200s_topk_entry);
+    B200S_CUDA_TRY(c, c->topk_all.ensure(bytes * world));
+    B200S_TRY(comm_allgather(c, c->topk_local.p, c->topk_all.p, bytes));
+    fold_topk_kernel<<<(P + 127) / 128, 128, 0, c->stream>>>(c->topk_all.as<b200s_topk_entry>(), world, P, k,
+                                                             c->topk_final.as<b200s_topk_entry>());
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  c->topk_valid = true;
+  c->total_valid = write_total != 0;
+  return B200S_OK;
+}
+
+}  // namespace b200s

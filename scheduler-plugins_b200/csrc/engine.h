@@ -126,6 +126,12 @@ struct b200s_ctx {
   int P = 0;
   bool has_feasible = false;
   b200s::DevBuf feasible_in;  // [P][Npad/64]
+  // eval_combined chains the filters: each plugin's "upstream" set is what the previous filters left
+  const uint64_t* mask_override = nullptr;
+  const uint64_t* upstream_mask() const {
+    if (mask_override) return mask_override;
+    return has_feasible ? feasible_in.as<uint64_t>() : nullptr;
+  }
   bool has_tlp_pods = false, has_lvrb_pods = false, has_nrt_pods = false, has_netoh_pods = false;
   b200s::DevBuf tlp_pod_cpu, lvrb_req_cpu, lvrb_req_mem;
   b200s::DevBuf nrt_pod_qos, nrt_pod_flags, nrt_pod_ninit, nrt_pod_napp, nrt_pod_kind, nrt_pod_req_mask,

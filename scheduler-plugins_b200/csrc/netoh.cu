@@ -254,7 +254,7 @@ int netoh_eval(b200s_ctx* c, int dtype) {
     netoh_raw_kernel<PT><<<grid, 256, 0, c->stream>>>(
         t, c->netoh_region.as<uint16_t>(), c->netoh_zone.as<uint16_t>(), c->node_off, c->netoh_equal.as<uint8_t>(),
         c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(),
-        c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr, words, N, Npad, P, c->raw_scores.as<int64_t>(),
+        c->upstream_mask(), words, N, Npad, P, c->raw_scores.as<int64_t>(),
         o.feas.as<uint64_t>(), o.reasons.as<uint8_t>());
     c->launches++;
     B200S_CUDA_TRY(c, cudaGetLastError());

@@ -460,7 +460,7 @@ int launch(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc,
   constexpr int PT = 16;
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
-  const uint64_t* up = c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr;
+  const uint64_t* up = c->upstream_mask();
   dim3 grid((Npad + 127) / 128, (P + PT - 1) / PT);
   if (dtype == B200S_OUT_I64)
     nrt_kernel<Z, R, int64_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,

@@ -1,0 +1,106 @@
+"""GPU parity: the combined profile (all five plugins, weighted sum, per-pod top-k) vs the oracle's
+restatement of the upstream cycle; single GPU here, the sharded path in test_multi_gpu.py."""
+import numpy as np
+import pytest
+
+from scheduler_plugins_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def build_inputs(seed, P, N, Z=4):
+    nodes = synth.gen_nodes(seed, N)
+    pods = synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    nrt_nodes, nrt_pods = synth.gen_nrt(seed, N, P, Z=Z)
+    net = synth.gen_netoh(seed, N, P)
+    return dict(nodes=nodes, pods=pods, tri=tri, nrt_nodes=nrt_nodes, nrt_pods=nrt_pods, net=net)
+
+
+def load_engine(eng, E, d, N, P, feas, node_offset=0, n_global=None, nrt_strategy=2):
+    nodes, pods, tri, net = d["nodes"], d["pods"], d["tri"], d["net"]
+    sl = slice(node_offset, node_offset + N)
+    eng.snapshot_begin(N, node_offset=node_offset, n_nodes_global=n_global or (node_offset + N))
+    eng.snapshot_allocatable([nodes["alloc_cpu_milli"][sl], nodes["alloc_mem_bytes"][sl]])
+    eng.snapshot_tlp(tri["cpu_avg"][sl], nodes["cap_cpu_milli"][sl], tri["missing_milli"][sl], tri["tlp_flags"][sl])
+    eng.snapshot_lvrb(tri["cpu_avg"][sl], tri["cpu_std"][sl], tri["mem_avg"][sl], tri["mem_std"][sl],
+                      nodes["alloc_cpu_milli"][sl], nodes["alloc_mem_bytes"][sl], tri["lvrb_flags"][sl])
+    nn = d["nrt_nodes"]
+    eng.snapshot_nrt(dict(nn, node_flags=nn["node_flags"][sl], max_numa=nn["max_numa"][sl],
+                          n_zones_node=nn["n_zones_node"][sl], node_res_mask=nn["node_res_mask"][sl],
+                          zone_res_mask=nn["zone_res_mask"][:, sl], avail=nn["avail"][:, :, sl],
+                          cost=nn["cost"][:, :, sl]))
+    eng.snapshot_network_overhead(net["region_all"][sl], net["zone_all"][sl], net["zone_cost"], net["region_cost"])
+    eng.snapshot_commit()
+    eng.config_allocatable(E.ALLOC_MOST, [1 << 20, 1])
+    eng.config_tlp(40)
+    eng.config_lvrb(1.0, 1.0)
+    eng.config_nrt(nrt_strategy, [1, 1, 1, 1])
+    eng.pods_upload(P, feasible=feas, tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"],
+                    lvrb_req_cpu_milli=pods["req_cpu_milli"], lvrb_req_mem_bytes=pods["req_mem_bytes"],
+                    nrt=d["nrt_pods"], netoh=net)
+
+
+def oracle_combined(d, P, N, pitch, feas, weights, k, mask, node_offset=0, nrt_strategy=2):
+    from oracle import combined as OC
+
+    nodes, pods, tri, net = d["nodes"], d["pods"], d["tri"], d["net"]
+    sl = slice(node_offset, node_offset + N)
+    nn = d["nrt_nodes"]
+    nrt_nodes = dict(nn, node_flags=nn["node_flags"][sl], max_numa=nn["max_numa"][sl], n_zones_node=nn["n_zones_node"][sl],
+                     node_res_mask=nn["node_res_mask"][sl], zone_res_mask=nn["zone_res_mask"][:, sl],
+                     avail=nn["avail"][:, :, sl], cost=nn["cost"][:, :, sl])
+    kw = {}
+    if mask & 1:
+        kw["alloc"] = dict(cols=[nodes["alloc_cpu_milli"][sl], nodes["alloc_mem_bytes"][sl]], weights=[1 << 20, 1], mode=1)
+    if mask & 2:
+        kw["tlp"] = dict(util=tri["cpu_avg"][sl], cap=nodes["cap_cpu_milli"][sl], missing=tri["missing_milli"][sl],
+                         flags=tri["tlp_flags"][sl], pod_cpu=pods["tlp_pod_cpu_milli"], target=40)
+    if mask & 4:
+        kw["lvrb"] = dict(node_cols=[tri["cpu_avg"][sl], tri["cpu_std"][sl], tri["mem_avg"][sl], tri["mem_std"][sl],
+                                     nodes["alloc_cpu_milli"][sl], nodes["alloc_mem_bytes"][sl], tri["lvrb_flags"][sl]],
+                          req_cpu=pods["req_cpu_milli"], req_mem=pods["req_mem_bytes"], margin=1.0, sens=1.0)
+    if mask & 8:
+        kw["nrt"] = dict(nodes=nrt_nodes, pods=d["nrt_pods"], strategy=nrt_strategy, weights=[1, 1, 1, 1])
+    if mask & 16:
+        kw["netoh"] = dict(zone_cost=net["zone_cost"], region_cost=net["region_cost"], region_id=net["region_all"][sl],
+                           zone_id=net["zone_all"][sl], score_equally=net["score_equally"], dep_offset=net["dep_offset"],
+                           deps=net["deps"])
+    return OC.combined(P, N, pitch, feas, weights, k, node_offset=node_offset, **kw)
+
+
+@pytest.mark.parametrize("mask,k", [(0b11111, 1), (0b11111, 4), (0b00111, 1), (0b01001, 3), (0b10001, 16), (0b00010, 2)])
+def test_combined_matches_oracle(eng, engine_mod, mask, k):
+    E = engine_mod
+    P, N = 48, 1300
+    seed = synth.BASE_SEED + 5
+    d = build_inputs(seed, P, N)
+    feas = synth.gen_feasible_words(seed, P, N, E.npad_of(N))
+    load_engine(eng, E, d, N, P, feas)
+    weights = [2, 1, 1, 3, 5]  # profile weights are launch parameters (NetworkOverhead weight 5 in the shipped profile)
+    eng.eval_combined(mask, weights, k=k, write_total=True)
+    got_topk = eng.fetch_topk()
+    got_total = eng.fetch_total()
+    got_feas = eng.fetch_total_feasible()
+    want_total, want_feas, want_topk = oracle_combined(d, P, N, eng.Npad, feas, weights, k, mask)
+    assert np.array_equal(got_feas, want_feas)
+    assert np.array_equal(got_total, want_total)
+    for p in range(P):
+        got = [(int(e["score"]), int(e["node"])) for e in got_topk[p]]
+        assert got == want_topk[p], (p, got, want_topk[p])
+    assert any(r[0][1] >= 0 for r in want_topk)
+
+
+def test_combined_without_total_matrix_and_no_upstream_mask(eng, engine_mod):
+    E = engine_mod
+    P, N = 20, 777
+    d = build_inputs(77, P, N, Z=2)
+    load_engine(eng, E, d, N, P, None, nrt_strategy=3)
+    weights = [1, 1, 1, 1, 1]
+    eng.eval_combined(0b11111, weights, k=2, write_total=False)
+    got = eng.fetch_topk()
+    with pytest.raises(E.B200SError):
+        eng.fetch_total()
+    _, _, want = oracle_combined(d, P, N, eng.Npad, None, weights, 2, 0b11111, nrt_strategy=3)
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in got[p]] == want[p]
