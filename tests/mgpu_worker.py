@@ -1,0 +1,74 @@
+"""Multi-GPU parity worker, launched by torchrun (one process per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P tests/mgpu_worker.py
+Every rank holds one shard of the node axis in its own engine ctx; the engine's NCCL communicator
+does the per-pod min/max all-reduce (NodeResourcesAllocatable / NetworkOverhead NormalizeScore) and
+the single all-gather of the per-pod top-k winners.  Each rank compares its shard of every score
+matrix and the folded global top-k with the UNSHARDED oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import pyoracle as orc
+    from scheduler_plugins_b200 import engine as E
+    from scheduler_plugins_b200 import sharding, synth
+    from test_gpu_combined import build_inputs, load_engine, oracle_combined
+
+    P, N, K = 40, 128 * 7 * world + 77, 3
+    seed = synth.BASE_SEED + 5
+    d = build_inputs(seed, P, N)
+    feas_full = synth.gen_feasible_words(seed, P, N, E.npad_of(N))
+    fb = E.unpack_bits(feas_full, N)
+    off, cnt = sharding.shard_bounds(N, world)[rank]
+    feas = E.pack_bits(fb[:, off:off + cnt], E.npad_of(cnt))
+
+    eng = E.Engine(local)
+    uid = [eng.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)
+    load_engine(eng, E, d, cnt, P, feas, node_offset=off, n_global=N)
+    weights = [2, 1, 1, 3, 5]
+
+    # --- NodeResourcesAllocatable alone: sharded NormalizeScore == unsharded
+    eng.eval(E.PLUGIN_ALLOCATABLE)
+    got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE)[:, :cnt]
+    want = orc.alloc_batch([d["nodes"]["alloc_cpu_milli"], d["nodes"]["alloc_mem_bytes"]], [1 << 20, 1], 1, P, feas_full,
+                           pitch=E.npad_of(N))
+    assert np.array_equal(got, want[:, off:off + cnt]), f"rank {rank}: sharded Allocatable != unsharded oracle"
+
+    # --- NetworkOverhead alone (global host-node indices, min/max all-reduce)
+    eng.eval(E.PLUGIN_NETWORK_OVERHEAD)
+    got = eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD)[:, :cnt]
+    net = d["net"]
+    ws, wf, _ = orc.netoh_batch(net["zone_cost"], net["region_cost"], net["region_all"], net["zone_all"],
+                                net["score_equally"], net["dep_offset"], net["deps"], feas_full, pitch=E.npad_of(N))
+    assert np.array_equal(got, ws[:, off:off + cnt]), f"rank {rank}: sharded NetworkOverhead != unsharded oracle"
+
+    # --- combined profile: total matrix shard + global top-k on every rank
+    eng.eval_combined(0b11111, weights, k=K, write_total=True)
+    want_total, want_feas, want_topk = oracle_combined(d, P, N, E.npad_of(N), feas_full, weights, K, 0b11111)
+    assert np.array_equal(eng.fetch_total()[:, :cnt], want_total[:, off:off + cnt]), f"rank {rank}: total differs"
+    got_topk = eng.fetch_topk()
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in got_topk[p]] == want_topk[p], (rank, p)
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu ok: world={world} P={P} N={N} shards={sharding.shard_bounds(N, world)}")
+    eng.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
