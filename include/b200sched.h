@@ -199,6 +199,12 @@ int b200s_config_tlp(b200s_ctx* ctx, int64_t target_utilization_pct);
 int b200s_config_lvrb(b200s_ctx* ctx, double safe_variance_margin, double safe_variance_sensitivity);
 /* weights[r] per resource slot of the NRT dictionary; values < 1 mean 1 (score.go:49-60) */
 int b200s_config_nrt(b200s_ctx* ctx, int strategy, int32_t n_res, const int64_t* weights);
+/* NetworkOverhead: want_counts != 0 also keeps PreFilterState.satisfiedMap / violatedMap
+ * (networkoverhead.go:283-296) for the Filter status message.  apply_own_filter (default 1): the
+ * plugin's Filter verdict is ANDed into the feasible set that NormalizeScore runs over, as in the
+ * upstream cycle; 0 = normalise over exactly the caller's mask (what NormalizeScore does when it is
+ * handed an arbitrary NodeScoreList, networkoverhead.go:389-418) — verdicts are still reported. */
+int b200s_config_network_overhead(b200s_ctx* ctx, int want_counts, int apply_own_filter);
 
 /* ---- pod batch ------------------------------------------------------------ */
 #define B200S_QOS_GUARANTEED 0
@@ -261,6 +267,11 @@ int b200s_eval(b200s_ctx* ctx, b200s_plugin plugin, b200s_out_dtype dtype);
 int b200s_fetch_scores(b200s_ctx* ctx, b200s_plugin plugin, void* out, size_t bytes);
 int b200s_fetch_feasible(b200s_ctx* ctx, b200s_plugin plugin, uint64_t* out, size_t bytes);
 int b200s_fetch_reasons(b200s_ctx* ctx, b200s_plugin plugin, uint8_t* out, size_t bytes);
+/* NetworkOverhead's PreFilterState after the last eval of that plugin: finalCostMap as
+ * [P][Npad] int64 (what Score returns before NormalizeScore, networkoverhead.go:383), and — if
+ * enabled — [P][Npad] uint32 = satisfied | violated << 16. */
+int b200s_fetch_network_overhead_raw(b200s_ctx* ctx, int64_t* out, size_t bytes);
+int b200s_fetch_network_overhead_counts(b200s_ctx* ctx, uint32_t* out, size_t bytes);
 /* Device pointers of the same matrices (valid until the next eval of that plugin). */
 void* b200s_device_scores(b200s_ctx* ctx, b200s_plugin plugin);
 uint64_t* b200s_device_feasible(b200s_ctx* ctx, b200s_plugin plugin);

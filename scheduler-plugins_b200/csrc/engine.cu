@@ -100,7 +100,7 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->nrt_pod_kind,    &c->nrt_pod_req_mask, &c->nrt_pod_req,      &c->netoh_equal,
                     &c->netoh_dep_off,   &c->netoh_deps,       &c->pod_lo,           &c->pod_hi,
                     &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
-                    &c->topk_local,      &c->topk_all,         &c->topk_final};
+                    &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();
@@ -360,6 +360,14 @@ int b200s_config_lvrb(b200s_ctx* c, double margin, double sens) {
   return B200S_OK;
 }
 
+int b200s_config_network_overhead(b200s_ctx* c, int want_counts, int apply_own_filter) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->netoh_want_counts = want_counts != 0;
+  c->netoh_apply_filter = apply_own_filter != 0;
+  return B200S_OK;
+}
+
 int b200s_config_nrt(b200s_ctx* c, int strategy, int32_t n_res, const int64_t* weights) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
@@ -523,6 +531,22 @@ int b200s_fetch_reasons(b200s_ctx* c, b200s_plugin plugin, uint8_t* out, size_t 
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
   return fetch_reasons_locked(c, plugin, out, bytes);
+}
+
+int b200s_fetch_network_overhead_raw(b200s_ctx* c, int64_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->out[B200S_PLUGIN_NETWORK_OVERHEAD].valid || c->netoh_raw_P != c->P)
+    return c->set_err(B200S_ERR_STATE, "fetch_network_overhead_raw: plugin not evaluated");
+  return fetch(c, c->raw_scores, out, bytes, (size_t)c->P * c->Npad * 8, "fetch_network_overhead_raw");
+}
+
+int b200s_fetch_network_overhead_counts(b200s_ctx* c, uint32_t* out, size_t bytes) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (!c->out[B200S_PLUGIN_NETWORK_OVERHEAD].valid || c->netoh_raw_P != c->P || !c->netoh_want_counts)
+    return c->set_err(B200S_ERR_STATE, "fetch_network_overhead_counts: counts not enabled or plugin not evaluated");
+  return fetch(c, c->netoh_counts, out, bytes, (size_t)c->P * c->Npad * 4, "fetch_network_overhead_counts");
 }
 
 void* b200s_device_scores(b200s_ctx* c, b200s_plugin plugin) {

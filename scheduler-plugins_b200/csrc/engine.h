@@ -143,6 +143,10 @@ struct b200s_ctx {
   b200s::DevBuf pod_lo, pod_hi;  // [P] int64
   b200s::DevBuf norm_params;     // [P] NormParam
   b200s::DevBuf raw_scores;      // [P][Npad] int64 scratch (NetworkOverhead raw cost)
+  b200s::DevBuf netoh_counts;    // [P][Npad] u32 satisfied | violated << 16 (opt-in)
+  bool netoh_want_counts = false;
+  bool netoh_apply_filter = true;
+  int netoh_raw_P = -1;          // P of the last NetworkOverhead eval (raw/counts validity)
 
   // ---- outputs ----
   b200s::PluginOut out[B200S_PLUGIN_COUNT];

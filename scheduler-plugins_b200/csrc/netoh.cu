@@ -95,7 +95,7 @@ netoh_raw_kernel(Topo t, const uint16_t* __restrict__ region, const uint16_t* __
                  const uint8_t* __restrict__ equal, const int32_t* __restrict__ dep_off,
                  const b200s_netoh_dep* __restrict__ deps, const uint64_t* __restrict__ upstream, int words, int N,
                  int Npad, int P, int64_t* __restrict__ raw, uint64_t* __restrict__ feas_out,
-                 uint8_t* __restrict__ reasons) {
+                 uint8_t* __restrict__ reasons, uint32_t* __restrict__ counts, bool apply_filter) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbase = (blockIdx.x * 8 + warp) * 64;  // this warp's 64-node group
   if (nbase >= Npad) return;
@@ -115,12 +115,19 @@ netoh_raw_kernel(Topo t, const uint16_t* __restrict__ region, const uint16_t* __
     }
     const bool pass0 = v0 && (eq || !(w0 > s0)), pass1 = v1 && (eq || !(w1 > s1));
     uint64_t up = upstream ? upstream[(size_t)p * words + word] : ~0ull;
-    const bool f0 = pass0 && ((up >> lane) & 1ull), f1 = pass1 && ((up >> (lane + 32)) & 1ull);
+    const bool f0 = (apply_filter ? pass0 : v0) && ((up >> lane) & 1ull);
+    const bool f1 = (apply_filter ? pass1 : v1) && ((up >> (lane + 32)) & 1ull);
     const uint64_t fw = (uint64_t)__ballot_sync(0xffffffffu, f0) | ((uint64_t)__ballot_sync(0xffffffffu, f1) << 32);
     if (lane == 0) feas_out[(size_t)p * words + word] = fw;
+    // raw = PreFilterState.finalCostMap (written for every node, filtered or not: Score reads it, :383)
     int64_t* row = raw + (size_t)p * Npad;
-    row[n0] = f0 ? (eq ? 0 : c0) : 0;
-    row[n1] = f1 ? (eq ? 0 : c1) : 0;
+    row[n0] = (v0 && !eq) ? c0 : 0;
+    row[n1] = (v1 && !eq) ? c1 : 0;
+    if (counts) {  // satisfiedMap / violatedMap for the Filter message (:355-356); counts <= #deps
+      uint32_t* cr = counts + (size_t)p * Npad;
+      cr[n0] = (uint32_t)(s0 & 0xffff) | ((uint32_t)(w0 & 0xffff) << 16);
+      cr[n1] = (uint32_t)(s1 & 0xffff) | ((uint32_t)(w1 & 0xffff) << 16);
+    }
     if (reasons) {
       uint8_t* rr = reasons + (size_t)p * Npad;
       rr[n0] = !v0 ? 0 : (!pass0 ? B200S_REASON_NETOH_VIOLATED : (f0 ? B200S_REASON_OK : B200S_REASON_UPSTREAM));
@@ -243,6 +250,7 @@ int netoh_eval(b200s_ctx* c, int dtype) {
     return B200S_OK;
   }
   B200S_CUDA_TRY(c, c->raw_scores.ensure((size_t)P * Npad * 8));
+  if (c->netoh_want_counts) B200S_CUDA_TRY(c, c->netoh_counts.ensure((size_t)P * Npad * 4));
   B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
   B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
   B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
@@ -255,7 +263,7 @@ int netoh_eval(b200s_ctx* c, int dtype) {
         t, c->netoh_region.as<uint16_t>(), c->netoh_zone.as<uint16_t>(), c->node_off, c->netoh_equal.as<uint8_t>(),
         c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(),
         c->upstream_mask(), words, N, Npad, P, c->raw_scores.as<int64_t>(),
-        o.feas.as<uint64_t>(), o.reasons.as<uint8_t>());
+        o.feas.as<uint64_t>(), o.reasons.as<uint8_t>(), c->netoh_want_counts ? c->netoh_counts.as<uint32_t>() : nullptr, c->netoh_apply_filter);
     c->launches++;
     B200S_CUDA_TRY(c, cudaGetLastError());
   }
@@ -279,6 +287,7 @@ int netoh_eval(b200s_ctx* c, int dtype) {
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
   o.valid = true;
+  c->netoh_raw_P = P;
   return B200S_OK;
 }
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "b200s_snapshot_begin", "b200s_snapshot_allocatable", "b200s_snapshot_tlp", "b200s_snapshot_lvrb",
     "b200s_snapshot_nrt", "b200s_snapshot_network_overhead", "b200s_snapshot_commit",
     "b200s_config_allocatable", "b200s_config_tlp", "b200s_config_lvrb", "b200s_config_nrt",
+    "b200s_config_network_overhead", "b200s_fetch_network_overhead_raw", "b200s_fetch_network_overhead_counts",
     "b200s_pods_upload", "b200s_eval", "b200s_fetch_scores", "b200s_fetch_feasible", "b200s_fetch_reasons",
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
@@ -330,6 +331,20 @@ class Engine:
         out = np.empty((self.P, self.Npad), dtype=np.uint8)
         self._chk(self.lib.b200s_fetch_reasons(self.ctx, C.c_int(plugin), _ptr(out), C.c_size_t(out.nbytes)))
         return out
+
+    def config_network_overhead(self, want_counts=True, apply_own_filter=True):
+        self._chk(self.lib.b200s_config_network_overhead(self.ctx, C.c_int(1 if want_counts else 0),
+                                                         C.c_int(1 if apply_own_filter else 0)))
+
+    def fetch_network_overhead_raw(self):
+        out = np.empty((self.P, self.Npad), dtype=np.int64)
+        self._chk(self.lib.b200s_fetch_network_overhead_raw(self.ctx, _ptr(out), C.c_size_t(out.nbytes)))
+        return out
+
+    def fetch_network_overhead_counts(self):
+        out = np.empty((self.P, self.Npad), dtype=np.uint32)
+        self._chk(self.lib.b200s_fetch_network_overhead_counts(self.ctx, _ptr(out), C.c_size_t(out.nbytes)))
+        return out & 0xffff, out >> 16
 
     def device_scores(self, plugin) -> int:
         return int(self.lib.b200s_device_scores(self.ctx, C.c_int(plugin)) or 0)
