@@ -3,7 +3,6 @@
 
 #include <algorithm>
 #include <cstring>
-#include <regex>
 #include <set>
 #include <stdexcept>
 
@@ -368,15 +367,23 @@ constexpr int Z_MAX = B200S_NRT_MAX_ZONES, R_MAX = B200S_NRT_MAX_RES, C_MAX = B2
 
 // createNUMANodeList (pluginhelpers.go:105-134): zones of type Node named node-<id>, id <= 64.
 // The dense encoding needs ids 0..k-1 in list order (see include/b200sched.h); else UNSUPPORTED.
+// numanode.NameToID: "node-<decimal id>" -> id, -1 if the name has another shape
+long NumaNameToID(const std::string& name) {
+  if (name.rfind("node-", 0) != 0 || name.size() == 5 || name.size() > 5 + 9) return -1;
+  long id = 0;
+  for (size_t i = 5; i < name.size(); ++i) {
+    if (name[i] < '0' || name[i] > '9') return -1;
+    id = id * 10 + (name[i] - '0');
+  }
+  return id;
+}
+
 bool NumaZones(const NodeResourceTopology& nrt, std::vector<const Zone*>* out) {
   std::vector<int> ids;
-  static const std::regex re("node-([0-9]+)");
   for (auto& z : nrt.zones) {
     if (z.type != "Node") continue;
-    std::smatch m;
-    if (!std::regex_match(z.name, m, re)) continue;
-    long id = std::stol(m[1]);
-    if (id > 64) continue;
+    long id = NumaNameToID(z.name);
+    if (id < 0 || id > 64) continue;
     out->push_back(&z);
     ids.push_back((int)id);
   }
@@ -454,7 +461,6 @@ std::shared_ptr<CycleResult> TopologyMatch::Run(CycleState& state, const Pod& po
           fl |= B200S_NRT_NODE_UNSUPPORTED;
         } else {
           nz[i] = (uint8_t)zl[i].size();
-          static const std::regex re("node-([0-9]+)");
           for (size_t z = 0; z < zl[i].size(); ++z) {
             for (int r = 0; r < R; ++r) {
               auto zr = zl[i][z]->resources.find(names[r]);
@@ -463,11 +469,8 @@ std::shared_ptr<CycleResult> TopologyMatch::Run(CycleState& state, const Pod& po
               avail[(z * R + r) * m + i] = zr->second.available;  // extractResources: Available
             }
             for (auto& [cname, cval] : zl[i][z]->costs) {  // extractCosts: pluginhelpers.go:136-153
-              std::smatch mm;
-              if (std::regex_match(cname, mm, re)) {
-                long id = std::stol(mm[1]);
-                if (id < (long)zl[i].size()) cost[(z * Z + id) * m + i] = (int32_t)cval;
-              }
+              long id = NumaNameToID(cname);
+              if (id >= 0 && id < (long)zl[i].size()) cost[(z * Z + id) * m + i] = (int32_t)cval;
             }
           }
         }

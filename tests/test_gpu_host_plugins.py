@@ -143,7 +143,9 @@ def test_target_load_packing_missing_utilisation_and_last_metric(H):
     pod = make_pod(H, {"containers": [{"requests": {"cpu": "100m"}, "limits": {}}]})  # 100m * 1.5 = 150
     score, _ = p.score(H.CycleState(), pod, fh.node_infos[0])
     predicted = 100 * (100 + 150 + 100) / 1000  # util 10% of 1000m + pod + bound pod (inside 60 s of window end)
-    assert score == round((100 - 40) * predicted / 40 + 40)
+    import math
+
+    assert score == math.floor((100 - 40) * predicted / 40 + 40 + 0.5) == 93  # math.Round(92.5) = 93 (half away from zero)
 
 
 def test_load_variation_risk_balancing_score(H):
