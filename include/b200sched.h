@@ -311,6 +311,11 @@ void b200s_free_pinned(void* p);
 int b200s_set_profiling(b200s_ctx* ctx, int on);
 int b200s_kernel_time(b200s_ctx* ctx, b200s_plugin plugin, double* total_ms, uint64_t* launches);
 
+/* Test hook: the Trimaran kernels divide by per-node / per-launch invariants with a hoisted
+ * reciprocal + FMA residual correction; this counts inputs where that differs (bitwise) from the
+ * IEEE division x[i]/d[i] on the device.  Must be 0. */
+int b200s_debug_div_check(b200s_ctx* ctx, const double* x, const double* d, int32_t n, uint64_t* mismatches);
+
 /* Padded node count of the current snapshot (row pitch of every matrix). */
 int32_t b200s_npad(b200s_ctx* ctx);
 

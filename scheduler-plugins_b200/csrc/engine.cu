@@ -588,6 +588,12 @@ int b200s_fetch_total_feasible(b200s_ctx* c, uint64_t* out, size_t bytes) {
   return fetch(c, c->total_feas, out, bytes, (size_t)c->P * (c->Npad / 64) * 8, "fetch_total_feasible");
 }
 
+int b200s_debug_div_check(b200s_ctx* c, const double* x, const double* d, int32_t n, uint64_t* mismatches) {
+  if (!c || !x || !d || !mismatches || n < 0) return B200S_ERR_INVALID;
+  Guard g(c);
+  return debug_div_check(c, x, d, n, mismatches);
+}
+
 int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,
                       void* scores_out, uint64_t* feasible_out, uint8_t* reasons_out) {
   if (!c) return B200S_ERR_INVALID;

@@ -201,6 +201,7 @@ int lvrb_eval(b200s_ctx* c, int dtype);
 int nrt_eval(b200s_ctx* c, int dtype);
 int netoh_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
+int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint64_t* mismatches);
 
 // comm.cu
 int comm_allreduce_minmax(b200s_ctx* c, int64_t* lo, int64_t* hi, int count);  // in place, device

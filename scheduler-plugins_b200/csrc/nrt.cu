@@ -60,6 +60,7 @@ int ensure_combos() {
 template <int R>
 struct PodS {  // one pod of the tile, in shared memory
   int64_t req[C_MAX + 1][R];
+  int64_t reqv[C_MAX + 1][R];  // Quantity.Value() of req (ceil to whole units), precomputed once per tile
   uint8_t req_mask[C_MAX + 1];
   uint8_t kind[C_MAX];
   uint8_t qos, flags, n_init, n_app;
@@ -83,6 +84,24 @@ __device__ __forceinline__ int64_t f2i(double x) {
   if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
   return (int64_t)x;
 }
+// floor(a*100/cv) for 0 <= a <= cv (quotient in 0..100): fp32 estimate + exact integer fix-up instead of
+// a 64-bit division; identical to Go's (a*100)/cv.  Absurdly large capacities keep the wrapping Go path.
+__device__ __forceinline__ int64_t div100(int64_t a, int64_t cv) {
+  if (cv >= (1ll << 52) || a < 0 || a > cv) return go_div(wrap_mul(a, 100), cv);
+  const int64_t num = a * 100;
+  int64_t q = (int64_t)__float2int_rd(__fdividef(__ll2float_rn(num), __ll2float_rn(cv)));
+  int64_t rem = num - q * cv;
+  while (rem < 0) {
+    --q;
+    rem += cv;
+  }
+  while (rem >= cv) {
+    ++q;
+    rem -= cv;
+  }
+  return q;
+}
+
 __device__ __forceinline__ bool suitable(int qos, uint32_t rflags, int64_t qty, int64_t numa_qty) {
   if (qos != B200S_QOS_GUARANTEED && (rflags & B200S_NRT_RES_AFFINE)) return true;
   return numa_qty >= qty;
@@ -162,10 +181,10 @@ __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t 
 }
 
 // one zone, Least/Most/Balanced strategies
-template <int Z, int R>
+template <int Z, int R, int SC>
 __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, const NrtCfg& cfg, uint32_t req_mask,
-                                                  const int64_t* req) {
-  if (cfg.strategy == B200S_NRT_BALANCED_ALLOCATION) {
+                                                  const int64_t* req, const int64_t* reqv) {
+  if constexpr (SC == 1) {
     double fr[R];
     int n = 0;
 #pragma unroll
@@ -173,7 +192,7 @@ __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, 
       if (!((req_mask >> r) & 1u)) continue;
       const int64_t cap = ((zs.zmask[z] >> r) & 1u) ? zs.avail[z][r] : 0;
       const int64_t cv = qty_value(cap);
-      const double f = cv == 0 ? 1.0 : (double)qty_value(req[r]) / (double)cv;
+      const double f = cv == 0 ? 1.0 : (double)reqv[r] / (double)cv;
       if (f > 1) return 0;
       fr[n++] = f;
     }
@@ -199,8 +218,8 @@ __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, 
     if (cap == 0 || req[r] > cap) {
       s = 0;
     } else {
-      const int64_t cv = qty_value(cap), rv = qty_value(req[r]);
-      s = most ? go_div(wrap_mul(rv, 100), cv) : go_div(wrap_mul(cv - rv, 100), cv);
+      const int64_t cv = qty_value(cap), rv = reqv[r];
+      s = most ? div100(rv, cv) : div100(cv - rv, cv);
     }
     node_score = wrap_add(node_score, wrap_mul(s, cfg.w[r]));
     weight_sum = wrap_add(weight_sum, cfg.w[r]);
@@ -209,14 +228,14 @@ __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, 
   return go_div(node_score, weight_sum);
 }
 
-template <int Z, int R>
+template <int Z, int R, int SC>
 __device__ __forceinline__ int64_t score_each_numa(const Zones<Z, R>& zs, const NrtCfg& cfg, uint32_t req_mask,
-                                                   const int64_t* req) {
+                                                   const int64_t* req, const int64_t* reqv) {
   int64_t min_score = 0;
 #pragma unroll
   for (int z = 0; z < Z; ++z) {
     if (z >= zs.nz) continue;
-    const int64_t s = strategy_score<Z, R>(zs, z, cfg, req_mask, req);
+    const int64_t s = strategy_score<Z, R, SC>(zs, z, cfg, req_mask, req, reqv);
     if (min_score == 0 || (s != 0 && s < min_score)) min_score = s;
   }
   return min_score;
@@ -311,7 +330,7 @@ __device__ __forceinline__ int64_t normalize_least_numa(int count, bool is_min, 
   return is_min ? s + unit / 2 : s;
 }
 
-template <int Z, int R>
+template <int Z, int R, int SC>
 __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z][Z], uint32_t nflags, int max_numa,
                              const NrtCfg& cfg, const PodS<R>& pod) {
   if (pod.qos != B200S_QOS_GUARANTEED) return 100;
@@ -319,7 +338,7 @@ __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z
   if (!(nflags & B200S_NRT_NODE_FRESH) || !(nflags & B200S_NRT_NODE_HAS_NRT)) return 0;
   const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
   const int nc = pod.n_init + pod.n_app;
-  if (cfg.strategy == B200S_NRT_LEAST_NUMA_NODES) {
+  if constexpr (SC == 2) {
     uint32_t mask = 0;
     bool is_min = false;
     if (scope_pod) {
@@ -358,12 +377,14 @@ __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z
       }
     }
     return max_count == 0 ? 100 : normalize_least_numa(max_count, all_min, max_numa);
+  } else {
+    if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return 0;
+    if (scope_pod) return score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[C_MAX], pod.req[C_MAX], pod.reqv[C_MAX]);
+    double sum = 0;
+    for (int c = 0; c < nc; ++c)
+      sum += (double)score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[c], pod.req[c], pod.reqv[c]);
+    return f2i(sum / (double)nc);
   }
-  if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return 0;
-  if (scope_pod) return score_each_numa<Z, R>(node_zs, cfg, pod.req_mask[C_MAX], pod.req[C_MAX]);
-  double sum = 0;
-  for (int c = 0; c < nc; ++c) sum += (double)score_each_numa<Z, R>(node_zs, cfg, pod.req_mask[c], pod.req[c]);
-  return f2i(sum / (double)nc);
 }
 
 struct NrtNodeCols {
@@ -386,8 +407,8 @@ struct NrtPodCols {
   const int64_t* req;       // [P][9][Rs]
 };
 
-template <int Z, int R, class OutT, int PT>
-__global__ void __launch_bounds__(128)
+template <int Z, int R, int SC, class OutT, int PT>
+__global__ void __launch_bounds__(128, (Z <= 4 ? 3 : 1))
 nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict__ upstream, int words, int N,
            int Npad, int P, OutT* __restrict__ out, uint32_t* __restrict__ feas_out32, uint8_t* __restrict__ reasons) {
   __shared__ PodS<R> sp[PT];
@@ -396,7 +417,9 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
   // stage the pod tile
   for (int i = threadIdx.x; i < pend * (C_MAX + 1) * R; i += 128) {
     const int pp = i / ((C_MAX + 1) * R), rest = i % ((C_MAX + 1) * R), c = rest / R, r = rest % R;
-    sp[pp].req[c][r] = r < nc.Rs ? pc.req[((size_t)(p0 + pp) * (C_MAX + 1) + c) * nc.Rs + r] : 0;
+    const int64_t q = r < nc.Rs ? pc.req[((size_t)(p0 + pp) * (C_MAX + 1) + c) * nc.Rs + r] : 0;
+    sp[pp].req[c][r] = q;
+    sp[pp].reqv[c][r] = q >= 0 ? (q + 999) / 1000 : -((-q) / 1000);
   }
   for (int i = threadIdx.x; i < pend; i += 128) {
     const int p = p0 + i;
@@ -427,9 +450,11 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
 #pragma unroll
     for (int r = 0; r < R; ++r)
       zs.avail[z][r] = (in && z < nc.Zs && r < nc.Rs) ? nc.avail[((size_t)z * nc.Rs + r) * Npad + n] : 0;
+    if constexpr (SC == 2) {
 #pragma unroll
-    for (int z2 = 0; z2 < Z; ++z2)
-      cost[z][z2] = (in && nc.cost && z < nc.Zs && z2 < nc.Zs) ? nc.cost[((size_t)z * nc.Zs + z2) * Npad + n] : -1;
+      for (int z2 = 0; z2 < Z; ++z2)
+        cost[z][z2] = (in && nc.cost && z < nc.Zs && z2 < nc.Zs) ? nc.cost[((size_t)z * nc.Zs + z2) * Npad + n] : -1;
+    }
   }
   __syncthreads();
   if (!in) return;
@@ -446,7 +471,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
       const bool up = upstream ? ((upstream[(size_t)p * words + word] >> (n & 63)) & 1ull) : true;
       feasible = reason == 0 && up;
       if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
-      if (feasible) score = nrt_score<Z, R>(zs, cost, nflags, max_numa, cfg, pod);
+      if (feasible) score = nrt_score<Z, R, SC>(zs, cost, nflags, max_numa, cfg, pod);
     }
     const uint32_t fw = __ballot_sync(0xffffffffu, feasible);
     if (lane == 0) feas_out32[((size_t)p * words + word) * 2 + half] = fw;
@@ -455,24 +480,31 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
   }
 }
 
-template <int Z, int R>
-int launch(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc, const NrtCfg& cfg) {
+template <int Z, int R, int SC>
+int launch_sc(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc, const NrtCfg& cfg) {
   constexpr int PT = 16;
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
   const uint64_t* up = c->upstream_mask();
   dim3 grid((Npad + 127) / 128, (P + PT - 1) / PT);
   if (dtype == B200S_OUT_I64)
-    nrt_kernel<Z, R, int64_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
+    nrt_kernel<Z, R, SC, int64_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
                                                                o.scores.as<int64_t>(), o.feas.as<uint32_t>(),
                                                                o.reasons.as<uint8_t>());
   else
-    nrt_kernel<Z, R, uint8_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
+    nrt_kernel<Z, R, SC, uint8_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
                                                                o.scores.as<uint8_t>(), o.feas.as<uint32_t>(),
                                                                o.reasons.as<uint8_t>());
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
   return B200S_OK;
+}
+
+template <int Z, int R>
+int launch(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc, const NrtCfg& cfg) {
+  if (cfg.strategy == B200S_NRT_LEAST_NUMA_NODES) return launch_sc<Z, R, 2>(c, dtype, nc, pc, cfg);
+  if (cfg.strategy == B200S_NRT_BALANCED_ALLOCATION) return launch_sc<Z, R, 1>(c, dtype, nc, pc, cfg);
+  return launch_sc<Z, R, 0>(c, dtype, nc, pc, cfg);
 }
 
 }  // namespace

@@ -57,6 +57,26 @@ __device__ double go_pow(double x, double y) {
   return pow(x, y);  // general exponent: <= 2 ulp from Go's software Pow; tolerance rule SURVEY §8c(ii)
 }
 
+// x / d for a divisor whose correctly rounded reciprocal r = RN(1/d) is hoisted out of the pod loop:
+// q0 = RN(x*r); rem = x - q0*d exactly (FMA); q1 = RN(q0 + rem*r) is the correctly rounded quotient
+// (Markstein's division-by-invariant; normal range, d finite and non-zero).  Replaces the ~35-instruction
+// IEEE division sequence by 3 fp64 ops and stays bit-identical to Go's x/d — checked exhaustively against
+// the hardware division by b200s_debug_div_check (tests/test_gpu_parity.py).
+__device__ __forceinline__ double div_inv(double x, double d, double r) {
+  const double q0 = x * r;
+  const double rem = __fma_rn(-q0, d, x);
+  return __fma_rn(rem, r, q0);
+}
+
+__global__ void div_check_kernel(const double* __restrict__ x, const double* __restrict__ d, int n,
+                                 unsigned long long* __restrict__ mismatches) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double want = x[i] / d[i];
+  const double got = div_inv(x[i], d[i], 1.0 / d[i]);
+  if (__double_as_longlong(want) != __double_as_longlong(got) && !(want != want && got != got)) atomicAdd(mismatches, 1ull);
+}
+
 template <class OutT, int NPT, int PT>
 __global__ void __launch_bounds__(256)
 tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, const int64_t* __restrict__ missing,
@@ -68,13 +88,14 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
   const int p0 = blockIdx.y * PT;
   for (int i = threadIdx.x; i < PT; i += 256)
     if (p0 + i < P) s_pod[i] = (double)pod_cpu[p0 + i];
-  double ncap[NPT], base[NPT], miss[NPT];
+  double ncap[NPT], rcap[NPT], base[NPT], miss[NPT];
   uint32_t ok = 0;
   if (nb < Npad) {
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
       int n = nb + j;
       ncap[j] = (double)cap[n];
+      rcap[j] = 1.0 / ncap[j];
       base[j] = (util[n] / 100) * ncap[j];  // nodeCPUUtilMillis, :147
       miss[j] = (double)missing[n];
       uint8_t f = flags[n];
@@ -85,6 +106,9 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
   if (nb >= Npad) return;
   const double t = (double)target;
   const double hundred_minus_t = 100 - t;
+  const double r_t = 1.0 / t, r_hmt = 1.0 / hundred_minus_t;
+  // the reciprocal trick needs finite non-zero divisors; target 0 or 100 keeps the plain IEEE division
+  const bool fast_t = t >= 1 && t <= 99;
   const int pend = min(PT, P - p0);
   OutT* orow = out + (size_t)p0 * Npad + nb;
   for (int pp = 0; pp < pend; ++pp, orow += Npad) {
@@ -93,12 +117,14 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
       double predicted = 0;
-      if (ncap[j] != 0) predicted = 100 * (base[j] + pc + miss[j]) / ncap[j];  // :170-173
+      if (ncap[j] != 0) predicted = div_inv(100 * (base[j] + pc + miss[j]), ncap[j], rcap[j]);  // :170-173
       double s;
       if (predicted > t) {
-        s = predicted > 100 ? 0.0 : go_round(t * (100 - predicted) / hundred_minus_t);  // :174-181
+        const double num = t * (100 - predicted);
+        s = predicted > 100 ? 0.0 : go_round(fast_t ? div_inv(num, hundred_minus_t, r_hmt) : num / hundred_minus_t);  // :174-181
       } else {
-        s = go_round(hundred_minus_t * predicted / t + t);  // :183-184
+        const double num = hundred_minus_t * predicted;
+        s = go_round((fast_t ? div_inv(num, t, r_t) : num / t) + t);  // :183-184
       }
       q[j] = ((ok >> j) & 1u) ? go_f2i(s) : 0;
     }
@@ -107,7 +133,7 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
 }
 
 struct LvrbNode {
-  double avg, cap, sigma;  // clamped usedAvg, capacity, final sigma (after Pow, margin, clamp)
+  double avg, cap, rcap, sigma;  // clamped usedAvg, capacity, RN(1/capacity), final sigma (after Pow, margin, clamp)
 };
 
 // Node-only part of computeScore (analysis.go:34-54) for one resource.
@@ -115,6 +141,7 @@ __device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, 
                                               double sens) {
   LvrbNode r;
   r.cap = cap;
+  r.rcap = 1.0 / cap;
   double used_avg = util_avg * cap / 100;  // resourcestats.go:68
   double used_std = util_std * cap / 100;  // :69
   r.avg = go_max(go_min(used_avg, cap), 0);
@@ -133,7 +160,7 @@ __device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, 
 
 __device__ __forceinline__ double lvrb_res_score(const LvrbNode& nd, double req) {
   if (nd.cap <= 0) return 0;  // analysis.go:35-38
-  double mu = (nd.avg + req) / nd.cap;
+  double mu = div_inv(nd.avg + req, nd.cap, nd.rcap);
   mu = go_max(go_min(mu, 1), 0);
   double risk = (mu + nd.sigma) / 2;
   return (1. - risk) * 100.0;
@@ -187,6 +214,26 @@ lvrb_kernel(const double* __restrict__ f64, const int64_t* __restrict__ i64, con
 }
 
 }  // namespace
+
+// Test hook: counts i with div_inv(x[i], d[i], 1/d[i]) != x[i]/d[i] (bit compare) on the device.
+int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint64_t* mismatches) {
+  DevBuf bx, bd, bm;
+  B200S_CUDA_TRY(c, bx.ensure((size_t)n * 8));
+  B200S_CUDA_TRY(c, bd.ensure((size_t)n * 8));
+  B200S_CUDA_TRY(c, bm.ensure(8));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(bx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(bd.p, d, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemsetAsync(bm.p, 0, 8, c->stream));
+  div_check_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(bx.as<double>(), bd.as<double>(), n,
+                                                           bm.as<unsigned long long>());
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(mismatches, bm.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  bx.release();
+  bd.release();
+  bm.release();
+  return B200S_OK;
+}
 
 int tlp_eval(b200s_ctx* c, int dtype) {
   if (!c->has_tlp) return c->set_err(B200S_ERR_STATE, "TargetLoadPacking: snapshot has no TLP columns");

@@ -34,7 +34,7 @@ EXPORTS = [
     "b200s_pods_upload", "b200s_eval", "b200s_fetch_scores", "b200s_fetch_feasible", "b200s_fetch_reasons",
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
-    "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time",
+    "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
 ]
 
 
@@ -178,6 +178,12 @@ class Engine:
         ms, n = C.c_double(), C.c_uint64()
         self._chk(self.lib.b200s_kernel_time(self.ctx, C.c_int(plugin), C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
+
+    def debug_div_check(self, x, d) -> int:
+        x = _arr(x, np.float64); d = _arr(d, np.float64)
+        out = C.c_uint64()
+        self._chk(self.lib.b200s_debug_div_check(self.ctx, _ptr(x), _ptr(d), C.c_int32(len(x)), C.byref(out)))
+        return int(out.value)
 
     def pinned(self, nbytes) -> PinnedBuffer:
         return PinnedBuffer(self.lib, nbytes)
