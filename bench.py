@@ -119,6 +119,77 @@ def cpu_sample(orc, cols, feas, sample_pods, threads):
     return sample_pods * N / dt, dt
 
 
+def cpu_gofaithful(orc, cols, feas, pods, sample_pods, threads):
+    """Times the Go-faithful restatement (oracle/gofaithful.cpp: per-call maps, string switches, NodeScoreList —
+    the structure the Go scheduler actually executes) on sample_pods x N, `threads` cycles in parallel."""
+    N = len(cols[0])
+    t0 = time.perf_counter()
+    orc.gofaithful_alloc_batch(cols, ["cpu", "memory"], WEIGHTS, MODE_MOST, pods["req_cpu_milli"][:sample_pods],
+                               pods["req_mem_bytes"][:sample_pods], np.ascontiguousarray(feas[:sample_pods]), pitch=N,
+                               threads=threads)
+    dt = time.perf_counter() - t0
+    return sample_pods * N / dt, dt
+
+
+def cycle_latency(E, synth, device, N, cycles=1000):
+    """Scheduling-cycle latency (BASELINE.json metric 2): P = 1 pod, snapshot already resident; per cycle the
+    pod columns go host->device, every enabled plugin is evaluated over all N nodes, and the result comes back.
+    Wall clock around the C-ABI calls (that is what the scheduler goroutine waits for)."""
+    seed = 0xB2005EED + 5
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, 1)
+    tri = synth.gen_trimaran(seed, nodes)
+    nn, npods = synth.gen_nrt(seed, N, 1, Z=4)
+    net = synth.gen_netoh(seed, N, 1)
+    net["score_equally"][:] = 0
+    if net["dep_offset"][1] == 0:  # make sure the one pod has dependencies
+        net = synth.gen_netoh(seed + 1, N, 1)
+        net["score_equally"][:] = 0
+    eng = E.Engine(device)
+    eng.snapshot_begin(N)
+    eng.snapshot_allocatable([nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]])
+    eng.snapshot_tlp(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"])
+    eng.snapshot_lvrb(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"], nodes["alloc_cpu_milli"],
+                      nodes["alloc_mem_bytes"], tri["lvrb_flags"])
+    eng.snapshot_nrt(nn)
+    eng.snapshot_network_overhead(net["region_all"], net["zone_all"], net["zone_cost"], net["region_cost"])
+    eng.snapshot_commit()
+    eng.config_allocatable(MODE_MOST, WEIGHTS)
+    eng.config_tlp(40)
+    eng.config_lvrb(1.0, 1.0)
+    eng.config_nrt(E.NRT_LEAST_ALLOCATED, [1, 1, 1, 1])
+    cols = dict(tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"], lvrb_req_cpu_milli=pods["req_cpu_milli"],
+                lvrb_req_mem_bytes=pods["req_mem_bytes"], nrt=npods, netoh=net)
+    batch, keep = eng.make_batch(1, **cols)
+    out = eng.pinned(eng.Npad)
+    row = out.view(np.uint8, (1, eng.Npad))
+
+    def p50(fn):
+        for _ in range(20):
+            fn()
+        ts = []
+        for _ in range(cycles):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e6
+        return {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99))}
+
+    res = {"nodes": N, "pods_per_cycle": 1, "cycles": cycles}
+    res["NodeResourcesAllocatable"] = p50(lambda: eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, E.OUT_U8, row))
+    w = [1, 1, 1, 1, 5]
+
+    def combined():
+        eng.lib.b200s_pods_upload(eng.ctx, batch)
+        eng.P = 1
+        eng.eval_combined(0b11111, w, k=1, write_total=False)
+        eng.fetch_topk()
+
+    res["all_five_plugins_top1"] = p50(combined)
+    out.free()
+    eng.close()
+    return res
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle port; the Go toolchain is absent) alone."""
     if rank != 0:
@@ -132,17 +203,21 @@ def run_reference(args, rank, world):
     seed = 0xB2005EED + CONFIG_NO
     N = N_NODES
     npad = E.npad_of(N)
+    from scheduler_plugins_b200 import synth
+
     threads = os.cpu_count() or 1
-    sample = max(threads * 64, 256)
+    sample = max(threads * 4, 64)  # ~0.1 s per thread per step at ~2 us per Score call
     nodes, feas = make_inputs(seed, sample, N, npad, 0)
+    pods = synth.gen_pods(seed, sample)
     cols = [nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]]
     for _ in range(args.warmup):
-        cpu_sample(orc, cols, feas, sample, threads)
+        cpu_gofaithful(orc, cols, feas, pods, sample, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_sample(orc, cols, feas, sample, threads)
+        cpu_gofaithful(orc, cols, feas, pods, sample, threads)
     dt = (time.perf_counter() - t0) / args.steps
     val = sample * N / dt
+    soa_val, _ = cpu_sample(orc, cols, feas, sample, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -150,8 +225,11 @@ def run_reference(args, rank, world):
         "config": {"workload": "configs[1]: NodeResourcesAllocatable Most + NormalizeScore, 10k pods x 50k nodes/GPU",
                    "note": f"each step = bounded sample of {sample} pods x {N} nodes of that workload"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} pods x {N} nodes per step, {threads} threads over pods; C port of "
-                                   "allocatable.go:63-168 (Go toolchain absent, reference not runnable)"},
+                         "sample": f"{sample} pods x {N} nodes per step, {threads} scheduling cycles in parallel; "
+                                   "Go-faithful C++ restatement of allocatable.go:63-168 + resource_allocation.go:49-131 "
+                                   "(per-call maps, string switches, NodeScoreList; Go toolchain absent, reference not runnable)",
+                         "soa_port_value": soa_val,
+                         "soa_port_note": "flat-column C port (oracle/alloc.c), same threads — the layout-only speed-up"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -165,6 +243,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pods", type=int, default=P_PODS)
     ap.add_argument("--nodes", type=int, default=N_NODES)
+    ap.add_argument("--cycles", type=int, default=1000, help="P=1 scheduling cycles for the latency leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip the e2e and CPU legs")
     args = ap.parse_args()
@@ -320,16 +399,27 @@ def main():
     if rank == 0 and world == 1:
         from oracle import pyoracle as orc
 
+        from scheduler_plugins_b200 import synth as _synth
+
         sample = 96
         v1, dt1 = cpu_sample(orc, cols, feas_np, sample, 1)
+        vg, dtg = cpu_gofaithful(orc, cols, feas_np, _synth.gen_pods(seed, 16), 16, 1)
         # checker, not product: the sampled rows of the e2e result equal the oracle's
         want = orc.alloc_batch(cols, WEIGHTS, MODE_MOST, 4, np.ascontiguousarray(feas_np[:4]), pitch=npad)
         assert np.array_equal(out8[:4].astype(np.int64), want), "GPU result differs from the oracle"
         cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{sample} pods x {N} nodes, scalar single-thread C port of allocatable.go:63-168 "
                          f"({dt1:.2f} s); Go toolchain absent so the reference itself cannot run",
-               "host_cores": os.cpu_count()}
+               "host_cores": os.cpu_count(),
+               "gofaithful_value": vg,
+               "gofaithful_note": f"Go-faithful per-call restatement (oracle/gofaithful.cpp), 16 pods x {N} nodes, 1 thread "
+                                  f"({dtg:.2f} s)"}
 
+    cycle = None
+    if rank == 0 and world == 1:
+        from scheduler_plugins_b200 import synth
+
+        cycle = cycle_latency(E, synth, local, N, args.cycles)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -346,6 +436,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "cycle_latency": cycle,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -39,6 +39,13 @@ void orc_alloc_normalize(int64_t* scores, int n);
 void orc_alloc_batch(const int64_t* const* cols, int R, int N, const int64_t* w, int mode, int P,
                      const uint64_t* feasible, int words, int64_t* out, int pitch);
 
+/* "Go-faithful" CPU baseline (oracle/gofaithful.cpp): the same result through the reference's per-call
+ * structure (maps, string switches, NodeScoreList), `threads` scheduling cycles in parallel. */
+void orc_gofaithful_alloc_batch(const int64_t* const* cols, const char* const* res_names, int R, int N,
+                                const int64_t* w, int mode, int P, const int64_t* pod_cpu_milli,
+                                const int64_t* pod_mem_bytes, const uint64_t* feasible, int words, int64_t* out,
+                                int pitch, int threads);
+
 /* ---- TargetLoadPacking (pkg/trimaran/targetloadpacking) ---- */
 int64_t orc_tlp_score(double cpu_util_pct, int64_t cap_milli, int64_t missing_milli, uint8_t flags,
                       int64_t pod_cpu_milli, int64_t target_pct);

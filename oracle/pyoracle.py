@@ -65,6 +65,24 @@ def alloc_batch(cols, weights, mode, P, feasible_words=None, pitch=None):
     return out
 
 
+def gofaithful_alloc_batch(cols, res_names, weights, mode, pod_cpu_milli, pod_mem_bytes, feasible_words=None,
+                           pitch=None, threads=1):
+    """NodeResourcesAllocatable through the reference's per-call structure (oracle/gofaithful.cpp)."""
+    cols = [_c(c, np.int64) for c in cols]
+    N, P = len(cols[0]), len(pod_cpu_milli)
+    pitch = pitch or N
+    w = _c(weights, np.int64)
+    arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    names = (C.c_char_p * len(cols))(*[n.encode() for n in res_names])
+    pc = _c(pod_cpu_milli, np.int64); pm = _c(pod_mem_bytes, np.int64)
+    out = np.zeros((P, pitch), dtype=np.int64)
+    fw = None if feasible_words is None else _c(feasible_words, np.uint64)
+    words = 0 if fw is None else fw.shape[1]
+    lib().orc_gofaithful_alloc_batch(arr, names, C.c_int(len(cols)), C.c_int(N), _p(w), C.c_int(mode), C.c_int(P),
+                                     _p(pc), _p(pm), _p(fw), C.c_int(words), _p(out), C.c_int(pitch), C.c_int(threads))
+    return out
+
+
 def tlp_score(util, cap, missing, flags, pod_cpu, target=40) -> int:
     return int(lib().orc_tlp_score(util, cap, missing, flags, pod_cpu, target))
 

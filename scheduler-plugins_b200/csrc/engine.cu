@@ -450,7 +450,7 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     c->netoh_total_deps = total;
   }
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
-  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& o : c->out) o.valid = false;
   c->total_valid = c->topk_valid = false;
   c->pods_valid = true;
@@ -489,7 +489,7 @@ static int fetch(b200s_ctx* c, const DevBuf& src, void* out, size_t bytes, size_
   if (bytes < want) return c->set_err(B200S_ERR_INVALID, std::string(what) + ": output buffer too small");
   if (want == 0) return B200S_OK;
   B200S_CUDA_TRY(c, cudaMemcpyAsync(out, src.p, want, cudaMemcpyDeviceToHost, c->stream));
-  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return B200S_OK;
 }
 
@@ -598,13 +598,22 @@ int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* 
                       void* scores_out, uint64_t* feasible_out, uint8_t* reasons_out) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
-  B200S_TRY(pods_upload_locked(c, batch));
-  B200S_TRY(eval_locked(c, plugin, dtype));
+  // one stream, one synchronisation at the very end: H2D copies, kernels and D2H copies are queued back to back
+  struct Defer {
+    b200s_ctx* c;
+    explicit Defer(b200s_ctx* x) : c(x) { c->defer_sync = true; }
+    ~Defer() { c->defer_sync = false; }
+  } defer(c);
+  int rc = pods_upload_locked(c, batch);
+  if (rc == B200S_OK) rc = eval_locked(c, plugin, dtype);
   size_t elems = (size_t)c->P * c->Npad;
-  B200S_TRY(fetch_scores_locked(c, plugin, scores_out, elems * (dtype == B200S_OUT_I64 ? 8 : 1)));
-  if (feasible_out && c->out[plugin].has_feas)
-    B200S_TRY(fetch_feasible_locked(c, plugin, feasible_out, (size_t)c->P * (c->Npad / 64) * 8));
-  if (reasons_out && c->out[plugin].has_reasons) B200S_TRY(fetch_reasons_locked(c, plugin, reasons_out, elems));
+  if (rc == B200S_OK) rc = fetch_scores_locked(c, plugin, scores_out, elems * (dtype == B200S_OUT_I64 ? 8 : 1));
+  if (rc == B200S_OK && feasible_out && c->out[plugin].has_feas)
+    rc = fetch_feasible_locked(c, plugin, feasible_out, (size_t)c->P * (c->Npad / 64) * 8);
+  if (rc == B200S_OK && reasons_out && c->out[plugin].has_reasons) rc = fetch_reasons_locked(c, plugin, reasons_out, elems);
+  cudaError_t e = cudaStreamSynchronize(c->stream);  // also on the error path: inputs must not be in flight on return
+  if (rc != B200S_OK) return rc;
+  if (e != cudaSuccess) return c->set_err(B200S_ERR_CUDA, std::string("score_batch: ") + cudaGetErrorString(e));
   return B200S_OK;
 }
 

@@ -127,6 +127,7 @@ struct b200s_ctx {
   bool has_feasible = false;
   b200s::DevBuf feasible_in;  // [P][Npad/64]
   // eval_combined chains the filters: each plugin's "upstream" set is what the previous filters left
+  bool defer_sync = false;  // inside b200s_score_batch: queue everything, synchronise once at the end
   const uint64_t* mask_override = nullptr;
   const uint64_t* upstream_mask() const {
     if (mask_override) return mask_override;

@@ -144,22 +144,23 @@ __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t 
   if (!(nflags & B200S_NRT_NODE_FRESH)) return B200S_REASON_NRT_INVALID_TOPOLOGY;
   if (!(nflags & B200S_NRT_NODE_HAS_NRT)) return B200S_REASON_OK;
   if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return B200S_REASON_OK;
-  int numa_id = 0;
-  if (nflags & B200S_NRT_NODE_SCOPE_POD) {
-    return available_in_any<Z, R>(node_zs, node_res_mask, cfg, pod.qos, pod.req_mask[C_MAX], pod.req[C_MAX], numa_id)
-               ? B200S_REASON_OK
-               : B200S_REASON_NRT_ALIGN_POD;
-  }
+  // One loop for both scopes (one call site of the unrolled zone x resource test keeps the kernel's
+  // code small — the round-1 profile was instruction-fetch bound): pod scope = a single step on the
+  // pod-effective request (slot C_MAX, singleNUMAPodLevelHandler :162-173); container scope = init
+  // containers without subtraction, then app containers with it (:39-78).
+  const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
+  const int n_init = pod.n_init, steps = scope_pod ? 1 : n_init + pod.n_app;
   Zones<Z, R> zs = node_zs;  // working copy: app containers subtract what they take
-  for (int c = 0; c < pod.n_init; ++c) {
-    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, pod.req_mask[c], pod.req[c], numa_id))
-      return pod.kind[c] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT;
-  }
-  const int nc = pod.n_init + pod.n_app;
-  for (int c = pod.n_init; c < nc; ++c) {
+  for (int s = 0; s < steps; ++s) {
+    const int c = scope_pod ? C_MAX : s;
     const uint32_t rm = pod.req_mask[c];
-    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, rm, pod.req[c], numa_id))
-      return B200S_REASON_NRT_ALIGN_CONTAINER;
+    int numa_id = 0;
+    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, rm, pod.req[c], numa_id)) {
+      if (scope_pod) return B200S_REASON_NRT_ALIGN_POD;
+      if (s >= n_init) return B200S_REASON_NRT_ALIGN_CONTAINER;
+      return pod.kind[c] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT;
+    }
+    if (scope_pod || s < n_init) continue;
     // subtractResourcesFromNUMANodeList (numaresources.go:145-182)
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
@@ -338,24 +339,23 @@ __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z
   if (!(nflags & B200S_NRT_NODE_FRESH) || !(nflags & B200S_NRT_NODE_HAS_NRT)) return 0;
   const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
   const int nc = pod.n_init + pod.n_app;
+  const int steps = scope_pod ? 1 : nc;  // pod scope: one step on the pod-effective request (slot C_MAX)
   if constexpr (SC == 2) {
-    uint32_t mask = 0;
-    bool is_min = false;
-    if (scope_pod) {
-      if (only_non_numa<Z, R>(node_zs, pod.req_mask[C_MAX])) return 100;
-      const int k = numa_nodes_required<Z, R>(node_zs, cost, cfg, pod.qos, pod.req_mask[C_MAX], pod.req[C_MAX], mask, is_min);
-      return k == 0 ? 0 : normalize_least_numa(k, is_min, max_numa);
-    }
+    // leastNUMAPodScopeScore :73-89 / leastNUMAContainerScopeScore :35-71 as one loop
     Zones<Z, R> zs = node_zs;
     int max_count = 0;
     bool all_min = true;
-    for (int c = 0; c < nc; ++c) {
+    for (int s = 0; s < steps; ++s) {
+      const int c = scope_pod ? C_MAX : s;
       const uint32_t rm = pod.req_mask[c];
       if (only_non_numa<Z, R>(zs, rm)) continue;
+      uint32_t mask = 0;
+      bool is_min = false;
       const int k = numa_nodes_required<Z, R>(zs, cost, cfg, pod.qos, rm, pod.req[c], mask, is_min);
       if (k == 0) return 0;
       if (!is_min) all_min = false;
       if (k > max_count) max_count = k;
+      if (scope_pod) break;
       // subtractFromNUMAs (numaresources.go:184-215)
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -379,11 +379,15 @@ __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z
     return max_count == 0 ? 100 : normalize_least_numa(max_count, all_min, max_numa);
   } else {
     if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return 0;
-    if (scope_pod) return score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[C_MAX], pod.req[C_MAX], pod.reqv[C_MAX]);
+    // podScopeScore :142-150 / containerScopeScore :152-165 (mean over init + app, no subtraction)
     double sum = 0;
-    for (int c = 0; c < nc; ++c)
-      sum += (double)score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[c], pod.req[c], pod.reqv[c]);
-    return f2i(sum / (double)nc);
+    int64_t last = 0;
+    for (int s = 0; s < steps; ++s) {
+      const int c = scope_pod ? C_MAX : s;
+      last = score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[c], pod.req[c], pod.reqv[c]);
+      sum += (double)last;
+    }
+    return scope_pod ? last : f2i(sum / (double)nc);
   }
 }
 
