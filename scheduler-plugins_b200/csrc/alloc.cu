@@ -197,7 +197,7 @@ alloc_norm_kernel(const int64_t* __restrict__ raw, const NormParam* __restrict__
 int build_norm_params(b200s_ctx* c, int P) {
   B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
   if (P == 0) return B200S_OK;
-  norm_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P,
+  norm_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(c->pod_lo.as<int64_t>(), c->pod_lo.as<int64_t>() + P, P,
                                                               c->norm_params.as<NormParam>());
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
@@ -246,18 +246,18 @@ int alloc_eval(b200s_ctx* c, int dtype) {
     return B200S_OK;
   }
   B200S_TRY(alloc_prepare(c));
-  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
-  B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));  // [lo | hi] contiguous: one all-reduce when sharded
+  int64_t* const lo_buf = c->pod_lo.as<int64_t>();
+  int64_t* const hi_buf = lo_buf + P;
   const uint64_t* feas = c->upstream_mask();
   {
     int threads = 128, warps_per_block = threads / 32;
     alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
-        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, c->pod_lo.as<int64_t>(),
-        c->pod_hi.as<int64_t>());
+        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo_buf, hi_buf);
     c->launches++;
     B200S_CUDA_TRY(c, cudaGetLastError());
   }
-  B200S_TRY(comm_allreduce_minmax(c, c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P));
+  B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
   B200S_TRY(build_norm_params(c, P));
   PluginOut& o = c->out[B200S_PLUGIN_ALLOCATABLE];
   KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);

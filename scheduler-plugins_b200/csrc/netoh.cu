@@ -251,8 +251,9 @@ int netoh_eval(b200s_ctx* c, int dtype) {
   }
   B200S_CUDA_TRY(c, c->raw_scores.ensure((size_t)P * Npad * 8));
   if (c->netoh_want_counts) B200S_CUDA_TRY(c, c->netoh_counts.ensure((size_t)P * Npad * 4));
-  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 8));
-  B200S_CUDA_TRY(c, c->pod_hi.ensure((size_t)P * 8));
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));  // [lo | hi] contiguous: one all-reduce when sharded
+  int64_t* const lo_buf = c->pod_lo.as<int64_t>();
+  int64_t* const hi_buf = lo_buf + P;
   B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
   Topo t{c->netoh_zone_cost.as<int64_t>(), c->netoh_region_cost.as<int64_t>(), c->netoh_K};
   constexpr int PT = 32;
@@ -268,11 +269,11 @@ int netoh_eval(b200s_ctx* c, int dtype) {
     B200S_CUDA_TRY(c, cudaGetLastError());
   }
   row_minmax_kernel<<<P, 256, 0, c->stream>>>(c->raw_scores.as<int64_t>(), o.feas.as<uint64_t>(), words, Npad,
-                                              c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>());
+                                              lo_buf, hi_buf);
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
-  B200S_TRY(comm_allreduce_minmax(c, c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P));
-  netoh_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(c->pod_lo.as<int64_t>(), c->pod_hi.as<int64_t>(), P,
+  B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
+  netoh_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(lo_buf, hi_buf, P,
                                                                c->norm_params.as<NormParam>());
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
