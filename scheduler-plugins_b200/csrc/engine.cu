@@ -2,8 +2,10 @@
 // include/b200sched.h.  Kernels live in alloc.cu / trimaran.cu / nrt.cu / netoh.cu / combined.cu.
 #include "engine.h"
 
+#include <algorithm>
 #include <cstring>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 using namespace b200s;
@@ -100,7 +102,9 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->nrt_pod_kind,    &c->nrt_pod_req_mask, &c->nrt_pod_req,      &c->netoh_equal,
                     &c->netoh_dep_off,   &c->netoh_deps,       &c->pod_lo,           &c->pod_hi,
                     &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
-                    &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts};
+                    &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts,
+                    &c->netoh_pair_id,   &c->netoh_pair_r,     &c->netoh_pair_z,     &c->netoh_pair_cost,
+                    &c->netoh_pair_sv};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();
@@ -309,6 +313,33 @@ int b200s_snapshot_network_overhead(b200s_ctx* c, const uint16_t* region_id, con
   B200S_CUDA_TRY(c, c->netoh_region_cost.ensure(kk * 8));
   B200S_TRY(upload_col<uint16_t>(c, c->netoh_region, 0, region_id, c->N, c->Npad));
   B200S_TRY(upload_col<uint16_t>(c, c->netoh_zone, 0, zone_id, c->N, c->Npad));
+  {  // pair dictionary (host side of the flattening, O(N))
+    std::vector<int32_t> pid(np, 0);
+    std::vector<uint16_t> pr, pz;
+    std::unordered_map<uint32_t, int32_t> dict;
+    for (int i = 0; i < c->N; ++i) {
+      const uint32_t key = ((uint32_t)region_id[i] << 16) | zone_id[i];
+      auto it = dict.find(key);
+      if (it == dict.end()) {
+        it = dict.emplace(key, (int32_t)pr.size()).first;
+        pr.push_back(region_id[i]);
+        pz.push_back(zone_id[i]);
+      }
+      pid[i] = it->second;
+    }
+    if (pr.empty()) {
+      pr.push_back(0);
+      pz.push_back(0);
+    }
+    c->netoh_NQ = (int)pr.size();
+    B200S_CUDA_TRY(c, c->netoh_pair_id.ensure(np * 4));
+    B200S_CUDA_TRY(c, c->netoh_pair_r.ensure(pr.size() * 2));
+    B200S_CUDA_TRY(c, c->netoh_pair_z.ensure(pz.size() * 2));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_id.p, pid.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_r.p, pr.data(), pr.size() * 2, cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_z.p, pz.data(), pz.size() * 2, cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the vectors die at the end of this scope
+  }
   B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_zone_cost.p, zone_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_region_cost.p, region_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -448,6 +479,8 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
       B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_deps.p, q->deps, (size_t)total * sizeof(b200s_netoh_dep),
                                         cudaMemcpyHostToDevice, c->stream));
     c->netoh_total_deps = total;
+    c->netoh_max_deps = 0;
+    for (int p = 0; p < P; ++p) c->netoh_max_deps = std::max(c->netoh_max_deps, q->dep_offset[p + 1] - q->dep_offset[p]);
   }
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
   if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));

@@ -120,6 +120,11 @@ struct b200s_ctx {
   bool has_netoh = false;
   int netoh_K = 0;
   b200s::DevBuf netoh_region, netoh_zone, netoh_zone_cost, netoh_region_cost;
+  // distinct (region, zone) label pairs of the snapshot: the cost/filter result of a node depends on the node
+  // only through its pair (plus the few dependencies hosted on the node itself)
+  int netoh_NQ = 0;
+  b200s::DevBuf netoh_pair_id, netoh_pair_r, netoh_pair_z;  // [Npad] int32, [NQ] u16, [NQ] u16
+  b200s::DevBuf netoh_pair_cost, netoh_pair_sv;              // [P][NQ] int64 cost, u32 satisfied | violated << 16
 
   // ---- pods ----
   bool pods_valid = false;
@@ -138,7 +143,7 @@ struct b200s_ctx {
   b200s::DevBuf nrt_pod_qos, nrt_pod_flags, nrt_pod_ninit, nrt_pod_napp, nrt_pod_kind, nrt_pod_req_mask,
       nrt_pod_req;
   b200s::DevBuf netoh_equal, netoh_dep_off, netoh_deps;
-  int netoh_total_deps = 0;
+  int netoh_total_deps = 0, netoh_max_deps = 0;
 
   // ---- per-pod scratch ----
   b200s::DevBuf pod_lo, pod_hi;  // [P] int64

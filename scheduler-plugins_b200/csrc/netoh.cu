@@ -237,6 +237,193 @@ netoh_norm_kernel(const int64_t* __restrict__ raw, const uint64_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path (B200 design, not in the reference): (satisfied, violated, cost) of a (pod, node) depend on
+// the node only through its (region, zone) label pair — except for the dependencies hosted on that very
+// node.  So per pod the dependency loop runs once per distinct PAIR (tens) instead of once per NODE
+// (hundreds of thousands); the P x N passes become a 16-byte table lookup, and the rare hosted nodes
+// (a per-tile shared-memory bitmap marks them) are evaluated directly.  Two light passes (min/max, then
+// normalise + store) replace the raw-matrix round trip: HBM traffic = the output matrix.
+__global__ void netoh_pair_kernel(Topo t, const uint16_t* __restrict__ pair_r, const uint16_t* __restrict__ pair_z, int NQ,
+                                  const uint8_t* __restrict__ equal, const int32_t* __restrict__ dep_off,
+                                  const b200s_netoh_dep* __restrict__ deps, int P, int64_t* __restrict__ pair_cost,
+                                  uint32_t* __restrict__ pair_sv) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P * NQ) return;
+  const int p = (int)(i / NQ), q = (int)(i % NQ);
+  int64_t s = 0, w = 0, cst = 0;
+  if (!equal[p]) eval_node(t, -1, pair_r[q], pair_z[q], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s, w, cst);
+  pair_cost[i] = cst;
+  pair_sv[i] = (uint32_t)s | ((uint32_t)w << 16);
+}
+
+__global__ void fill_lohi_kernel(int64_t* lo, int64_t* hi, int P) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) {
+    lo[p] = INT64_MAX;  // getMinMaxScores :422-423
+    hi[p] = INT64_MIN;
+  }
+}
+
+// PASS 1: filter verdict, feasibility words, reason codes, per-pod min/max.  PASS 2: normalised scores.
+template <int PASS, class OutT, int PT>
+__global__ void __launch_bounds__(256)
+netoh_fast_kernel(Topo t, const int32_t* __restrict__ pair_id, int NQ, const int64_t* __restrict__ pair_cost,
+                  const uint32_t* __restrict__ pair_sv, int node_off, const uint8_t* __restrict__ equal,
+                  const int32_t* __restrict__ dep_off, const b200s_netoh_dep* __restrict__ deps,
+                  const uint16_t* __restrict__ region, const uint16_t* __restrict__ zone,
+                  const uint64_t* __restrict__ upstream, int words, int N, int Npad, int P, bool apply_filter,
+                  uint64_t* __restrict__ feas, uint8_t* __restrict__ reasons, int64_t* __restrict__ lo,
+                  int64_t* __restrict__ hi, const NormParam* __restrict__ params, OutT* __restrict__ out) {
+  __shared__ uint32_t bm[PT][16];  // hosted-node bitmap of this CTA's 512 nodes, per pod of the tile
+  __shared__ long long s_lo[PT], s_hi[PT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncta = blockIdx.x * 512;
+  const int nbase = ncta + warp * 64;
+  const int p0 = blockIdx.y * PT, pend = min(p0 + PT, P);
+  for (int i = threadIdx.x; i < PT * 16; i += 256) bm[i / 16][i % 16] = 0;
+  if (PASS == 1)
+    for (int i = threadIdx.x; i < PT; i += 256) {
+      s_lo[i] = INT64_MAX;
+      s_hi[i] = INT64_MIN;
+    }
+  __syncthreads();
+  for (int p = p0; p < pend; ++p) {
+    if (equal[p]) continue;
+    const int d0 = dep_off[p], d1 = dep_off[p + 1];
+    for (int i = d0 + threadIdx.x; i < d1; i += 256) {
+      const int local = deps[i].host_node - node_off - ncta;
+      if (local >= 0 && local < 512) atomicOr(&bm[p - p0][local >> 5], 1u << (local & 31));
+    }
+  }
+  __syncthreads();
+  const bool active = nbase < Npad;
+  const int n0 = nbase + lane, n1 = n0 + 32;
+  int q0 = 0, q1 = 0;
+  if (active) {
+    q0 = pair_id[n0];
+    q1 = pair_id[n1];
+  }
+  const bool v0 = active && n0 < N, v1 = active && n1 < N;
+  const int word = nbase >> 6;
+  for (int p = p0; p < pend && active; ++p) {
+    const int pp = p - p0;
+    const bool eq = equal[p] != 0;
+    int64_t c0 = 0, c1 = 0, s0 = 0, w0 = 0, s1 = 0, w1 = 0;
+    if (!eq) {
+      const uint32_t h0 = bm[pp][warp * 2], h1 = bm[pp][warp * 2 + 1];
+      if ((h0 >> lane) & 1u) {  // a dependency is hosted on this very node: evaluate directly
+        eval_node(t, node_off + n0, region[n0], zone[n0], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s0, w0, c0);
+      } else {
+        const size_t k = (size_t)p * NQ + q0;
+        c0 = __ldg(&pair_cost[k]);
+        const uint32_t sv = __ldg(&pair_sv[k]);
+        s0 = sv & 0xffff;
+        w0 = sv >> 16;
+      }
+      if ((h1 >> lane) & 1u) {
+        eval_node(t, node_off + n1, region[n1], zone[n1], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s1, w1, c1);
+      } else {
+        const size_t k = (size_t)p * NQ + q1;
+        c1 = __ldg(&pair_cost[k]);
+        const uint32_t sv = __ldg(&pair_sv[k]);
+        s1 = sv & 0xffff;
+        w1 = sv >> 16;
+      }
+    }
+    if (PASS == 1) {
+      const bool pass0 = v0 && (eq || !(w0 > s0)), pass1 = v1 && (eq || !(w1 > s1));
+      const uint64_t up = upstream ? upstream[(size_t)p * words + word] : ~0ull;
+      const bool f0 = (apply_filter ? pass0 : v0) && ((up >> lane) & 1ull);
+      const bool f1 = (apply_filter ? pass1 : v1) && ((up >> (lane + 32)) & 1ull);
+      const uint64_t fw = (uint64_t)__ballot_sync(0xffffffffu, f0) | ((uint64_t)__ballot_sync(0xffffffffu, f1) << 32);
+      if (lane == 0) feas[(size_t)p * words + word] = fw;
+      uint8_t* rr = reasons + (size_t)p * Npad;
+      rr[n0] = !v0 ? 0 : (!pass0 ? B200S_REASON_NETOH_VIOLATED : (f0 ? B200S_REASON_OK : B200S_REASON_UPSTREAM));
+      rr[n1] = !v1 ? 0 : (!pass1 ? B200S_REASON_NETOH_VIOLATED : (f1 ? B200S_REASON_OK : B200S_REASON_UPSTREAM));
+      if (fw) {  // warp-uniform
+        int64_t mn = INT64_MAX, mx = INT64_MIN;
+        if (f0) mn = mx = c0;
+        if (f1) {
+          mn = c1 < mn ? c1 : mn;
+          mx = c1 > mx ? c1 : mx;
+        }
+        for (int o = 16; o; o >>= 1) {
+          const int64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+          mn = a < mn ? a : mn;
+          mx = b > mx ? b : mx;
+        }
+        if (lane == 0) {
+          atomicMin(&s_lo[pp], (long long)mn);
+          atomicMax(&s_hi[pp], (long long)mx);
+        }
+      }
+    } else {
+      const NormParam np = params[p];
+      const uint64_t fw = feas[(size_t)p * words + word];
+      OutT* orow = out + (size_t)p * Npad;
+      orow[n0] = (OutT)(((fw >> lane) & 1ull) ? netoh_norm_one(np, c0) : 0);
+      orow[n1] = (OutT)(((fw >> (lane + 32)) & 1ull) ? netoh_norm_one(np, c1) : 0);
+    }
+  }
+  if (PASS == 1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < pend - p0; i += 256) {
+      if (s_lo[i] != INT64_MAX || s_hi[i] != INT64_MIN) {
+        atomicMin(reinterpret_cast<long long*>(lo) + p0 + i, s_lo[i]);
+        atomicMax(reinterpret_cast<long long*>(hi) + p0 + i, s_hi[i]);
+      }
+    }
+  }
+}
+
+int netoh_eval_fast(b200s_ctx* c, int dtype) {
+  const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64, NQ = c->netoh_NQ;
+  PluginOut& o = c->out[B200S_PLUGIN_NETWORK_OVERHEAD];
+  B200S_CUDA_TRY(c, c->netoh_pair_cost.ensure((size_t)P * NQ * 8));
+  B200S_CUDA_TRY(c, c->netoh_pair_sv.ensure((size_t)P * NQ * 4));
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));
+  int64_t* const lo_buf = c->pod_lo.as<int64_t>();
+  int64_t* const hi_buf = lo_buf + P;
+  B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
+  Topo t{c->netoh_zone_cost.as<int64_t>(), c->netoh_region_cost.as<int64_t>(), c->netoh_K};
+  const size_t pairs = (size_t)P * NQ;
+  netoh_pair_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(
+      t, c->netoh_pair_r.as<uint16_t>(), c->netoh_pair_z.as<uint16_t>(), NQ, c->netoh_equal.as<uint8_t>(),
+      c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(), P, c->netoh_pair_cost.as<int64_t>(),
+      c->netoh_pair_sv.as<uint32_t>());
+  fill_lohi_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(lo_buf, hi_buf, P);
+  c->launches += 2;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  constexpr int PT = 32;
+  dim3 grid((Npad + 511) / 512, (P + PT - 1) / PT);
+#define NETOH_FAST_ARGS(outp)                                                                                          \
+  t, c->netoh_pair_id.as<int32_t>(), NQ, c->netoh_pair_cost.as<int64_t>(), c->netoh_pair_sv.as<uint32_t>(), c->node_off, \
+      c->netoh_equal.as<uint8_t>(), c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(),                 \
+      c->netoh_region.as<uint16_t>(), c->netoh_zone.as<uint16_t>(), c->upstream_mask(), words, N, Npad, P,               \
+      c->netoh_apply_filter, o.feas.as<uint64_t>(), o.reasons.as<uint8_t>(), lo_buf, hi_buf,                             \
+      c->norm_params.as<NormParam>(), outp
+  {
+    KernelTimer kt(c, B200S_PLUGIN_NETWORK_OVERHEAD);
+    netoh_fast_kernel<1, uint8_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS((uint8_t*)nullptr));
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
+  B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
+  netoh_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(lo_buf, hi_buf, P, c->norm_params.as<NormParam>());
+  c->launches++;
+  if (dtype == B200S_OUT_I64)
+    netoh_fast_kernel<2, int64_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<int64_t>()));
+  else
+    netoh_fast_kernel<2, uint8_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<uint8_t>()));
+#undef NETOH_FAST_ARGS
+  c->launches++;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  o.valid = true;
+  c->netoh_raw_P = -1;  // finalCostMap is not materialised on this path
+  return B200S_OK;
+}
+
 }  // namespace
 
 int netoh_eval(b200s_ctx* c, int dtype) {
@@ -249,6 +436,11 @@ int netoh_eval(b200s_ctx* c, int dtype) {
     o.valid = true;
     return B200S_OK;
   }
+  // throughput path: per-pod pair table; the PreFilterState maps (raw cost / counts, opt-in via
+  // b200s_config_network_overhead) keep the materialising 3-pass path below
+  if (!c->netoh_want_counts && c->netoh_NQ <= 4096 && c->netoh_max_deps < 65535 &&
+      (size_t)P * c->netoh_NQ <= (size_t)1 << 31)
+    return netoh_eval_fast(c, dtype);
   B200S_CUDA_TRY(c, c->raw_scores.ensure((size_t)P * Npad * 8));
   if (c->netoh_want_counts) B200S_CUDA_TRY(c, c->netoh_counts.ensure((size_t)P * Npad * 4));
   B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));  // [lo | hi] contiguous: one all-reduce when sharded
