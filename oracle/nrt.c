@@ -284,6 +284,24 @@ static int64_t normalize_least_numa(int count, int is_min, int max_numa) { /* :9
   return score;
 }
 
+/* exported for the golden tests of least_numa_test.go (TestNormalizeScore :706-756, TestMinDistance :758-912) */
+int64_t orc_nrt_normalize_least_numa(int count, int is_min, int max_numa) {
+  return normalize_least_numa(count, is_min, max_numa);
+}
+float orc_nrt_min_avg_distance(const int32_t* cost /* [n][n], -1 = missing */, int n, const int* combos, int n_combos,
+                               int k) { /* minAvgDistanceInCombinations :102-114 */
+  orc_nrt_node nd;
+  memset(&nd, 0, sizeof(nd));
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) nd.cost[i][j] = cost[i * n + j];
+  float min_d = 255.0f;
+  for (int c = 0; c < n_combos; ++c) {
+    float d = avg_distance(&nd, combos + c * k, k);
+    if (d < min_d) min_d = d;
+  }
+  return min_d;
+}
+
 /* subtractFromNUMAs: numaresources.go:184-215 (greedy across the chosen zones in bit order) */
 static void subtract_from_numas(zones_t* zs, uint8_t req_mask, const int64_t* req, uint32_t mask, int R) {
   for (int r = 0; r < R; ++r) {

@@ -133,6 +133,8 @@ typedef struct {
 int orc_nrt_filter(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R);
 int64_t orc_nrt_score(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R, int strategy,
                       const int64_t* weights);
+int64_t orc_nrt_normalize_least_numa(int count, int is_min, int max_numa);
+float orc_nrt_min_avg_distance(const int32_t* cost, int n, const int* combos, int n_combos, int k);
 typedef struct {
   int32_t n_zones, n_res;
   const uint8_t* res_flags;     /* [R] */
