@@ -12,6 +12,7 @@
 // on `threads` threads — more generous to the CPU than upstream, which schedules one pod at a time with a
 // 16-goroutine fan-out over nodes (targetloadpacking_test.go:386-405 mirrors that Parallelizer).
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -125,7 +126,7 @@ void normalize(std::vector<NodeScore>& scores) {  // allocatable.go:143-168
 extern "C" void orc_gofaithful_alloc_batch(const int64_t* const* cols, const char* const* res_names, int R, int N,
                                            const int64_t* w, int mode, int P, const int64_t* pod_cpu_milli,
                                            const int64_t* pod_mem_bytes, const uint64_t* feasible, int words,
-                                           int64_t* out, int pitch, int threads) {
+                                           int64_t* out, int pitch, int threads, double* compute_seconds) {
   Plugin pl;
   pl.mode = mode;
   for (int r = 0; r < R; ++r) pl.resource_to_weight[res_names[r]] = w[r];
@@ -140,6 +141,8 @@ extern "C" void orc_gofaithful_alloc_batch(const int64_t* const* cols, const cha
       else nodes[n].allocatable.scalar[nm] = cols[r][n];
     }
   }
+  // the NodeInfo list above is the scheduler's pre-existing snapshot: only the cycles below are timed
+  const auto t_start = std::chrono::steady_clock::now();
   std::atomic<int> next(0);
   auto worker = [&]() {
     std::vector<NodeScore> list;
@@ -174,4 +177,6 @@ extern "C" void orc_gofaithful_alloc_batch(const int64_t* const* cols, const cha
     for (int t = 0; t < threads; ++t) ts.emplace_back(worker);
     for (auto& t : ts) t.join();
   }
+  if (compute_seconds)
+    *compute_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
 }

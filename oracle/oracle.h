@@ -44,7 +44,7 @@ void orc_alloc_batch(const int64_t* const* cols, int R, int N, const int64_t* w,
 void orc_gofaithful_alloc_batch(const int64_t* const* cols, const char* const* res_names, int R, int N,
                                 const int64_t* w, int mode, int P, const int64_t* pod_cpu_milli,
                                 const int64_t* pod_mem_bytes, const uint64_t* feasible, int words, int64_t* out,
-                                int pitch, int threads);
+                                int pitch, int threads, double* compute_seconds);
 
 /* ---- TargetLoadPacking (pkg/trimaran/targetloadpacking) ---- */
 int64_t orc_tlp_score(double cpu_util_pct, int64_t cap_milli, int64_t missing_milli, uint8_t flags,

@@ -66,7 +66,7 @@ def alloc_batch(cols, weights, mode, P, feasible_words=None, pitch=None):
 
 
 def gofaithful_alloc_batch(cols, res_names, weights, mode, pod_cpu_milli, pod_mem_bytes, feasible_words=None,
-                           pitch=None, threads=1):
+                           pitch=None, threads=1, return_seconds=False):
     """NodeResourcesAllocatable through the reference's per-call structure (oracle/gofaithful.cpp)."""
     cols = [_c(c, np.int64) for c in cols]
     N, P = len(cols[0]), len(pod_cpu_milli)
@@ -78,9 +78,11 @@ def gofaithful_alloc_batch(cols, res_names, weights, mode, pod_cpu_milli, pod_me
     out = np.zeros((P, pitch), dtype=np.int64)
     fw = None if feasible_words is None else _c(feasible_words, np.uint64)
     words = 0 if fw is None else fw.shape[1]
+    secs = C.c_double()
     lib().orc_gofaithful_alloc_batch(arr, names, C.c_int(len(cols)), C.c_int(N), _p(w), C.c_int(mode), C.c_int(P),
-                                     _p(pc), _p(pm), _p(fw), C.c_int(words), _p(out), C.c_int(pitch), C.c_int(threads))
-    return out
+                                     _p(pc), _p(pm), _p(fw), C.c_int(words), _p(out), C.c_int(pitch), C.c_int(threads),
+                                     C.byref(secs))
+    return (out, secs.value) if return_seconds else out
 
 
 def tlp_score(util, cap, missing, flags, pod_cpu, target=40) -> int:

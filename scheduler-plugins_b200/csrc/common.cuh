@@ -59,6 +59,16 @@ struct Store<int64_t, 2> {
   __device__ static __forceinline__ void put64(int64_t* p, const int64_t* q) { st_stream_v2(p, q[0], q[1]); }
 };
 template <>
+struct Store<uint8_t, 2> {
+  __device__ static __forceinline__ void put32(uint8_t* p, const uint32_t* q) {
+    st_stream_u16(p, (q[0] & 255u) | ((q[1] & 255u) << 8));
+  }
+  __device__ static __forceinline__ void put64(uint8_t* p, const int64_t* q) {
+    uint32_t v[2] = {(uint32_t)q[0], (uint32_t)q[1]};
+    put32(p, v);
+  }
+};
+template <>
 struct Store<uint8_t, 4> {
   __device__ static __forceinline__ void put32(uint8_t* p, const uint32_t* q) {
     st_stream_u32(p, (q[0] & 255u) | ((q[1] & 255u) << 8) | ((q[2] & 255u) << 16) | (q[3] << 24));
