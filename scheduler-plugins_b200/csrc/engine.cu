@@ -104,7 +104,7 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
                     &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts,
                     &c->netoh_pair_id,   &c->netoh_pair_r,     &c->netoh_pair_z,     &c->netoh_pair_cost,
-                    &c->netoh_pair_sv};
+                    &c->netoh_pair_sv,   &c->nrt_perm};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();
@@ -286,6 +286,16 @@ int b200s_snapshot_nrt(b200s_ctx* c, const b200s_nrt_nodes* nn) {
                                   c->N, c->Npad));
   for (int i = 0; i < Z * R; ++i)
     B200S_TRY(upload_col<int64_t>(c, c->nrt_avail, (size_t)i * np, nn->avail + (size_t)i * c->N, c->N, c->Npad));
+  {  // thread-slot permutation: warps of the P x N kernel get nodes of one control-flow class (flags, zone
+     // count) so pod-scope and container-scope nodes do not serialise inside a warp (stable: runs stay coalesced)
+    std::vector<int32_t> perm(np);
+    for (size_t i = 0; i < np; ++i) perm[i] = (int32_t)i;
+    auto key = [&](int32_t i) { return ((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]; };
+    std::stable_sort(perm.begin(), perm.begin() + c->N, [&](int32_t a, int32_t b) { return key(a) < key(b); });
+    B200S_CUDA_TRY(c, c->nrt_perm.ensure(np * 4));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->nrt_perm.p, perm.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
+    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
   c->nrt_has_cost = nn->cost != nullptr;
   if (nn->cost) {
     B200S_CUDA_TRY(c, c->nrt_cost.ensure((size_t)Z * Z * np * 4));

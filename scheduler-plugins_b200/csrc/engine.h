@@ -111,7 +111,7 @@ struct b200s_ctx {
   bool nrt_has_cost = false;
   uint8_t nrt_res_flags[B200S_NRT_MAX_RES] = {0};
   b200s::DevBuf nrt_node_flags, nrt_max_numa, nrt_nz, nrt_node_res_mask, nrt_zone_res_mask, nrt_avail,
-      nrt_cost;
+      nrt_cost, nrt_perm;  // nrt_perm [Npad] int32: thread slot -> node, nodes grouped by control-flow class
   bool nrt_cfg = false;
   int nrt_strategy = B200S_NRT_LEAST_ALLOCATED;
   int64_t nrt_w[B200S_NRT_MAX_RES] = {1, 1, 1, 1, 1, 1, 1, 1};

@@ -399,6 +399,7 @@ struct NrtNodeCols {
   const uint8_t* zone_res_mask;  // [Zs][Npad]
   const int64_t* avail;          // [Zs][Rs][Npad]
   const int32_t* cost;           // [Zs][Zs][Npad] or null
+  const int32_t* perm;           // [Npad] thread slot -> node
   int Zs, Rs;
 };
 struct NrtPodCols {
@@ -416,7 +417,8 @@ __global__ void __launch_bounds__(128, (Z <= 4 ? 3 : 1))
 nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict__ upstream, int words, int N,
            int Npad, int P, OutT* __restrict__ out, uint32_t* __restrict__ feas_out32, uint8_t* __restrict__ reasons) {
   __shared__ PodS<R> sp[PT];
-  const int n = blockIdx.x * 128 + threadIdx.x;
+  // thread slot -> node through the class-sorted permutation (Npad is a multiple of 128: every slot has a node)
+  const int n = nc.perm[blockIdx.x * 128 + threadIdx.x];
   const int p0 = blockIdx.y * PT, pend = min(PT, P - p0);
   // stage the pod tile
   for (int i = threadIdx.x; i < pend * (C_MAX + 1) * R; i += 128) {
@@ -462,8 +464,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
   }
   __syncthreads();
   if (!in) return;
-  const int lane = threadIdx.x & 31;
-  const int word = n >> 6, half = (n >> 5) & 1;
+  const int word = n >> 6;
   for (int pp = 0; pp < pend; ++pp) {
     const int p = p0 + pp;
     const PodS<R>& pod = sp[pp];
@@ -477,11 +478,20 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
       if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
       if (feasible) score = nrt_score<Z, R, SC>(zs, cost, nflags, max_numa, cfg, pod);
     }
-    const uint32_t fw = __ballot_sync(0xffffffffu, feasible);
-    if (lane == 0) feas_out32[((size_t)p * words + word) * 2 + half] = fw;
+    // scattered (permuted) stores; the feasibility words are rebuilt from the reason codes afterwards
     out[(size_t)p * Npad + n] = (OutT)score;
     reasons[(size_t)p * Npad + n] = (uint8_t)reason;
   }
+}
+
+// feasible <=> reason == OK (own rejects, UNSUPPORTED and upstream-infeasible all carry a non-zero code)
+__global__ void nrt_feas_kernel(const uint8_t* __restrict__ reasons, int N, int Npad, size_t total,
+                                uint32_t* __restrict__ feas32) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool f = false;
+  if (i < total) f = reasons[i] == B200S_REASON_OK && (int)(i % Npad) < N;
+  const uint32_t w = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && i < total) feas32[i >> 5] = w;
 }
 
 template <int Z, int R, int SC>
@@ -499,7 +509,10 @@ int launch_sc(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& 
     nrt_kernel<Z, R, SC, uint8_t, PT><<<grid, 128, 0, c->stream>>>(nc, pc, cfg, up, words, N, Npad, P,
                                                                o.scores.as<uint8_t>(), o.feas.as<uint32_t>(),
                                                                o.reasons.as<uint8_t>());
-  c->launches++;
+  const size_t total = (size_t)P * Npad;
+  nrt_feas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(o.reasons.as<uint8_t>(), N, Npad, total,
+                                                                         o.feas.as<uint32_t>());
+  c->launches += 2;
   B200S_CUDA_TRY(c, cudaGetLastError());
   return B200S_OK;
 }
@@ -527,7 +540,7 @@ int nrt_eval(b200s_ctx* c, int dtype) {
   }
   NrtNodeCols nc{c->nrt_node_flags.as<uint8_t>(), c->nrt_max_numa.as<uint16_t>(), c->nrt_nz.as<uint8_t>(),
                  c->nrt_node_res_mask.as<uint8_t>(), c->nrt_zone_res_mask.as<uint8_t>(), c->nrt_avail.as<int64_t>(),
-                 c->nrt_has_cost ? c->nrt_cost.as<int32_t>() : nullptr, c->nrt_Z, c->nrt_R};
+                 c->nrt_has_cost ? c->nrt_cost.as<int32_t>() : nullptr, c->nrt_perm.as<int32_t>(), c->nrt_Z, c->nrt_R};
   NrtPodCols pc{c->nrt_pod_qos.as<uint8_t>(), c->nrt_pod_flags.as<uint8_t>(), c->nrt_pod_ninit.as<uint8_t>(),
                 c->nrt_pod_napp.as<uint8_t>(), c->nrt_pod_kind.as<uint8_t>(), c->nrt_pod_req_mask.as<uint8_t>(),
                 c->nrt_pod_req.as<int64_t>()};
