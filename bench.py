@@ -21,6 +21,7 @@ density 0.875, MATRIX output (every pod x node score, the layout the Go framewor
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -177,7 +178,7 @@ def cycle_latency(E, synth, device, N, cycles=1000):
     w = [1, 1, 1, 1, 5]
 
     def combined():
-        eng.lib.b200s_pods_upload(eng.ctx, batch)
+        eng._chk(eng.lib.b200s_pods_upload(eng.ctx, C.byref(batch)))
         eng.P = 1
         eng.eval_combined(0b11111, w, k=1, write_total=False)
         eng.fetch_topk()
