@@ -220,7 +220,7 @@ def run_reference(args, rank, world):
     from scheduler_plugins_b200 import synth
 
     threads = os.cpu_count() or 1
-    sample = max(threads * 4, 64)  # ~0.1 s per thread per step at ~2 us per Score call
+    sample = max(threads * 24, 256)  # ~0.2-0.3 s per thread per step: amortises thread start-up on many-core hosts
     nodes, feas = make_inputs(seed, sample, N, npad, 0)
     pods = synth.gen_pods(seed, sample)
     cols = [nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]]
