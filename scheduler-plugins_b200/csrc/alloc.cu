@@ -19,6 +19,8 @@
 //     128-bit evict-first stores.  Inputs (raw 4-8 B/node, 32 B/pod, 1 bit/eval mask) stay in L2.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "engine.h"
 
 namespace b200s {
@@ -192,6 +194,102 @@ alloc_norm_kernel(const int64_t* __restrict__ raw, const NormParam* __restrict__
   }
 }
 
+// ---- TMA-store variant of the int64 pass (experiment, selected with B200S_ALLOC_TMA=1) -------------------
+// Same arithmetic; the scores of PB pods x 512 nodes are staged in shared memory (registers -> STS.128) and
+// one elected thread hands each 4 KB row segment to the TMA engine (cp.async.bulk.global.shared::cta), NSTAGE
+// staging buffers deep, so the LSU issues shared-memory stores only and global stores are bulk, asynchronous.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int PT, int PB, int NSTAGE>
+__global__ void __launch_bounds__(256)
+alloc_norm_tma_kernel(const int64_t* __restrict__ raw, const NormParam* __restrict__ params,
+                      const uint64_t* __restrict__ feasible, int words, int N, int Npad, int P,
+                      int64_t* __restrict__ out) {
+  constexpr int NPT = 2, CHUNK = 256 * NPT;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  int64_t* stage = reinterpret_cast<int64_t*>(dyn);  // [NSTAGE][PB][CHUNK]
+  __shared__ NormParam sp[PT];
+  __shared__ uint64_t sm[PT][CHUNK / 64];
+  const int n0 = blockIdx.x * CHUNK, p0 = blockIdx.y * PT, t = threadIdx.x, nb = n0 + t * NPT;
+  for (int i = t; i < PT; i += 256)
+    if (p0 + i < P) sp[i] = params[p0 + i];
+  if (feasible)
+    for (int i = t; i < PT * (CHUNK / 64); i += 256) {
+      int pp = i / (CHUNK / 64), w = i % (CHUNK / 64), gw = n0 / 64 + w;
+      sm[pp][w] = (p0 + pp < P && gw < words) ? feasible[(size_t)(p0 + pp) * words + gw] : 0ull;
+    }
+  uint32_t r32[NPT];
+  uint32_t valid = 0;
+  const bool in = nb < Npad;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    r32[j] = in ? (uint32_t)(uint64_t)raw[nb + j] : 0u;
+    if (in && nb + j < N) valid |= 1u << j;
+  }
+  __syncthreads();
+  const int wi = (t * NPT) / 64, sh = (t * NPT) % 64;
+  const int pend = min(PT, P - p0);
+  const int cols = min(CHUNK, Npad - n0);  // columns of this CTA that exist (multiple of 128)
+  int g = 0;
+  for (int pg = 0; pg < pend; pg += PB, ++g) {
+    const int s = g % NSTAGE;
+    if (g >= NSTAGE) {  // the buffer's previous bulk stores must have finished READING shared memory
+      if (t == 0) bulk_wait_read<NSTAGE - 1>();
+      __syncthreads();
+    }
+    int64_t* buf = stage + (size_t)s * PB * CHUNK;
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const int pp = pg + b;
+      if (pp >= pend) break;
+      const NormParam np = sp[pp];
+      uint32_t bits = valid;
+      if (feasible) bits &= (uint32_t)(sm[pp][wi] >> sh);
+      int64_t q[NPT];
+      if (np.mode == 1) {
+        const uint32_t lo32 = (uint32_t)(uint64_t)np.lo, rg = (uint32_t)np.range;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+          uint32_t n100 = (r32[j] - lo32) * 100u;
+          uint32_t q0 = __umulhi(n100, np.magic) >> np.shift;
+          uint32_t rem = n100 - q0 * rg;
+          q0 += rem >= rg ? 1u : 0u;
+          q[j] = ((bits >> j) & 1u) ? (int64_t)q0 : 0;
+        }
+      } else if (np.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) q[j] = 0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+          int64_t v = in ? go_div(wrap_mul(wrap_sub(raw[nb + j], np.lo), 100), np.range) : 0;
+          q[j] = ((bits >> j) & 1u) ? v : 0;
+        }
+      }
+      *reinterpret_cast<longlong2*>(buf + (size_t)b * CHUNK + t * NPT) = make_longlong2(q[0], q[1]);
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+    __syncthreads();
+    if (t == 0) {
+      for (int b = 0; b < PB && pg + b < pend; ++b)
+        bulk_store_s2g(out + (size_t)(p0 + pg + b) * Npad + n0, buf + (size_t)b * CHUNK, (uint32_t)cols * 8u);
+      bulk_commit();
+    }
+  }
+  if (t == 0) bulk_wait_read<0>();  // shared memory must stay alive until the engine has read it
+  __syncthreads();
+}
+
 }  // namespace
 
 int build_norm_params(b200s_ctx* c, int P) {
@@ -261,7 +359,16 @@ int alloc_eval(b200s_ctx* c, int dtype) {
   B200S_TRY(build_norm_params(c, P));
   PluginOut& o = c->out[B200S_PLUGIN_ALLOCATABLE];
   KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
-  if (dtype == B200S_OUT_I64) {
+  static const bool use_tma = getenv("B200S_ALLOC_TMA") && atoi(getenv("B200S_ALLOC_TMA")) != 0;
+  if (dtype == B200S_OUT_I64 && use_tma) {
+    constexpr int PT = 64, PB = 4, NSTAGE = 4;
+    constexpr size_t smem = (size_t)NSTAGE * PB * 512 * 8;
+    auto kern = alloc_norm_tma_kernel<PT, PB, NSTAGE>;
+    B200S_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((Npad + 511) / 512, (P + PT - 1) / PT);
+    kern<<<grid, 256, smem, c->stream>>>(c->alloc_raw.as<int64_t>(), c->norm_params.as<NormParam>(), feas, words, N,
+                                         Npad, P, o.scores.as<int64_t>());
+  } else if (dtype == B200S_OUT_I64) {
     constexpr int NPT = 2, PT = 64;
     dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
     alloc_norm_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(),
