@@ -48,10 +48,14 @@ __global__ void alloc_raw_kernel(const int64_t* __restrict__ cols, int N, int Np
   if (n < N) iota[n] = n;
 }
 
+__device__ __forceinline__ NormParam make_norm_param(int64_t lo, int64_t hi);
+
 // One warp per pod.  lo = raw of the first feasible node in ascending sorted order, hi = last.
+// Single-GPU: also emits the pod's NormParam (no all-reduce in between, one launch less per step).
 __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, const int32_t* __restrict__ order,
                                     const uint64_t* __restrict__ feasible, int words, int N, int P,
-                                    int64_t* __restrict__ lo, int64_t* __restrict__ hi) {
+                                    int64_t* __restrict__ lo, int64_t* __restrict__ hi,
+                                    NormParam* __restrict__ params_out) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= P) return;
@@ -95,20 +99,18 @@ __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, cons
   if (lane == 0) {
     lo[warp] = vlo;
     hi[warp] = vhi;
+    if (params_out) params_out[warp] = make_norm_param(vlo, vhi);
   }
 }
 
-__global__ void norm_params_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, int P,
-                                   NormParam* __restrict__ out) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+__device__ __forceinline__ NormParam make_norm_param(int64_t lo, int64_t hi) {
   NormParam q;
-  q.lo = lo[p];
-  q.range = wrap_sub(hi[p], lo[p]);
+  q.lo = lo;
+  q.range = wrap_sub(hi, lo);
   q.magic = 0;
   q.shift = 0;
   q.pad = 0;
-  if (lo[p] > hi[p] || q.range == 0) {
+  if (lo > hi || q.range == 0) {
     q.mode = 0;  // empty feasible set, or oldRange == 0 => MinNodeScore (allocatable.go:158-160)
   } else if (q.range > 0 && q.range <= (int64_t)(0xffffffffu / 100u)) {
     // (raw-lo)*100 < 2^32 for every feasible node: exact 32-bit reciprocal division with one fix-up.
@@ -121,7 +123,13 @@ __global__ void norm_params_kernel(const int64_t* __restrict__ lo, const int64_t
   } else {
     q.mode = 2;  // generic wrapping int64 path (Go semantics incl. overflow)
   }
-  out[p] = q;
+  return q;
+}
+
+__global__ void norm_params_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, int P,
+                                   NormParam* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) out[p] = make_norm_param(lo[p], hi[p]);
 }
 
 // Tile: (256 threads x NPT nodes) x PT pods.  Thread t owns nodes n0 + t*NPT .. +NPT-1.
@@ -348,15 +356,20 @@ int alloc_eval(b200s_ctx* c, int dtype) {
   int64_t* const lo_buf = c->pod_lo.as<int64_t>();
   int64_t* const hi_buf = lo_buf + P;
   const uint64_t* feas = c->upstream_mask();
+  const bool sharded = comm_world(c) > 1;
+  B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
   {
     int threads = 128, warps_per_block = threads / 32;
     alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
-        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo_buf, hi_buf);
+        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo_buf, hi_buf,
+        sharded ? nullptr : c->norm_params.as<NormParam>());
     c->launches++;
     B200S_CUDA_TRY(c, cudaGetLastError());
   }
-  B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
-  B200S_TRY(build_norm_params(c, P));
+  if (sharded) {
+    B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
+    B200S_TRY(build_norm_params(c, P));
+  }
   PluginOut& o = c->out[B200S_PLUGIN_ALLOCATABLE];
   KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
   static const bool use_tma = getenv("B200S_ALLOC_TMA") && atoi(getenv("B200S_ALLOC_TMA")) != 0;

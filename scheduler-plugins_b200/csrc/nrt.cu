@@ -25,10 +25,11 @@ constexpr int C_MAX = B200S_NRT_MAX_CONT;
 // lexicographically by index tuple (gonum combin.Combinations order, least_numa.go:161).
 __constant__ uint8_t c_combo_mask[8][255];
 __constant__ uint8_t c_combo_off[8][10];  // [n-1][k] = first index of size-k subsets; [n-1][n+1] = end
-bool g_combo_ready = false;
+bool g_combo_ready[64] = {false};  // __constant__ memory is per device (one process may drive several GPUs)
 
-int ensure_combos() {
-  if (g_combo_ready) return 0;
+int ensure_combos(int device) {
+  if (device < 0 || device >= 64) return -1;
+  if (g_combo_ready[device]) return 0;
   static uint8_t mask[8][255];
   static uint8_t off[8][10];
   for (int n = 1; n <= 8; ++n) {
@@ -53,7 +54,7 @@ int ensure_combos() {
   }
   if (cudaMemcpyToSymbol(c_combo_mask, mask, sizeof(mask)) != cudaSuccess) return -1;
   if (cudaMemcpyToSymbol(c_combo_off, off, sizeof(off)) != cudaSuccess) return -1;
-  g_combo_ready = true;
+  g_combo_ready[device] = true;
   return 0;
 }
 
@@ -531,7 +532,7 @@ int nrt_eval(b200s_ctx* c, int dtype) {
   if (!c->has_nrt_pods) return c->set_err(B200S_ERR_STATE, "NodeResourceTopologyMatch: pod batch has no NRT columns");
   if (c->nrt_strategy == B200S_NRT_LEAST_NUMA_NODES && !c->nrt_has_cost)
     return c->set_err(B200S_ERR_STATE, "NodeResourceTopologyMatch: LeastNUMANodes needs the zone cost columns");
-  if (ensure_combos() != 0) return c->set_err(B200S_ERR_CUDA, "NodeResourceTopologyMatch: combination table upload failed");
+  if (ensure_combos(c->device) != 0) return c->set_err(B200S_ERR_CUDA, "NodeResourceTopologyMatch: combination table upload failed");
   B200S_TRY(ensure_out(c, B200S_PLUGIN_NRT, dtype, true, true));
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
   if (c->P == 0) {
