@@ -252,7 +252,7 @@ __global__ void netoh_pair_kernel(Topo t, const uint16_t* __restrict__ pair_r, c
   if (i >= (size_t)P * NQ) return;
   const int p = (int)(i / NQ), q = (int)(i % NQ);
   int64_t s = 0, w = 0, cst = 0;
-  if (!equal[p]) eval_node(t, -1, pair_r[q], pair_z[q], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s, w, cst);
+  if (!equal[p]) eval_node(t, INT32_MIN /* no node: the same-host case is handled per node */, pair_r[q], pair_z[q], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s, w, cst);
   pair_cost[i] = cst;
   pair_sv[i] = (uint32_t)s | ((uint32_t)w << 16);
 }
