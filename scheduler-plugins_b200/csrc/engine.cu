@@ -117,6 +117,8 @@ void b200s_shutdown(b200s_ctx* c) {
       cudaEventDestroy(pr.second);
     }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+  c->pods_arena.release();
+  if (c->pods_stage) cudaFreeHost(c->pods_stage);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -423,6 +425,52 @@ int b200s_config_nrt(b200s_ctx* c, int strategy, int32_t n_res, const int64_t* w
 }
 
 // ---------------------------------------------------------------- pods
+namespace {
+
+// Collects the columns of one pod batch; small ones are packed into one pinned staging buffer and travel
+// as a single cudaMemcpyAsync into the pod arena, large ones (the feasibility words of a big batch) go direct.
+struct PodUpload {
+  struct Item {
+    DevBuf* d;
+    const void* s;
+    size_t bytes;
+  };
+  std::vector<Item> items;
+  void add(DevBuf* d, const void* s, size_t bytes) { items.push_back({d, s, bytes}); }
+  int flush(b200s_ctx* c) {
+    constexpr size_t kSmall = 64 * 1024, kAlign = 256;
+    size_t total = 0;
+    for (auto& it : items)
+      if (it.bytes <= kSmall) total += (it.bytes + kAlign - 1) / kAlign * kAlign;
+    if (total > 0) {
+      if (total > c->pods_stage_cap) {
+        if (c->pods_stage) cudaFreeHost(c->pods_stage);
+        c->pods_stage = nullptr;
+        c->pods_stage_cap = 0;
+        B200S_CUDA_TRY(c, cudaHostAlloc(&c->pods_stage, total * 2, cudaHostAllocDefault));
+        c->pods_stage_cap = total * 2;
+      }
+      B200S_CUDA_TRY(c, c->pods_arena.ensure(total));
+    }
+    size_t off = 0;
+    for (auto& it : items) {
+      if (it.bytes <= kSmall) {
+        memcpy(static_cast<char*>(c->pods_stage) + off, it.s, it.bytes);
+        it.d->view(static_cast<char*>(c->pods_arena.p) + off);
+        off += (it.bytes + kAlign - 1) / kAlign * kAlign;
+      } else {
+        B200S_CUDA_TRY(c, it.d->ensure(it.bytes));
+        B200S_CUDA_TRY(c, cudaMemcpyAsync(it.d->p, it.s, it.bytes, cudaMemcpyHostToDevice, c->stream));
+      }
+    }
+    if (total > 0)
+      B200S_CUDA_TRY(c, cudaMemcpyAsync(c->pods_arena.p, c->pods_stage, total, cudaMemcpyHostToDevice, c->stream));
+    return B200S_OK;
+  }
+};
+
+}  // namespace
+
 static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   if (!c->snap_valid) return c->set_err(B200S_ERR_STATE, "pods_upload: no committed snapshot");
   if (!b || b->n_pods < 0) return c->set_err(B200S_ERR_INVALID, "pods_upload: bad batch");
@@ -430,26 +478,15 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   c->pods_valid = false;
   c->P = P;
   size_t words = (size_t)(c->Npad / 64);
+  PodUpload up;
   c->has_feasible = b->feasible != nullptr;
-  if (b->feasible && P > 0) {
-    B200S_CUDA_TRY(c, c->feasible_in.ensure((size_t)P * words * 8));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->feasible_in.p, b->feasible, (size_t)P * words * 8,
-                                      cudaMemcpyHostToDevice, c->stream));
-  }
+  if (b->feasible && P > 0) up.add(&c->feasible_in, b->feasible, (size_t)P * words * 8);
   c->has_tlp_pods = b->tlp_pod_cpu_milli != nullptr;
-  if (c->has_tlp_pods && P > 0) {
-    B200S_CUDA_TRY(c, c->tlp_pod_cpu.ensure((size_t)P * 8));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->tlp_pod_cpu.p, b->tlp_pod_cpu_milli, (size_t)P * 8,
-                                      cudaMemcpyHostToDevice, c->stream));
-  }
+  if (c->has_tlp_pods && P > 0) up.add(&c->tlp_pod_cpu, b->tlp_pod_cpu_milli, (size_t)P * 8);
   c->has_lvrb_pods = b->lvrb_req_cpu_milli && b->lvrb_req_mem_bytes;
   if (c->has_lvrb_pods && P > 0) {
-    B200S_CUDA_TRY(c, c->lvrb_req_cpu.ensure((size_t)P * 8));
-    B200S_CUDA_TRY(c, c->lvrb_req_mem.ensure((size_t)P * 8));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->lvrb_req_cpu.p, b->lvrb_req_cpu_milli, (size_t)P * 8,
-                                      cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->lvrb_req_mem.p, b->lvrb_req_mem_bytes, (size_t)P * 8,
-                                      cudaMemcpyHostToDevice, c->stream));
+    up.add(&c->lvrb_req_cpu, b->lvrb_req_cpu_milli, (size_t)P * 8);
+    up.add(&c->lvrb_req_mem, b->lvrb_req_mem_bytes, (size_t)P * 8);
   }
   c->has_nrt_pods = b->nrt != nullptr;
   if (b->nrt && P > 0) {
@@ -458,21 +495,13 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     if (!q->qos || !q->flags || !q->n_init || !q->n_app || !q->cont_kind || !q->req_mask || !q->req)
       return c->set_err(B200S_ERR_INVALID, "pods_upload: null NRT pod column");
     const int C = B200S_NRT_MAX_CONT, R = c->nrt_R;
-    struct {
-      DevBuf* d;
-      const void* s;
-      size_t bytes;
-    } cols[] = {{&c->nrt_pod_qos, q->qos, (size_t)P},
-                {&c->nrt_pod_flags, q->flags, (size_t)P},
-                {&c->nrt_pod_ninit, q->n_init, (size_t)P},
-                {&c->nrt_pod_napp, q->n_app, (size_t)P},
-                {&c->nrt_pod_kind, q->cont_kind, (size_t)P * C},
-                {&c->nrt_pod_req_mask, q->req_mask, (size_t)P * (C + 1)},
-                {&c->nrt_pod_req, q->req, (size_t)P * (C + 1) * R * 8}};
-    for (auto& col : cols) {
-      B200S_CUDA_TRY(c, col.d->ensure(col.bytes));
-      B200S_CUDA_TRY(c, cudaMemcpyAsync(col.d->p, col.s, col.bytes, cudaMemcpyHostToDevice, c->stream));
-    }
+    up.add(&c->nrt_pod_qos, q->qos, (size_t)P);
+    up.add(&c->nrt_pod_flags, q->flags, (size_t)P);
+    up.add(&c->nrt_pod_ninit, q->n_init, (size_t)P);
+    up.add(&c->nrt_pod_napp, q->n_app, (size_t)P);
+    up.add(&c->nrt_pod_kind, q->cont_kind, (size_t)P * C);
+    up.add(&c->nrt_pod_req_mask, q->req_mask, (size_t)P * (C + 1));
+    up.add(&c->nrt_pod_req, q->req, (size_t)P * (C + 1) * R * 8);
   }
   c->has_netoh_pods = b->netoh != nullptr;
   if (b->netoh && P > 0) {
@@ -480,18 +509,17 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     if (!q->score_equally || !q->dep_offset) return c->set_err(B200S_ERR_INVALID, "pods_upload: null NetworkOverhead column");
     int total = q->dep_offset[P];
     if (total < 0 || (total > 0 && !q->deps)) return c->set_err(B200S_ERR_INVALID, "pods_upload: bad dependency CSR");
-    B200S_CUDA_TRY(c, c->netoh_equal.ensure((size_t)P));
-    B200S_CUDA_TRY(c, c->netoh_dep_off.ensure((size_t)(P + 1) * 4));
-    B200S_CUDA_TRY(c, c->netoh_deps.ensure((size_t)(total > 0 ? total : 1) * sizeof(b200s_netoh_dep)));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_equal.p, q->score_equally, (size_t)P, cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_dep_off.p, q->dep_offset, (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    up.add(&c->netoh_equal, q->score_equally, (size_t)P);
+    up.add(&c->netoh_dep_off, q->dep_offset, (size_t)(P + 1) * 4);
     if (total > 0)
-      B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_deps.p, q->deps, (size_t)total * sizeof(b200s_netoh_dep),
-                                        cudaMemcpyHostToDevice, c->stream));
+      up.add(&c->netoh_deps, q->deps, (size_t)total * sizeof(b200s_netoh_dep));
+    else
+      B200S_CUDA_TRY(c, c->netoh_deps.ensure(sizeof(b200s_netoh_dep)));
     c->netoh_total_deps = total;
     c->netoh_max_deps = 0;
     for (int p = 0; p < P; ++p) c->netoh_max_deps = std::max(c->netoh_max_deps, q->dep_offset[p + 1] - q->dep_offset[p]);
   }
+  B200S_TRY(up.flush(c));
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
   if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& o : c->out) o.valid = false;

@@ -15,7 +15,19 @@ namespace b200s {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;  // false: a view into another allocation (the pod arena); never freed here
+  void view(void* ptr) {
+    if (owned && p) cudaFree(p);
+    p = ptr;
+    cap = 0;
+    owned = false;
+  }
   cudaError_t ensure(size_t bytes) {
+    if (!owned) {
+      p = nullptr;
+      cap = 0;
+      owned = true;
+    }
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr;
@@ -26,9 +38,10 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <class T>
   T* as() const {
@@ -129,6 +142,11 @@ struct b200s_ctx {
   // ---- pods ----
   bool pods_valid = false;
   int P = 0;
+  // small pod columns travel as ONE host->device copy: packed into a pinned staging buffer, copied into a
+  // device arena, and the column buffers become views into it (a P=1 cycle has ~13 tiny columns)
+  b200s::DevBuf pods_arena;
+  void* pods_stage = nullptr;
+  size_t pods_stage_cap = 0;
   bool has_feasible = false;
   b200s::DevBuf feasible_in;  // [P][Npad/64]
   // eval_combined chains the filters: each plugin's "upstream" set is what the previous filters left
