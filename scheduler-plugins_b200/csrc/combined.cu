@@ -12,6 +12,8 @@
 // Per-plugin scores travel as u8 (0..100); the weighted sum, the optional int64 total matrix and
 // the per-pod top-k are produced by one kernel.  Sharded: ONE ncclAllGather of the [P][k]
 // winners, then a fold — every rank ends up with the global top-k.
+#include <algorithm>
+
 #include "engine.h"
 
 namespace b200s {
@@ -34,12 +36,14 @@ struct PluginPtrs {
   int n;
 };
 
-// One CTA per pod.
+// One CTA per (pod, node slice): blockIdx.y selects a `chunk`-node slice so that a small batch (P = 1 in the
+// real scheduling cycle) still fills the 148 SMs; the per-slice winners [slice][P][k] are folded afterwards.
 template <int K>
 __global__ void __launch_bounds__(256)
 combine_topk_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words, int N, int Npad, int node_off, int k,
-                    int64_t* __restrict__ total, b200s_topk_entry* __restrict__ out) {
+                    int chunk, int P, int64_t* __restrict__ total, b200s_topk_entry* __restrict__ out) {
   const int p = blockIdx.x, t = threadIdx.x;
+  const int n_begin = blockIdx.y * chunk, n_end = min(Npad, n_begin + chunk);
   int64_t bs[K];
   int32_t bn[K];
 #pragma unroll
@@ -48,7 +52,7 @@ combine_topk_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words,
     bn[i] = INT32_MAX;
   }
   const size_t rowoff = (size_t)p * Npad;
-  for (int n4 = t * 4; n4 < Npad; n4 += 256 * 4) {
+  for (int n4 = n_begin + t * 4; n4 < n_end; n4 += 256 * 4) {
     uint32_t packed[B200S_PLUGIN_COUNT];
     for (int j = 0; j < pl.n; ++j) packed[j] = *reinterpret_cast<const uint32_t*>(pl.s[j] + rowoff + n4);
     const uint64_t fw = feas ? feas[(size_t)p * words + (n4 >> 6)] : ~0ull;
@@ -113,7 +117,7 @@ combine_topk_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words,
       e.score = n == INT32_MAX ? 0 : s;
       e.node = n == INT32_MAX ? -1 : n;
       e.pad = 0;
-      out[(size_t)p * k + round] = e;
+      out[((size_t)blockIdx.y * P + p) * k + round] = e;
     }
     __syncthreads();
     if (bn[0] == win_n && win_n != INT32_MAX) {  // the owner pops its head
@@ -237,14 +241,30 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
   const int world = comm_world(c);
   b200s_topk_entry* local = world > 1 ? c->topk_local.as<b200s_topk_entry>() : c->topk_final.as<b200s_topk_entry>();
   int64_t* tot = write_total ? c->total.as<int64_t>() : nullptr;
+  // node slices per pod: enough CTAs for 4 waves of the 148 SMs, slices of >= 1024 nodes (multiple of 1024)
+  int S = (4 * B200S_SM_COUNT + P - 1) / P;
+  S = std::max(1, std::min(S, std::min(64, (Npad + 1023) / 1024)));
+  const int chunk = ((Npad + S - 1) / S + 1023) / 1024 * 1024;
+  S = (Npad + chunk - 1) / chunk;
+  b200s_topk_entry* stage1 = local;
+  if (S > 1) {
+    B200S_CUDA_TRY(c, c->topk_slices.ensure((size_t)S * P * k * sizeof(b200s_topk_entry)));
+    stage1 = c->topk_slices.as<b200s_topk_entry>();
+  }
+  dim3 grid(P, S);
   if (k == 1)
-    combine_topk_kernel<1><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+    combine_topk_kernel<1><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   else if (k <= 4)
-    combine_topk_kernel<4><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+    combine_topk_kernel<4><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   else
-    combine_topk_kernel<K_MAX><<<P, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, tot, local);
+    combine_topk_kernel<K_MAX><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
+  if (S > 1) {
+    fold_topk_kernel<<<(P + 127) / 128, 128, 0, c->stream>>>(stage1, S, P, k, local);
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  }
   if (world > 1) {
     const size_t bytes = (size_t)P * k * sizeof(b200s_topk_entry);
     B200S_CUDA_TRY(c, c->topk_all.ensure(bytes * world));

@@ -104,7 +104,7 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
                     &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts,
                     &c->netoh_pair_id,   &c->netoh_pair_r,     &c->netoh_pair_z,     &c->netoh_pair_cost,
-                    &c->netoh_pair_sv,   &c->nrt_perm};
+                    &c->netoh_pair_sv,   &c->nrt_perm,         &c->topk_slices};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();

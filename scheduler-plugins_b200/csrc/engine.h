@@ -179,6 +179,7 @@ struct b200s_ctx {
   b200s::DevBuf topk_local;  // [P][k] entries of this shard
   b200s::DevBuf topk_all;    // [world][P][k]
   b200s::DevBuf topk_final;  // [P][k]
+  b200s::DevBuf topk_slices; // [slices][P][k] per-node-slice winners of a small batch
   int topk_k = 0;
   bool total_valid = false, topk_valid = false;
 
