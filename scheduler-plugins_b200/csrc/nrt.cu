@@ -62,9 +62,6 @@ template <int R>
 struct PodS {  // one pod of the tile, in shared memory
   int64_t req[C_MAX + 1][R];
   int64_t reqv[C_MAX + 1][R];  // Quantity.Value() of req (ceil to whole units), precomputed once per tile
-  float reqvf[C_MAX + 1][R];   // float(reqv): numerator estimate of the Least/Most quotient
-  int64_t wsum[C_MAX + 1];     // sum of the strategy weights over the slot's requested resources
-  float wrcp[C_MAX + 1];       // 1 / float(wsum)
   uint8_t req_mask[C_MAX + 1];
   uint8_t kind[C_MAX];
   uint8_t qos, flags, n_init, n_app;
@@ -76,31 +73,6 @@ struct Zones {
   uint32_t zmask[Z];
   int nz;
 };
-
-// Per-node constants of the Least/Most strategies, computed once per pod tile: Value() of every zone
-// capacity (the /1000 with round-up), its float image and float reciprocal (quotient estimates).
-template <int Z, int R>
-struct ZoneVals {
-  int64_t cv[Z][R];
-  float cvf[Z][R], rcp[Z][R];
-};
-
-// floor(num/den) for 0 <= num, 0 < den < 2^52 with a small quotient: `est` is a float estimate within +-1 of the
-// true quotient (callers build it from float images of the operands); exact integer fix-up.
-__device__ __forceinline__ int64_t div_fix(int64_t num, int64_t den, float est) {
-  int64_t q = (int64_t)__float2int_rd(est);
-  q = q < 0 ? 0 : q;
-  int64_t rem = num - q * den;
-  while (rem < 0) {
-    --q;
-    rem += den;
-  }
-  while (rem >= den) {
-    ++q;
-    rem -= den;
-  }
-  return q;
-}
 
 struct NrtCfg {
   int strategy;
@@ -212,9 +184,8 @@ __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t 
 
 // one zone, Least/Most/Balanced strategies
 template <int Z, int R, int SC>
-__device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, const ZoneVals<Z, R>& zv, int z, const NrtCfg& cfg,
-                                                  uint32_t req_mask, const int64_t* req, const int64_t* reqv,
-                                                  const float* reqvf, int64_t wsum, float wrcp) {
+__device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, const NrtCfg& cfg, uint32_t req_mask,
+                                                  const int64_t* req, const int64_t* reqv) {
   if constexpr (SC == 1) {
     double fr[R];
     int n = 0;
@@ -249,33 +220,24 @@ __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, const Z
     if (cap == 0 || req[r] > cap) {
       s = 0;
     } else {
-      const int64_t cv = zv.cv[z][r], rv = reqv[r];
-      const int64_t a = most ? rv : cv - rv;
-      if (cv >= (1ll << 52) || a < 0 || a > cv) {
-        s = go_div(wrap_mul(a, 100), cv);  // absurd capacities: Go's wrapping arithmetic verbatim
-      } else {
-        const float af = most ? reqvf[r] : zv.cvf[z][r] - reqvf[r];
-        s = div_fix(a * 100, cv, af * 100.0f * zv.rcp[z][r]);
-      }
+      const int64_t cv = qty_value(cap), rv = reqv[r];
+      s = most ? div100(rv, cv) : div100(cv - rv, cv);
     }
     node_score = wrap_add(node_score, wrap_mul(s, cfg.w[r]));
     weight_sum = wrap_add(weight_sum, cfg.w[r]);
   }
   if (weight_sum == 0) return 0;
-  // weight_sum == wsum (same resources, same weights); quotient <= 100
-  if (node_score < 0 || wsum >= (1ll << 40) || node_score > wsum * 100) return go_div(node_score, weight_sum);
-  return div_fix(node_score, wsum, __ll2float_rn(node_score) * wrcp);
+  return go_div(node_score, weight_sum);
 }
 
 template <int Z, int R, int SC>
-__device__ __forceinline__ int64_t score_each_numa(const Zones<Z, R>& zs, const ZoneVals<Z, R>& zv, const NrtCfg& cfg,
-                                                   uint32_t req_mask, const int64_t* req, const int64_t* reqv,
-                                                   const float* reqvf, int64_t wsum, float wrcp) {
+__device__ __forceinline__ int64_t score_each_numa(const Zones<Z, R>& zs, const NrtCfg& cfg, uint32_t req_mask,
+                                                   const int64_t* req, const int64_t* reqv) {
   int64_t min_score = 0;
 #pragma unroll
   for (int z = 0; z < Z; ++z) {
     if (z >= zs.nz) continue;
-    const int64_t s = strategy_score<Z, R, SC>(zs, zv, z, cfg, req_mask, req, reqv, reqvf, wsum, wrcp);
+    const int64_t s = strategy_score<Z, R, SC>(zs, z, cfg, req_mask, req, reqv);
     if (min_score == 0 || (s != 0 && s < min_score)) min_score = s;
   }
   return min_score;
@@ -371,8 +333,8 @@ __device__ __forceinline__ int64_t normalize_least_numa(int count, bool is_min, 
 }
 
 template <int Z, int R, int SC>
-__device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const ZoneVals<Z, R>& zv, const int32_t (&cost)[Z][Z],
-                             uint32_t nflags, int max_numa, const NrtCfg& cfg, const PodS<R>& pod) {
+__device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z][Z], uint32_t nflags, int max_numa,
+                             const NrtCfg& cfg, const PodS<R>& pod) {
   if (pod.qos != B200S_QOS_GUARANTEED) return 100;
   if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return 0;
   if (!(nflags & B200S_NRT_NODE_FRESH) || !(nflags & B200S_NRT_NODE_HAS_NRT)) return 0;
@@ -423,8 +385,7 @@ __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const ZoneVals<Z, R>& z
     int64_t last = 0;
     for (int s = 0; s < steps; ++s) {
       const int c = scope_pod ? C_MAX : s;
-      last = score_each_numa<Z, R, SC>(node_zs, zv, cfg, pod.req_mask[c], pod.req[c], pod.reqv[c], pod.reqvf[c],
-                                       pod.wsum[c], pod.wrcp[c]);
+      last = score_each_numa<Z, R, SC>(node_zs, cfg, pod.req_mask[c], pod.req[c], pod.reqv[c]);
       sum += (double)last;
     }
     return scope_pod ? last : f2i(sum / (double)nc);
@@ -465,9 +426,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
     const int pp = i / ((C_MAX + 1) * R), rest = i % ((C_MAX + 1) * R), c = rest / R, r = rest % R;
     const int64_t q = r < nc.Rs ? pc.req[((size_t)(p0 + pp) * (C_MAX + 1) + c) * nc.Rs + r] : 0;
     sp[pp].req[c][r] = q;
-    const int64_t qv = q >= 0 ? (q + 999) / 1000 : -((-q) / 1000);
-    sp[pp].reqv[c][r] = qv;
-    sp[pp].reqvf[c][r] = __ll2float_rn(qv);
+    sp[pp].reqv[c][r] = q >= 0 ? (q + 999) / 1000 : -((-q) / 1000);
   }
   for (int i = threadIdx.x; i < pend; i += 128) {
     const int p = p0 + i;
@@ -476,15 +435,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
     sp[i].n_init = pc.n_init[p];
     sp[i].n_app = pc.n_app[p];
     for (int c = 0; c < C_MAX; ++c) sp[i].kind[c] = pc.kind[(size_t)p * C_MAX + c];
-    for (int c = 0; c <= C_MAX; ++c) {
-      const uint32_t m = pc.req_mask[(size_t)p * (C_MAX + 1) + c];
-      sp[i].req_mask[c] = (uint8_t)m;
-      int64_t ws = 0;
-      for (int r = 0; r < R; ++r)
-        if ((m >> r) & 1u) ws = wrap_add(ws, cfg.w[r]);
-      sp[i].wsum[c] = ws;
-      sp[i].wrcp[c] = ws > 0 ? 1.0f / __ll2float_rn(ws) : 0.0f;
-    }
+    for (int c = 0; c <= C_MAX; ++c) sp[i].req_mask[c] = pc.req_mask[(size_t)p * (C_MAX + 1) + c];
   }
   // this thread's node: zones x resources block into registers, once for the whole pod tile
   Zones<Z, R> zs;
@@ -512,18 +463,6 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
         cost[z][z2] = (in && nc.cost && z < nc.Zs && z2 < nc.Zs) ? nc.cost[((size_t)z * nc.Zs + z2) * Npad + n] : -1;
     }
   }
-  ZoneVals<Z, R> zv;
-  if constexpr (SC == 0) {
-#pragma unroll
-    for (int z = 0; z < Z; ++z)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int64_t cv = qty_value(zs.avail[z][r]);
-        zv.cv[z][r] = cv;
-        zv.cvf[z][r] = __ll2float_rn(cv);
-        zv.rcp[z][r] = cv > 0 ? 1.0f / zv.cvf[z][r] : 0.0f;
-      }
-  }
   __syncthreads();
   if (!in) return;
   const int word = n >> 6;
@@ -538,7 +477,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
       const bool up = upstream ? ((upstream[(size_t)p * words + word] >> (n & 63)) & 1ull) : true;
       feasible = reason == 0 && up;
       if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
-      if (feasible) score = nrt_score<Z, R, SC>(zs, zv, cost, nflags, max_numa, cfg, pod);
+      if (feasible) score = nrt_score<Z, R, SC>(zs, cost, nflags, max_numa, cfg, pod);
     }
     // scattered (permuted) stores; the feasibility words are rebuilt from the reason codes afterwards
     out[(size_t)p * Npad + n] = (OutT)score;
