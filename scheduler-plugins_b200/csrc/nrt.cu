@@ -62,6 +62,11 @@ template <int R>
 struct PodS {  // one pod of the tile, in shared memory
   int64_t req[C_MAX + 1][R];
   int64_t reqv[C_MAX + 1][R];  // Quantity.Value() of req (ceil to whole units), precomputed once per tile
+  // Filter operands (see nrt_filter): eff = threshold a zone's availability must reach (INT64_MIN: resource does
+  // not constrain), sub = what an app container takes from its zone, need = requested with a non-zero quantity
+  int64_t eff[C_MAX + 1][R];
+  int64_t sub[C_MAX + 1][R];
+  uint8_t need[C_MAX + 1];
   uint8_t req_mask[C_MAX + 1];
   uint8_t kind[C_MAX];
   uint8_t qos, flags, n_init, n_app;
@@ -108,35 +113,16 @@ __device__ __forceinline__ bool suitable(int qos, uint32_t rflags, int64_t qty, 
   return numa_qty >= qty;
 }
 
-// resourcesAvailableInAnyNUMANodes (filter.go:90-160)
-template <int Z, int R>
-__device__ __forceinline__ bool available_in_any(const Zones<Z, R>& zs, uint32_t node_res_mask, const NrtCfg& cfg,
-                                                 int qos, uint32_t req_mask, const int64_t* req, int& numa_id) {
-  uint32_t bitmask = 0xffffffffu;  // only bits < nz <= 8 can be cleared; all-ones <=> untouched
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (!((req_mask >> r) & 1u)) continue;
-    const int64_t q = req[r];
-    if (q == 0) continue;
-    if (!((node_res_mask >> r) & 1u)) return false;
-    bool has_affinity = false;
-    uint32_t res_bits = 0;
-#pragma unroll
-    for (int z = 0; z < Z; ++z) {
-      if (z < zs.nz && ((zs.zmask[z] >> r) & 1u)) {
-        has_affinity = true;
-        if (suitable(qos, cfg.res_flags[r], q, zs.avail[z][r])) res_bits |= 1u << z;
-      }
-    }
-    if (!has_affinity && (cfg.res_flags[r] & B200S_NRT_RES_HOST_LEVEL)) continue;
-    bitmask &= res_bits;
-    if (bitmask == 0) return false;
-  }
-  numa_id = __ffs(bitmask) - 1;
-  return true;
-}
-
-// TopologyMatch.Filter -> reason code
+// TopologyMatch.Filter -> reason code (filter.go:176-225, handlers :39-78 / :162-173).
+//
+// resourcesAvailableInAnyNUMANodes (:90-160) as a branch-free dominance test.  The node side is pre-encoded once
+// per tile (kernel prologue): avail[z][r] = Available where the zone lists r; INT64_MIN where it does not but
+// another zone does (never suitable, :121-125); INT64_MAX where NO zone lists r and r is host-level (no constraint,
+// :139-142); INT64_MIN where no zone lists a NUMA-bound resource (bitmask becomes empty, :144-148).  The pod side
+// is pre-encoded per tile in shared memory: eff[r] = INT64_MIN if r is not requested or zero (:101-105: passes
+// everywhere), INT64_MIN+1 if the pod is not Guaranteed and r is NUMA-affine (isResourceSetSuitable :137-142:
+// every LISTING zone is suitable), else the quantity.  Zone z survives iff avail[z][r] >= eff[r] for all r; the chosen NUMA id is the lowest
+// surviving zone (an unconstrained request keeps the all-ones mask -> id 0, :154).
 template <int Z, int R>
 __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t node_res_mask, const NrtCfg& cfg,
                           const PodS<R>& pod) {
@@ -145,34 +131,39 @@ __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t 
   if (!(nflags & B200S_NRT_NODE_FRESH)) return B200S_REASON_NRT_INVALID_TOPOLOGY;
   if (!(nflags & B200S_NRT_NODE_HAS_NRT)) return B200S_REASON_OK;
   if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return B200S_REASON_OK;
-  // One loop for both scopes (one call site of the unrolled zone x resource test keeps the kernel's
-  // code small — the round-1 profile was instruction-fetch bound): pod scope = a single step on the
-  // pod-effective request (slot C_MAX, singleNUMAPodLevelHandler :162-173); container scope = init
-  // containers without subtraction, then app containers with it (:39-78).
+  // One loop for both scopes: pod scope = a single step on the pod-effective request (slot C_MAX,
+  // singleNUMAPodLevelHandler :162-173); container scope = init containers without subtraction, then app
+  // containers with it (:39-78).
   const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
   const int n_init = pod.n_init, steps = scope_pod ? 1 : n_init + pod.n_app;
   Zones<Z, R> zs = node_zs;  // working copy: app containers subtract what they take
   for (int s = 0; s < steps; ++s) {
     const int c = scope_pod ? C_MAX : s;
-    const uint32_t rm = pod.req_mask[c];
-    int numa_id = 0;
-    if (!available_in_any<Z, R>(zs, node_res_mask, cfg, pod.qos, rm, pod.req[c], numa_id)) {
+    uint32_t ok = 0;
+    if (!(pod.need[c] & ~node_res_mask)) {  // every requested resource is reported at node level (:107-113)
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        bool fits = true;
+#pragma unroll
+        for (int r = 0; r < R; ++r) fits &= zs.avail[z][r] >= pod.eff[c][r];
+        ok |= (fits ? 1u : 0u) << z;
+      }
+    }
+    if (ok == 0) {
       if (scope_pod) return B200S_REASON_NRT_ALIGN_POD;
       if (s >= n_init) return B200S_REASON_NRT_ALIGN_CONTAINER;
       return pod.kind[c] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT;
     }
     if (scope_pod || s < n_init) continue;
-    // subtractResourcesFromNUMANodeList (numaresources.go:145-182)
+    // subtractResourcesFromNUMANodeList (numaresources.go:145-182) on the zone with the lowest surviving id
+    const int numa_id = __ffs(ok) - 1;
 #pragma unroll
     for (int z = 0; z < Z; ++z) {
-      if (z != numa_id || z >= zs.nz) continue;
+      if (z != numa_id) continue;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (!((rm >> r) & 1u)) continue;
-        if (pod.qos != B200S_QOS_GUARANTEED && (cfg.res_flags[r] & B200S_NRT_RES_AFFINE)) continue;
-        const int64_t q = pod.req[c][r];
-        if (q == 0) continue;
-        if (!((zs.zmask[z] >> r) & 1u)) continue;
+        const int64_t q = pod.sub[c][r];
+        if (q == 0 || !((zs.zmask[z] >> r) & 1u)) continue;  // zero / QoS-exempt / resource missing in the zone
         const int64_t left = zs.avail[z][r] - q;
         if (left < 0) return B200S_REASON_NRT_ACCOUNTING;
         zs.avail[z][r] = left;
@@ -295,7 +286,8 @@ __device__ int numa_nodes_required(const Zones<Z, R>& zs, const int32_t (&cost)[
         if (!((m >> z) & 1u)) continue;
         if ((zs.zmask[z] & req_mask) != req_mask) valid = false;  // isValidCombineResources
 #pragma unroll
-        for (int r = 0; r < R; ++r) sum[r] += zs.avail[z][r];
+        for (int r = 0; r < R; ++r)
+          if ((zs.zmask[z] >> r) & 1u) sum[r] += zs.avail[z][r];  // unlisted cells hold filter sentinels
       }
       if (!valid) continue;
       bool fit = true;
@@ -427,6 +419,13 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
     const int64_t q = r < nc.Rs ? pc.req[((size_t)(p0 + pp) * (C_MAX + 1) + c) * nc.Rs + r] : 0;
     sp[pp].req[c][r] = q;
     sp[pp].reqv[c][r] = q >= 0 ? (q + 999) / 1000 : -((-q) / 1000);
+    {
+      const uint32_t m = r < nc.Rs ? pc.req_mask[(size_t)(p0 + pp) * (C_MAX + 1) + c] : 0u;
+      const bool needed = ((m >> r) & 1u) && q != 0;
+      const bool exempt = pc.qos[p0 + pp] != B200S_QOS_GUARANTEED && (cfg.res_flags[r] & B200S_NRT_RES_AFFINE);
+      sp[pp].eff[c][r] = needed ? (exempt ? INT64_MIN + 1 : q) : INT64_MIN;
+      sp[pp].sub[c][r] = (needed && !exempt) ? q : 0;
+    }
   }
   for (int i = threadIdx.x; i < pend; i += 128) {
     const int p = p0 + i;
@@ -435,7 +434,14 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
     sp[i].n_init = pc.n_init[p];
     sp[i].n_app = pc.n_app[p];
     for (int c = 0; c < C_MAX; ++c) sp[i].kind[c] = pc.kind[(size_t)p * C_MAX + c];
-    for (int c = 0; c <= C_MAX; ++c) sp[i].req_mask[c] = pc.req_mask[(size_t)p * (C_MAX + 1) + c];
+    for (int c = 0; c <= C_MAX; ++c) {
+      const uint32_t m = pc.req_mask[(size_t)p * (C_MAX + 1) + c];
+      sp[i].req_mask[c] = (uint8_t)m;
+      uint32_t need = 0;
+      for (int r = 0; r < nc.Rs; ++r)
+        if (((m >> r) & 1u) && pc.req[((size_t)p * (C_MAX + 1) + c) * nc.Rs + r] != 0) need |= 1u << r;
+      sp[i].need[c] = (uint8_t)need;
+    }
   }
   // this thread's node: zones x resources block into registers, once for the whole pod tile
   Zones<Z, R> zs;
@@ -462,6 +468,20 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
       for (int z2 = 0; z2 < Z; ++z2)
         cost[z][z2] = (in && nc.cost && z < nc.Zs && z2 < nc.Zs) ? nc.cost[((size_t)z * nc.Zs + z2) * Npad + n] : -1;
     }
+  }
+  // filter encoding of the node (see nrt_filter): zones beyond nz list nothing
+#pragma unroll
+  for (int z = 0; z < Z; ++z)
+    if (z >= zs.nz) zs.zmask[z] = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) any |= (zs.zmask[z] >> r) & 1u;
+    const int64_t none = (!any && (cfg.res_flags[r] & B200S_NRT_RES_HOST_LEVEL)) ? INT64_MAX : INT64_MIN;
+#pragma unroll
+    for (int z = 0; z < Z; ++z)
+      if (!((zs.zmask[z] >> r) & 1u)) zs.avail[z][r] = none;
   }
   __syncthreads();
   if (!in) return;
