@@ -184,6 +184,46 @@ def cycle_latency(E, synth, device, N, cycles=1000):
         eng.fetch_topk()
 
     res["all_five_plugins_top1"] = p50(combined)
+
+    # snapshot refresh between two cycles: a node event changes a few NodeInfos.  Either the host
+    # re-uploads every column of all five plugins, or it patches the 16 rows that changed; both leave the engine
+    # ready for the next cycle (the patch re-sorts Allocatable's raw scores at the next eval, so one eval is inside).
+    g = np.random.default_rng(seed)
+    idx = np.sort(g.choice(N, size=16, replace=False)).astype(np.int32)
+    nrt_rows = {k: np.ascontiguousarray(np.asarray(nn[k])[..., idx])
+                for k in ("node_flags", "max_numa", "n_zones_node", "node_res_mask", "zone_res_mask", "avail", "cost")}
+    nrt_rows.update(n_zones=nn["n_zones"], n_res=nn["n_res"])
+    gen = [2]
+
+    def refresh_patch():
+        gen[0] += 1
+        eng.snapshot_patch_begin(gen[0])
+        eng.snapshot_patch_allocatable(idx, [nodes["alloc_cpu_milli"][idx], nodes["alloc_mem_bytes"][idx]])
+        eng.snapshot_patch_tlp(idx, tri["cpu_avg"][idx], nodes["cap_cpu_milli"][idx], tri["missing_milli"][idx],
+                               tri["tlp_flags"][idx])
+        eng.snapshot_patch_lvrb(idx, tri["cpu_avg"][idx], tri["cpu_std"][idx], tri["mem_avg"][idx], tri["mem_std"][idx],
+                                nodes["alloc_cpu_milli"][idx], nodes["alloc_mem_bytes"][idx], tri["lvrb_flags"][idx])
+        eng.snapshot_patch_nrt(idx, nrt_rows)
+        eng.snapshot_patch_network_overhead(idx, net["region_all"][idx], net["zone_all"][idx])
+        eng.snapshot_commit()
+        eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, E.OUT_U8, row)
+
+    def refresh_full():
+        gen[0] += 1
+        eng.snapshot_begin(N, generation=gen[0])
+        eng.snapshot_allocatable([nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]])
+        eng.snapshot_tlp(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"])
+        eng.snapshot_lvrb(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"], nodes["alloc_cpu_milli"],
+                          nodes["alloc_mem_bytes"], tri["lvrb_flags"])
+        eng.snapshot_nrt(nn)
+        eng.snapshot_network_overhead(net["region_all"], net["zone_all"], net["zone_cost"], net["region_cost"])
+        eng.snapshot_commit()
+        eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, E.OUT_U8, row)
+
+    full_cycles, cycles = cycles, max(20, cycles // 10)
+    res["snapshot_refresh_16_rows_patch_plus_cycle"] = p50(refresh_patch)
+    res["snapshot_refresh_full_upload_plus_cycle"] = p50(refresh_full)
+    cycles = full_cycles
     out.free()
     eng.close()
     # the same cycle on the CPU: one pod x N nodes through the Go-faithful restatement of

@@ -192,6 +192,34 @@ int b200s_snapshot_network_overhead(b200s_ctx* ctx, const uint16_t* region_id,
 
 int b200s_snapshot_commit(b200s_ctx* ctx);
 
+/* ---- incremental snapshot: rewrite a few node rows of the resident columns ----
+ * Upstream's scheduler cache refreshes its snapshot by per-node generation, the NRT cache carries its
+ * own generation (pkg/noderesourcetopology/cache/cache.go:27-39, overreserve.go:101-127) and a bind
+ * touches one node's Trimaran bookkeeping (pkg/trimaran/handler.go:131-167): between two cycles only a
+ * handful of nodes change.  b200s_snapshot_patch_begin re-opens the COMMITTED snapshot (same node list,
+ * same N, same column shapes); each b200s_snapshot_patch_* call rewrites `count` rows of one plugin's
+ * columns in place (one host->device copy + one scatter launch); b200s_snapshot_commit closes it and
+ * re-derives what depends on the rows (Allocatable's sorted raw scores, NRT's thread permutation,
+ * NetworkOverhead's label-pair dictionary).  node_idx[count] are shard-local node indices in [0, N);
+ * when an index repeats, the last row wins.  Value arrays hold `count` elements per column, in the
+ * layouts of the full calls with N replaced by count.  A plugin whose columns were never uploaded in
+ * full returns B200S_ERR_STATE.  The pod batch and the plugin args stay valid; results of earlier evals
+ * do not. */
+int b200s_snapshot_patch_begin(b200s_ctx* ctx, uint64_t generation);
+int b200s_snapshot_patch_allocatable(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, int32_t n_res,
+                                     const int64_t* const* alloc);
+int b200s_snapshot_patch_tlp(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const double* cpu_util_pct,
+                             const int64_t* cap_milli, const int64_t* missing_milli, const uint8_t* flags);
+int b200s_snapshot_patch_lvrb(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const double* cpu_avg,
+                              const double* cpu_std, const double* mem_avg, const double* mem_std,
+                              const int64_t* alloc_cpu_milli, const int64_t* alloc_mem_bytes, const uint8_t* flags);
+/* rows->n_zones / n_res must equal the resident snapshot's; rows->res_flags is ignored; rows->cost must be
+ * non-NULL iff the snapshot has costs. */
+int b200s_snapshot_patch_nrt(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const b200s_nrt_nodes* rows);
+/* labels only (ids into the resident name dictionary); a changed cost table needs the full call */
+int b200s_snapshot_patch_network_overhead(b200s_ctx* ctx, int32_t count, const int32_t* node_idx,
+                                          const uint16_t* region_id, const uint16_t* zone_id);
+
 /* ---- plugin args (per ctx = per profile; TLP's package-level globals of the
  * reference, targetloadpacking.go:49-53, become per-instance here) ----------- */
 int b200s_config_allocatable(b200s_ctx* ctx, int mode, int32_t n_res, const int64_t* weights);

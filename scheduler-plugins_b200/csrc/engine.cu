@@ -29,6 +29,151 @@ int upload_col(b200s_ctx* c, DevBuf& dst, size_t dst_off_elems, const T* src, in
   return B200S_OK;
 }
 
+// NRT thread-slot permutation: warps of the P x N kernel get nodes of one control-flow class (flags, zone count)
+// so pod-scope and container-scope nodes do not serialise inside a warp.  Stable counting sort over the host
+// mirror of the class keys: equal-class nodes keep their order, so runs stay coalesced.
+int upload_nrt_perm(b200s_ctx* c) {
+  const size_t np = c->Npad;
+  std::vector<int32_t> perm(np);
+  std::vector<uint32_t> start(65537, 0);
+  for (int i = 0; i < c->N; ++i) start[(size_t)c->nrt_key_h[i] + 1]++;
+  for (size_t k = 1; k <= 65536; ++k) start[k] += start[k - 1];
+  for (int i = 0; i < c->N; ++i) perm[start[c->nrt_key_h[i]]++] = i;
+  for (size_t i = c->N; i < np; ++i) perm[i] = (int32_t)i;
+  B200S_CUDA_TRY(c, c->nrt_perm.ensure(np * 4));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->nrt_perm.p, perm.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // perm dies at return
+  c->nrt_perm_dirty = false;
+  return B200S_OK;
+}
+
+// NetworkOverhead pair dictionary: id of the (region, zone) label pair, appended on first sight.
+int32_t netoh_pair_of(b200s_ctx* c, uint16_t region, uint16_t zone) {
+  const uint32_t key = ((uint32_t)region << 16) | zone;
+  auto it = c->netoh_dict.find(key);
+  if (it != c->netoh_dict.end()) return it->second;
+  const int32_t id = (int32_t)c->netoh_pair_r_h.size();
+  c->netoh_dict.emplace(key, id);
+  c->netoh_pair_r_h.push_back(region);
+  c->netoh_pair_z_h.push_back(zone);
+  c->netoh_pairs_dirty = true;
+  return id;
+}
+
+int upload_netoh_pairs(b200s_ctx* c) {
+  if (c->netoh_pair_r_h.empty()) netoh_pair_of(c, 0, 0);
+  const size_t nq = c->netoh_pair_r_h.size();
+  c->netoh_NQ = (int)nq;
+  B200S_CUDA_TRY(c, c->netoh_pair_r.ensure(nq * 2));
+  B200S_CUDA_TRY(c, c->netoh_pair_z.ensure(nq * 2));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_r.p, c->netoh_pair_r_h.data(), nq * 2, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_z.p, c->netoh_pair_z_h.data(), nq * 2, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources: do not let them change under the copy
+  c->netoh_pairs_dirty = false;
+  return B200S_OK;
+}
+
+// ---- snapshot patch: `count` rows of up to a few hundred columns, one copy + one scatter launch
+struct PatchCol {
+  void* dst;          // device column base (element 0 = node 0)
+  uint32_t src_off;   // byte offset of the column's `count` values inside the staged block
+  uint32_t elem;      // element size: 1, 2, 4 or 8
+};
+
+__global__ void patch_scatter_kernel(const unsigned char* __restrict__ stage, const PatchCol* __restrict__ cols,
+                                     const int32_t* __restrict__ idx, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const PatchCol pc = cols[blockIdx.y];
+  const size_t n = (size_t)idx[i];
+  const unsigned char* src = stage + pc.src_off;
+  switch (pc.elem) {
+    case 8: static_cast<uint64_t*>(pc.dst)[n] = reinterpret_cast<const uint64_t*>(src)[i]; break;
+    case 4: static_cast<uint32_t*>(pc.dst)[n] = reinterpret_cast<const uint32_t*>(src)[i]; break;
+    case 2: static_cast<uint16_t*>(pc.dst)[n] = reinterpret_cast<const uint16_t*>(src)[i]; break;
+    default: static_cast<uint8_t*>(pc.dst)[n] = src[i]; break;
+  }
+}
+
+// Collects the columns of one patch call, packs them behind the index list and launches the scatter.
+// Repeated indices: rows are de-duplicated on the host (last wins) so that the scatter has no write race.
+struct Patch {
+  b200s_ctx* c;
+  int count;
+  std::vector<int32_t> keep;  // positions of the surviving rows, ascending
+  struct Item {
+    void* dst;
+    const void* src;
+    uint32_t elem;
+  };
+  std::vector<Item> items;
+  Patch(b200s_ctx* ctx, int n) : c(ctx), count(n) {}
+  int prepare(const int32_t* node_idx) {
+    if (count < 0 || (count > 0 && !node_idx)) return c->set_err(B200S_ERR_INVALID, "snapshot_patch: bad count / null node_idx");
+    std::unordered_map<int32_t, int32_t> last;
+    for (int i = 0; i < count; ++i) {
+      if (node_idx[i] < 0 || node_idx[i] >= c->N) return c->set_err(B200S_ERR_INVALID, "snapshot_patch: node index out of range");
+      last[node_idx[i]] = i;
+    }
+    keep.reserve(last.size());
+    for (int i = 0; i < count; ++i)
+      if (last[node_idx[i]] == i) keep.push_back(i);
+    return B200S_OK;
+  }
+  template <class T>
+  void add(DevBuf& dst, size_t dst_off_elems, const T* src) {
+    items.push_back({dst.as<T>() + dst_off_elems, src, (uint32_t)sizeof(T)});
+  }
+  int run(const int32_t* node_idx) {
+    const int m = (int)keep.size();
+    if (m == 0 || items.empty()) return B200S_OK;
+    auto up8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+    const size_t idx_bytes = up8((size_t)m * 4), desc_bytes = up8(items.size() * sizeof(PatchCol));
+    size_t total = idx_bytes + desc_bytes;
+    std::vector<PatchCol> desc(items.size());
+    for (size_t k = 0; k < items.size(); ++k) {
+      desc[k] = {items[k].dst, (uint32_t)total, items[k].elem};
+      total += up8((size_t)m * items[k].elem);
+    }
+    if (total > ((size_t)1 << 31)) return c->set_err(B200S_ERR_INVALID, "snapshot_patch: too many rows for one call");
+    if (total > c->patch_stage_cap) {
+      if (c->patch_stage) cudaFreeHost(c->patch_stage);
+      c->patch_stage = nullptr;
+      c->patch_stage_cap = 0;
+      B200S_CUDA_TRY(c, cudaHostAlloc(&c->patch_stage, total * 2, cudaHostAllocDefault));
+      c->patch_stage_cap = total * 2;
+    }
+    B200S_CUDA_TRY(c, c->patch_dev.ensure(total));
+    char* st = static_cast<char*>(c->patch_stage);
+    int32_t* sidx = reinterpret_cast<int32_t*>(st);
+    for (int j = 0; j < m; ++j) sidx[j] = node_idx[keep[j]];
+    memcpy(st + idx_bytes, desc.data(), items.size() * sizeof(PatchCol));
+    for (size_t k = 0; k < items.size(); ++k) {
+      char* d = st + desc[k].src_off;
+      const char* sp = static_cast<const char*>(items[k].src);
+      const uint32_t e = items[k].elem;
+      for (int j = 0; j < m; ++j) memcpy(d + (size_t)j * e, sp + (size_t)keep[j] * e, e);
+    }
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->patch_dev.p, st, total, cudaMemcpyHostToDevice, c->stream));
+    const unsigned char* dev = c->patch_dev.as<unsigned char>();
+    dim3 grid((m + 255) / 256, (unsigned)items.size());
+    patch_scatter_kernel<<<grid, 256, 0, c->stream>>>(dev, reinterpret_cast<const PatchCol*>(dev + idx_bytes),
+                                                      reinterpret_cast<const int32_t*>(dev), m);
+    B200S_CUDA_TRY(c, cudaGetLastError());
+    // the staging buffer is re-used by the next patch call of this session
+    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->launches++;
+    return B200S_OK;
+  }
+};
+
+int require_patching(b200s_ctx* c, bool has, const char* what) {
+  if (!c->snap_open || !c->snap_patching)
+    return c->set_err(B200S_ERR_STATE, std::string(what) + " outside b200s_snapshot_patch_begin/commit");
+  if (!has) return c->set_err(B200S_ERR_STATE, std::string(what) + ": these columns were never uploaded in full");
+  return B200S_OK;
+}
+
 int require_open(b200s_ctx* c) {
   if (!c->snap_open) return c->set_err(B200S_ERR_STATE, "snapshot column set outside b200s_snapshot_begin/commit");
   return B200S_OK;
@@ -119,6 +264,8 @@ void b200s_shutdown(b200s_ctx* c) {
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   c->pods_arena.release();
   if (c->pods_stage) cudaFreeHost(c->pods_stage);
+  c->patch_dev.release();
+  if (c->patch_stage) cudaFreeHost(c->patch_stage);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -188,6 +335,7 @@ int b200s_snapshot_begin(b200s_ctx* c, uint64_t generation, int32_t n_nodes, int
   if (n_nodes < 0 || node_offset < 0 || n_nodes_global < n_nodes + node_offset)
     return c->set_err(B200S_ERR_INVALID, "snapshot_begin: bad node counts");
   c->snap_open = true;
+  c->snap_patching = false;
   c->snap_valid = false;
   c->pods_valid = false;
   c->gen = generation;
@@ -288,16 +436,9 @@ int b200s_snapshot_nrt(b200s_ctx* c, const b200s_nrt_nodes* nn) {
                                   c->N, c->Npad));
   for (int i = 0; i < Z * R; ++i)
     B200S_TRY(upload_col<int64_t>(c, c->nrt_avail, (size_t)i * np, nn->avail + (size_t)i * c->N, c->N, c->Npad));
-  {  // thread-slot permutation: warps of the P x N kernel get nodes of one control-flow class (flags, zone
-     // count) so pod-scope and container-scope nodes do not serialise inside a warp (stable: runs stay coalesced)
-    std::vector<int32_t> perm(np);
-    for (size_t i = 0; i < np; ++i) perm[i] = (int32_t)i;
-    auto key = [&](int32_t i) { return ((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]; };
-    std::stable_sort(perm.begin(), perm.begin() + c->N, [&](int32_t a, int32_t b) { return key(a) < key(b); });
-    B200S_CUDA_TRY(c, c->nrt_perm.ensure(np * 4));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->nrt_perm.p, perm.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  }
+  c->nrt_key_h.resize((size_t)std::max(c->N, 0));
+  for (int i = 0; i < c->N; ++i) c->nrt_key_h[i] = (uint16_t)(((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]);
+  B200S_TRY(upload_nrt_perm(c));
   c->nrt_has_cost = nn->cost != nullptr;
   if (nn->cost) {
     B200S_CUDA_TRY(c, c->nrt_cost.ensure((size_t)Z * Z * np * 4));
@@ -327,30 +468,13 @@ int b200s_snapshot_network_overhead(b200s_ctx* c, const uint16_t* region_id, con
   B200S_TRY(upload_col<uint16_t>(c, c->netoh_zone, 0, zone_id, c->N, c->Npad));
   {  // pair dictionary (host side of the flattening, O(N))
     std::vector<int32_t> pid(np, 0);
-    std::vector<uint16_t> pr, pz;
-    std::unordered_map<uint32_t, int32_t> dict;
-    for (int i = 0; i < c->N; ++i) {
-      const uint32_t key = ((uint32_t)region_id[i] << 16) | zone_id[i];
-      auto it = dict.find(key);
-      if (it == dict.end()) {
-        it = dict.emplace(key, (int32_t)pr.size()).first;
-        pr.push_back(region_id[i]);
-        pz.push_back(zone_id[i]);
-      }
-      pid[i] = it->second;
-    }
-    if (pr.empty()) {
-      pr.push_back(0);
-      pz.push_back(0);
-    }
-    c->netoh_NQ = (int)pr.size();
+    c->netoh_dict.clear();
+    c->netoh_pair_r_h.clear();
+    c->netoh_pair_z_h.clear();
+    for (int i = 0; i < c->N; ++i) pid[i] = netoh_pair_of(c, region_id[i], zone_id[i]);
     B200S_CUDA_TRY(c, c->netoh_pair_id.ensure(np * 4));
-    B200S_CUDA_TRY(c, c->netoh_pair_r.ensure(pr.size() * 2));
-    B200S_CUDA_TRY(c, c->netoh_pair_z.ensure(pz.size() * 2));
     B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_id.p, pid.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_r.p, pr.data(), pr.size() * 2, cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_pair_z.p, pz.data(), pz.size() * 2, cudaMemcpyHostToDevice, c->stream));
-    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the vectors die at the end of this scope
+    B200S_TRY(upload_netoh_pairs(c));  // synchronises: pid dies at the end of this scope
   }
   B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_zone_cost.p, zone_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(c->netoh_region_cost.p, region_cost, kk * 8, cudaMemcpyHostToDevice, c->stream));
@@ -364,10 +488,133 @@ int b200s_snapshot_commit(b200s_ctx* c) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
   if (!c->snap_open) return c->set_err(B200S_ERR_STATE, "snapshot_commit without begin");
+  if (c->has_nrt && c->nrt_perm_dirty) B200S_TRY(upload_nrt_perm(c));
+  if (c->has_netoh && c->netoh_pairs_dirty) B200S_TRY(upload_netoh_pairs(c));
   c->snap_open = false;
+  c->snap_patching = false;
   c->snap_valid = true;
   c->snap_serial++;
   return B200S_OK;
+}
+
+// ---------------------------------------------------------------- incremental snapshot
+int b200s_snapshot_patch_begin(b200s_ctx* c, uint64_t generation) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (c->snap_open) return c->set_err(B200S_ERR_STATE, "snapshot_patch_begin: a snapshot is already open");
+  if (!c->snap_valid) return c->set_err(B200S_ERR_STATE, "snapshot_patch_begin: no committed snapshot to patch");
+  c->snap_open = true;
+  c->snap_patching = true;
+  c->snap_valid = false;
+  c->gen = generation;
+  for (auto& o : c->out) o.valid = false;
+  c->total_valid = c->topk_valid = false;
+  c->netoh_raw_P = -1;
+  return B200S_OK;
+}
+
+int b200s_snapshot_patch_allocatable(b200s_ctx* c, int32_t count, const int32_t* node_idx, int32_t n_res,
+                                     const int64_t* const* alloc) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_alloc, "snapshot_patch_allocatable"));
+  if (n_res != c->alloc_R || !alloc) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_allocatable: resource count differs from the snapshot");
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  for (int r = 0; r < n_res; ++r) {
+    if (!alloc[r]) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_allocatable: null column");
+    p.add<int64_t>(c->alloc_cols, (size_t)r * c->Npad, alloc[r]);
+  }
+  return p.run(node_idx);
+}
+
+int b200s_snapshot_patch_tlp(b200s_ctx* c, int32_t count, const int32_t* node_idx, const double* util,
+                             const int64_t* cap, const int64_t* missing, const uint8_t* flags) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_tlp, "snapshot_patch_tlp"));
+  if (!util || !cap || !missing || !flags) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_tlp: null column");
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  p.add<double>(c->tlp_util, 0, util);
+  p.add<int64_t>(c->tlp_cap, 0, cap);
+  p.add<int64_t>(c->tlp_missing, 0, missing);
+  p.add<uint8_t>(c->tlp_flags, 0, flags);
+  return p.run(node_idx);
+}
+
+int b200s_snapshot_patch_lvrb(b200s_ctx* c, int32_t count, const int32_t* node_idx, const double* cpu_avg,
+                              const double* cpu_std, const double* mem_avg, const double* mem_std,
+                              const int64_t* alloc_cpu, const int64_t* alloc_mem, const uint8_t* flags) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_lvrb, "snapshot_patch_lvrb"));
+  if (!cpu_avg || !cpu_std || !mem_avg || !mem_std || !alloc_cpu || !alloc_mem || !flags)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_lvrb: null column");
+  const size_t np = c->Npad;
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  p.add<double>(c->lvrb_f64, 0 * np, cpu_avg);
+  p.add<double>(c->lvrb_f64, 1 * np, cpu_std);
+  p.add<double>(c->lvrb_f64, 2 * np, mem_avg);
+  p.add<double>(c->lvrb_f64, 3 * np, mem_std);
+  p.add<int64_t>(c->lvrb_i64, 0 * np, alloc_cpu);
+  p.add<int64_t>(c->lvrb_i64, 1 * np, alloc_mem);
+  p.add<uint8_t>(c->lvrb_flags, 0, flags);
+  return p.run(node_idx);
+}
+
+int b200s_snapshot_patch_nrt(b200s_ctx* c, int32_t count, const int32_t* node_idx, const b200s_nrt_nodes* nn) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_nrt, "snapshot_patch_nrt"));
+  if (!nn) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt: null");
+  const int Z = c->nrt_Z, R = c->nrt_R;
+  if (nn->n_zones != Z || nn->n_res != R)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt: zone/resource shape differs from the snapshot");
+  if (!nn->node_flags || !nn->max_numa || !nn->n_zones_node || !nn->node_res_mask || !nn->zone_res_mask || !nn->avail)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt: null column");
+  if ((nn->cost != nullptr) != c->nrt_has_cost)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt: cost columns must match the snapshot");
+  const size_t np = c->Npad, cnt = (size_t)std::max(count, 0);
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  p.add<uint8_t>(c->nrt_node_flags, 0, nn->node_flags);
+  p.add<uint16_t>(c->nrt_max_numa, 0, nn->max_numa);
+  p.add<uint8_t>(c->nrt_nz, 0, nn->n_zones_node);
+  p.add<uint8_t>(c->nrt_node_res_mask, 0, nn->node_res_mask);
+  for (int z = 0; z < Z; ++z) p.add<uint8_t>(c->nrt_zone_res_mask, (size_t)z * np, nn->zone_res_mask + (size_t)z * cnt);
+  for (int i = 0; i < Z * R; ++i) p.add<int64_t>(c->nrt_avail, (size_t)i * np, nn->avail + (size_t)i * cnt);
+  if (nn->cost)
+    for (int i = 0; i < Z * Z; ++i) p.add<int32_t>(c->nrt_cost, (size_t)i * np, nn->cost + (size_t)i * cnt);
+  B200S_TRY(p.run(node_idx));
+  for (int i : p.keep) {  // class keys behind the thread permutation
+    const uint16_t key = (uint16_t)(((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]);
+    if (c->nrt_key_h[node_idx[i]] != key) {
+      c->nrt_key_h[node_idx[i]] = key;
+      c->nrt_perm_dirty = true;
+    }
+  }
+  return B200S_OK;
+}
+
+int b200s_snapshot_patch_network_overhead(b200s_ctx* c, int32_t count, const int32_t* node_idx,
+                                          const uint16_t* region_id, const uint16_t* zone_id) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_netoh, "snapshot_patch_network_overhead"));
+  if (!region_id || !zone_id) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_network_overhead: null column");
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  for (int i : p.keep)
+    if (region_id[i] >= c->netoh_K || zone_id[i] >= c->netoh_K)
+      return c->set_err(B200S_ERR_INVALID, "snapshot_patch_network_overhead: label id outside the name dictionary");
+  std::vector<int32_t> pid((size_t)std::max(count, 1), 0);
+  for (int i : p.keep) pid[i] = netoh_pair_of(c, region_id[i], zone_id[i]);
+  p.add<uint16_t>(c->netoh_region, 0, region_id);
+  p.add<uint16_t>(c->netoh_zone, 0, zone_id);
+  p.add<int32_t>(c->netoh_pair_id, 0, pid.data());
+  return p.run(node_idx);
 }
 
 // ---------------------------------------------------------------- plugin args

@@ -4,6 +4,7 @@
 
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -84,7 +85,12 @@ struct b200s_ctx {
 
   // ---- snapshot ----
   bool snap_open = false, snap_valid = false;
+  bool snap_patching = false;  // open through b200s_snapshot_patch_begin: same node list, rows rewritten in place
   uint64_t gen = 0;
+  // patch rows travel like the small pod columns: packed into pinned memory, one copy, one scatter launch
+  void* patch_stage = nullptr;
+  size_t patch_stage_cap = 0;
+  b200s::DevBuf patch_dev;
   int N = 0, Npad = 0, node_off = 0, Nglobal = 0;
 
   // NodeResourcesAllocatable
@@ -125,6 +131,8 @@ struct b200s_ctx {
   uint8_t nrt_res_flags[B200S_NRT_MAX_RES] = {0};
   b200s::DevBuf nrt_node_flags, nrt_max_numa, nrt_nz, nrt_node_res_mask, nrt_zone_res_mask, nrt_avail,
       nrt_cost, nrt_perm;  // nrt_perm [Npad] int32: thread slot -> node, nodes grouped by control-flow class
+  std::vector<uint16_t> nrt_key_h;  // [N] host mirror of the control-flow class (flags << 8 | zones) behind nrt_perm
+  bool nrt_perm_dirty = false;
   bool nrt_cfg = false;
   int nrt_strategy = B200S_NRT_LEAST_ALLOCATED;
   int64_t nrt_w[B200S_NRT_MAX_RES] = {1, 1, 1, 1, 1, 1, 1, 1};
@@ -137,6 +145,10 @@ struct b200s_ctx {
   // only through its pair (plus the few dependencies hosted on the node itself)
   int netoh_NQ = 0;
   b200s::DevBuf netoh_pair_id, netoh_pair_r, netoh_pair_z;  // [Npad] int32, [NQ] u16, [NQ] u16
+  // host mirror of the dictionary, so that a patched node finds (or appends) its pair without a rebuild
+  std::vector<uint16_t> netoh_pair_r_h, netoh_pair_z_h;
+  std::unordered_map<uint32_t, int32_t> netoh_dict;
+  bool netoh_pairs_dirty = false;
   b200s::DevBuf netoh_pair_cost, netoh_pair_sv;              // [P][NQ] int64 cost, u32 satisfied | violated << 16
 
   // ---- pods ----

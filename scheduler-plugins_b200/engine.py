@@ -29,6 +29,8 @@ EXPORTS = [
     "b200s_launch_count", "b200s_comm_unique_id", "b200s_comm_init", "b200s_comm_rank", "b200s_comm_world",
     "b200s_snapshot_begin", "b200s_snapshot_allocatable", "b200s_snapshot_tlp", "b200s_snapshot_lvrb",
     "b200s_snapshot_nrt", "b200s_snapshot_network_overhead", "b200s_snapshot_commit",
+    "b200s_snapshot_patch_begin", "b200s_snapshot_patch_allocatable", "b200s_snapshot_patch_tlp",
+    "b200s_snapshot_patch_lvrb", "b200s_snapshot_patch_nrt", "b200s_snapshot_patch_network_overhead",
     "b200s_config_allocatable", "b200s_config_tlp", "b200s_config_lvrb", "b200s_config_nrt",
     "b200s_config_network_overhead", "b200s_fetch_network_overhead_raw", "b200s_fetch_network_overhead_counts",
     "b200s_pods_upload", "b200s_eval", "b200s_fetch_scores", "b200s_fetch_feasible", "b200s_fetch_reasons",
@@ -253,6 +255,59 @@ class Engine:
 
     def snapshot_commit(self):
         self._chk(self.lib.b200s_snapshot_commit(self.ctx))
+
+    # -- incremental snapshot: rewrite a few node rows in place (same node list) -------------
+    def snapshot_patch_begin(self, generation=0):
+        self._chk(self.lib.b200s_snapshot_patch_begin(self.ctx, C.c_uint64(generation)))
+
+    def _idx(self, node_idx):
+        return _arr(node_idx, np.int32)
+
+    def snapshot_patch_allocatable(self, node_idx, cols):
+        idx = self._idx(node_idx)
+        cols = [_arr(c, np.int64, (len(idx),)) for c in cols]
+        arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        self._chk(self.lib.b200s_snapshot_patch_allocatable(self.ctx, C.c_int32(len(idx)), _ptr(idx),
+                                                            C.c_int32(len(cols)), arr))
+
+    def snapshot_patch_tlp(self, node_idx, cpu_util_pct, cap_milli, missing_milli, flags):
+        idx = self._idx(node_idx); m = (len(idx),)
+        a = _arr(cpu_util_pct, np.float64, m); b = _arr(cap_milli, np.int64, m)
+        c = _arr(missing_milli, np.int64, m); d = _arr(flags, np.uint8, m)
+        self._chk(self.lib.b200s_snapshot_patch_tlp(self.ctx, C.c_int32(len(idx)), _ptr(idx), _ptr(a), _ptr(b),
+                                                    _ptr(c), _ptr(d)))
+
+    def snapshot_patch_lvrb(self, node_idx, cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu_milli, alloc_mem_bytes,
+                            flags):
+        idx = self._idx(node_idx); m = (len(idx),)
+        f = [_arr(x, np.float64, m) for x in (cpu_avg, cpu_std, mem_avg, mem_std)]
+        i = [_arr(x, np.int64, m) for x in (alloc_cpu_milli, alloc_mem_bytes)]
+        fl = _arr(flags, np.uint8, m)
+        self._chk(self.lib.b200s_snapshot_patch_lvrb(self.ctx, C.c_int32(len(idx)), _ptr(idx),
+                                                     *[_ptr(x) for x in f], *[_ptr(x) for x in i], _ptr(fl)))
+
+    def snapshot_patch_nrt(self, node_idx, rows: dict):
+        """rows: the dict of snapshot_nrt with every [..][N] array cut down to [..][len(node_idx)]."""
+        idx = self._idx(node_idx); m = len(idx)
+        Z, R = int(rows["n_zones"]), int(rows["n_res"])
+        keep = dict(
+            node_flags=_arr(rows["node_flags"], np.uint8, (m,)),
+            max_numa=_arr(rows["max_numa"], np.uint16, (m,)),
+            n_zones_node=_arr(rows["n_zones_node"], np.uint8, (m,)),
+            node_res_mask=_arr(rows["node_res_mask"], np.uint8, (m,)),
+            zone_res_mask=_arr(rows["zone_res_mask"], np.uint8, (Z, m)),
+            avail=_arr(rows["avail"], np.int64, (Z, R, m)),
+            cost=None if rows.get("cost") is None else _arr(rows["cost"], np.int32, (Z, Z, m)),
+        )
+        s = NrtNodes(Z, R, None, *[_ptr(keep[k]) for k in ("node_flags", "max_numa", "n_zones_node",
+                                                           "node_res_mask", "zone_res_mask", "avail", "cost")])
+        self._chk(self.lib.b200s_snapshot_patch_nrt(self.ctx, C.c_int32(m), _ptr(idx), C.byref(s)))
+
+    def snapshot_patch_network_overhead(self, node_idx, region_id, zone_id):
+        idx = self._idx(node_idx); m = (len(idx),)
+        a = _arr(region_id, np.uint16, m); b = _arr(zone_id, np.uint16, m)
+        self._chk(self.lib.b200s_snapshot_patch_network_overhead(self.ctx, C.c_int32(len(idx)), _ptr(idx), _ptr(a),
+                                                                 _ptr(b)))
 
     # -- plugin args ----------------------------------------------------------------------
     def config_allocatable(self, mode, weights):

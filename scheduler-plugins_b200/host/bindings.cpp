@@ -125,7 +125,13 @@ PYBIND11_MODULE(_b200host, m) {
       .def_readwrite("nrt_not_fresh", &Handle::nrt_not_fresh)
       .def_readwrite("app_groups", &Handle::app_groups)
       .def_readwrite("network_topologies", &Handle::network_topologies)
-      .def("touch", &Handle::Touch);
+      .def("touch", &Handle::Touch)
+      .def("touch_node", &Handle::TouchNode)
+      .def("nodes_changed_since", [](const Handle& h, uint64_t g) -> py::object {
+        std::vector<int32_t> idx;
+        if (!h.NodesChangedSince(g, &idx)) return py::none();
+        return py::cast(idx);
+      });
   py::class_<CycleState>(m, "CycleState").def(py::init<>());
 
   py::class_<ResourceSpec>(m, "ResourceSpec")
@@ -140,6 +146,7 @@ PYBIND11_MODULE(_b200host, m) {
       .def("name", &Allocatable::Name)
       .def("pre_score", &Allocatable::PreScore)
       .def("score", &Allocatable::Score)
+      .def("patched_rows", &Allocatable::PatchedRows)
       .def("normalize_score", [](Allocatable& a, CycleState& s, const Pod& p, std::vector<NodeScore> l) {
         Status st = a.NormalizeScore(s, p, l);
         return std::make_pair(st, l);
@@ -153,7 +160,8 @@ PYBIND11_MODULE(_b200host, m) {
       .def_static("new", &TargetLoadPacking::New)
       .def("name", &TargetLoadPacking::Name)
       .def("pre_score", &TargetLoadPacking::PreScore)
-      .def("score", &TargetLoadPacking::Score);
+      .def("score", &TargetLoadPacking::Score)
+      .def("patched_rows", &TargetLoadPacking::PatchedRows);
   py::class_<LoadVariationRiskBalancingArgs>(m, "LoadVariationRiskBalancingArgs")
       .def(py::init<>())
       .def_readwrite("safe_variance_margin", &LoadVariationRiskBalancingArgs::safe_variance_margin)
@@ -162,7 +170,8 @@ PYBIND11_MODULE(_b200host, m) {
       .def_static("new", &LoadVariationRiskBalancing::New)
       .def("name", &LoadVariationRiskBalancing::Name)
       .def("pre_score", &LoadVariationRiskBalancing::PreScore)
-      .def("score", &LoadVariationRiskBalancing::Score);
+      .def("score", &LoadVariationRiskBalancing::Score)
+      .def("patched_rows", &LoadVariationRiskBalancing::PatchedRows);
   py::class_<NodeResourceTopologyMatchArgs>(m, "NodeResourceTopologyMatchArgs")
       .def(py::init<>())
       .def_readwrite("scoring_strategy", &NodeResourceTopologyMatchArgs::scoring_strategy)

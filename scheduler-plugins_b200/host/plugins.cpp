@@ -108,8 +108,52 @@ static int64_t AllocatableColumn(const Node& n, const std::string& res) {
   return 0;
 }
 
+bool Handle::NodesChangedSince(uint64_t g, std::vector<int32_t>* out) const {
+  if (g < log_base_ || g > generation) return false;
+  std::vector<int32_t> idx;
+  uint64_t logged = 0;
+  for (auto it = node_log_.rbegin(); it != node_log_.rend() && it->first > g; ++it, ++logged) idx.push_back(it->second);
+  if (logged != generation - g) return false;  // generation moved without a log entry (set directly)
+  std::sort(idx.begin(), idx.end());
+  idx.erase(std::unique(idx.begin(), idx.end()), idx.end());
+  for (int32_t i : idx)
+    if (i < 0 || i >= (int32_t)node_infos.size()) return false;
+  *out = std::move(idx);
+  return true;
+}
+
+// A patch pays off while few rows changed; past a quarter of the nodes one bulk upload is cheaper.
+static bool WorthPatching(size_t changed, int32_t n) { return changed * 4 <= (size_t)std::max(n, 1); }
+
+bool Allocatable::PatchSnapshot() {
+  std::vector<int32_t> idx;
+  if (snap_gen_ == 0 || n_ != (int32_t)h_->node_infos.size() || !h_->NodesChangedSince(snap_gen_, &idx) ||
+      !WorthPatching(idx.size(), n_))
+    return false;
+  const auto& nodes = h_->node_infos;
+  for (int32_t i : idx) {  // the name -> column map must still hold
+    const Node* nd = nodes[i].GetNode();
+    auto it = nd ? index_.find(nd->name) : index_.end();
+    if (nd && (it == index_.end() || it->second != i)) return false;
+  }
+  std::vector<std::vector<int64_t>> cols(res_.size(), std::vector<int64_t>(std::max<size_t>(idx.size(), 1), 0));
+  for (size_t j = 0; j < idx.size(); ++j)
+    if (const Node* nd = nodes[idx[j]].GetNode())
+      for (size_t r = 0; r < res_.size(); ++r) cols[r][j] = AllocatableColumn(*nd, res_[r].name);
+  std::vector<const int64_t*> ptrs;
+  for (auto& c : cols) ptrs.push_back(c.data());
+  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+  eng_->Check(b200s_snapshot_patch_allocatable(eng_->ctx(), (int32_t)idx.size(), idx.data(), (int32_t)ptrs.size(), ptrs.data()),
+              "snapshot_patch_allocatable");
+  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  snap_gen_ = h_->generation;
+  patched_rows_ += (int64_t)idx.size();
+  return true;
+}
+
 void Allocatable::EnsureSnapshot() {
   if (snap_gen_ == h_->generation && n_ == (int32_t)h_->node_infos.size()) return;
+  if (PatchSnapshot()) return;
   const auto& nodes = h_->node_infos;
   n_ = (int32_t)nodes.size();
   npad_ = NPad(n_);
@@ -185,8 +229,66 @@ std::unique_ptr<TargetLoadPacking> TargetLoadPacking::New(const TargetLoadPackin
   return p;
 }
 
+TargetLoadPacking::Row TargetLoadPacking::FlattenRow(const NodeInfo& ni) const {
+  Row row;
+  const Node* nd = ni.GetNode();
+  if (!nd) return row;
+  row.cap = Get(nd->capacity, ResourceCPU);  // Status.Capacity, targetloadpacking.go:146
+  const WatcherMetrics* wm = h_->metrics.get();
+  // GetNodeMetrics: collector.go:110-123
+  if (!wm || !wm->has_map) return row;
+  auto it = wm->node_metrics.find(nd->name);
+  if (it == wm->node_metrics.end()) return row;
+  row.flags |= B200S_TLP_HAS_METRICS;
+  for (auto& mt : it->second.metrics)  // LAST matching entry wins, :131-140
+    if (mt.type == "CPU" && (mt.op == "AVG" || mt.op == "Latest")) {
+      row.util = mt.value;
+      row.flags |= B200S_TLP_CPU_FOUND;
+    }
+  // missing utilisation of recently bound pods, :151-167
+  auto sc = h_->scheduled_pods_cache.find(nd->name);
+  if (sc != h_->scheduled_pods_cache.end())
+    for (auto& info : sc->second) {
+      const int64_t ts = info.timestamp_unix, end = wm->window_end;
+      if (ts > end || (ts <= end && (end - ts) < 60)) {  // metricsAgentReportingIntervalSeconds = 60, :46
+        for (auto& cont : info.pod->containers)
+          row.missing += PredictUtilisation(cont, args_.default_requests_cpu_milli, multiplier_);
+        row.missing += Get(info.pod->overhead, ResourceCPU);
+      }
+    }
+  return row;
+}
+
+// A bind adds one entry to ScheduledPodsCache[node] (handler.go:131-167): one row changes, the rest stays.
+bool TargetLoadPacking::PatchSnapshot() {
+  std::vector<int32_t> idx;
+  if (snap_gen_ == 0 || n_ != (int32_t)h_->node_infos.size() || !h_->NodesChangedSince(snap_gen_, &idx) ||
+      !WorthPatching(idx.size(), n_))
+    return false;
+  const size_t m = std::max<size_t>(idx.size(), 1);
+  std::vector<double> util(m, 0);
+  std::vector<int64_t> cap(m, 0), missing(m, 0);
+  std::vector<uint8_t> flags(m, 0);
+  for (size_t j = 0; j < idx.size(); ++j) {
+    const NodeInfo& ni = h_->node_infos[idx[j]];
+    auto it = ni.GetNode() ? index_.find(ni.GetNode()->name) : index_.end();
+    if (ni.GetNode() && (it == index_.end() || it->second != idx[j])) return false;
+    const Row row = FlattenRow(ni);
+    util[j] = row.util, cap[j] = row.cap, missing[j] = row.missing, flags[j] = row.flags;
+  }
+  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+  eng_->Check(b200s_snapshot_patch_tlp(eng_->ctx(), (int32_t)idx.size(), idx.data(), util.data(), cap.data(), missing.data(),
+                                       flags.data()),
+              "snapshot_patch_tlp");
+  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  snap_gen_ = h_->generation;
+  patched_rows_ += (int64_t)idx.size();
+  return true;
+}
+
 void TargetLoadPacking::EnsureSnapshot() {
   if (snap_gen_ == h_->generation && n_ == (int32_t)h_->node_infos.size()) return;
+  if (PatchSnapshot()) return;
   const auto& nodes = h_->node_infos;
   n_ = (int32_t)nodes.size();
   npad_ = NPad(n_);
@@ -195,32 +297,9 @@ void TargetLoadPacking::EnsureSnapshot() {
   std::vector<double> util(m, 0);
   std::vector<int64_t> cap(m, 0), missing(m, 0);
   std::vector<uint8_t> flags(m, 0);
-  const WatcherMetrics* wm = h_->metrics.get();
   for (int32_t i = 0; i < n_; ++i) {
-    const Node* nd = nodes[i].GetNode();
-    if (!nd) continue;
-    cap[i] = Get(nd->capacity, ResourceCPU);  // Status.Capacity, targetloadpacking.go:146
-    // GetNodeMetrics: collector.go:110-123
-    if (!wm || !wm->has_map) continue;
-    auto it = wm->node_metrics.find(nd->name);
-    if (it == wm->node_metrics.end()) continue;
-    flags[i] |= B200S_TLP_HAS_METRICS;
-    for (auto& mt : it->second.metrics)  // LAST matching entry wins, :131-140
-      if (mt.type == "CPU" && (mt.op == "AVG" || mt.op == "Latest")) {
-        util[i] = mt.value;
-        flags[i] |= B200S_TLP_CPU_FOUND;
-      }
-    // missing utilisation of recently bound pods, :151-167
-    auto sc = h_->scheduled_pods_cache.find(nd->name);
-    if (sc != h_->scheduled_pods_cache.end())
-      for (auto& info : sc->second) {
-        const int64_t ts = info.timestamp_unix, end = wm->window_end;
-        if (ts > end || (ts <= end && (end - ts) < 60)) {  // metricsAgentReportingIntervalSeconds = 60, :46
-          for (auto& cont : info.pod->containers)
-            missing[i] += PredictUtilisation(cont, args_.default_requests_cpu_milli, multiplier_);
-          missing[i] += Get(info.pod->overhead, ResourceCPU);
-        }
-      }
+    const Row row = FlattenRow(nodes[i]);
+    util[i] = row.util, cap[i] = row.cap, missing[i] = row.missing, flags[i] = row.flags;
   }
   eng_->Check(b200s_snapshot_begin(eng_->ctx(), h_->generation, n_, 0, n_), "snapshot_begin");
   eng_->Check(b200s_snapshot_tlp(eng_->ctx(), util.data(), cap.data(), missing.data(), flags.data()), "snapshot_tlp");
@@ -274,8 +353,54 @@ std::unique_ptr<LoadVariationRiskBalancing> LoadVariationRiskBalancing::New(cons
   return p;
 }
 
+LoadVariationRiskBalancing::Row LoadVariationRiskBalancing::FlattenRow(const NodeInfo& ni) const {
+  Row row;
+  const Node* nd = ni.GetNode();
+  if (!nd) return row;
+  row.acpu = Get(nd->allocatable, ResourceCPU);                    // resourcestats.go:55-59: Allocatable
+  row.amem = QuantityValue(Get(nd->allocatable, ResourceMemory));  // :62 am.Value()
+  const WatcherMetrics* wm = h_->metrics.get();
+  if (!wm || !wm->has_map) return row;
+  auto it = wm->node_metrics.find(nd->name);
+  if (it == wm->node_metrics.end()) return row;
+  row.flags |= B200S_LVRB_HAS_METRICS;
+  bool ok;
+  GetResourceData(it->second.metrics, "CPU", &row.ca, &row.cs, &ok);
+  if (ok) row.flags |= B200S_LVRB_CPU_OK;
+  GetResourceData(it->second.metrics, "Memory", &row.ma, &row.ms, &ok);
+  if (ok) row.flags |= B200S_LVRB_MEM_OK;
+  return row;
+}
+
+bool LoadVariationRiskBalancing::PatchSnapshot() {
+  std::vector<int32_t> idx;
+  if (snap_gen_ == 0 || n_ != (int32_t)h_->node_infos.size() || !h_->NodesChangedSince(snap_gen_, &idx) ||
+      !WorthPatching(idx.size(), n_))
+    return false;
+  const size_t m = std::max<size_t>(idx.size(), 1);
+  std::vector<double> ca(m, 0), cs(m, 0), ma(m, 0), ms(m, 0);
+  std::vector<int64_t> acpu(m, 0), amem(m, 0);
+  std::vector<uint8_t> flags(m, 0);
+  for (size_t j = 0; j < idx.size(); ++j) {
+    const NodeInfo& ni = h_->node_infos[idx[j]];
+    auto it = ni.GetNode() ? index_.find(ni.GetNode()->name) : index_.end();
+    if (ni.GetNode() && (it == index_.end() || it->second != idx[j])) return false;
+    const Row row = FlattenRow(ni);
+    ca[j] = row.ca, cs[j] = row.cs, ma[j] = row.ma, ms[j] = row.ms, acpu[j] = row.acpu, amem[j] = row.amem, flags[j] = row.flags;
+  }
+  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+  eng_->Check(b200s_snapshot_patch_lvrb(eng_->ctx(), (int32_t)idx.size(), idx.data(), ca.data(), cs.data(), ma.data(), ms.data(),
+                                        acpu.data(), amem.data(), flags.data()),
+              "snapshot_patch_lvrb");
+  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  snap_gen_ = h_->generation;
+  patched_rows_ += (int64_t)idx.size();
+  return true;
+}
+
 void LoadVariationRiskBalancing::EnsureSnapshot() {
   if (snap_gen_ == h_->generation && n_ == (int32_t)h_->node_infos.size()) return;
+  if (PatchSnapshot()) return;
   const auto& nodes = h_->node_infos;
   n_ = (int32_t)nodes.size();
   npad_ = NPad(n_);
@@ -284,21 +409,9 @@ void LoadVariationRiskBalancing::EnsureSnapshot() {
   std::vector<double> ca(m, 0), cs(m, 0), ma(m, 0), ms(m, 0);
   std::vector<int64_t> acpu(m, 0), amem(m, 0);
   std::vector<uint8_t> flags(m, 0);
-  const WatcherMetrics* wm = h_->metrics.get();
   for (int32_t i = 0; i < n_; ++i) {
-    const Node* nd = nodes[i].GetNode();
-    if (!nd) continue;
-    acpu[i] = Get(nd->allocatable, ResourceCPU);                    // resourcestats.go:55-59: Allocatable
-    amem[i] = QuantityValue(Get(nd->allocatable, ResourceMemory));  // :62 am.Value()
-    if (!wm || !wm->has_map) continue;
-    auto it = wm->node_metrics.find(nd->name);
-    if (it == wm->node_metrics.end()) continue;
-    flags[i] |= B200S_LVRB_HAS_METRICS;
-    bool ok;
-    GetResourceData(it->second.metrics, "CPU", &ca[i], &cs[i], &ok);
-    if (ok) flags[i] |= B200S_LVRB_CPU_OK;
-    GetResourceData(it->second.metrics, "Memory", &ma[i], &ms[i], &ok);
-    if (ok) flags[i] |= B200S_LVRB_MEM_OK;
+    const Row row = FlattenRow(nodes[i]);
+    ca[i] = row.ca, cs[i] = row.cs, ma[i] = row.ma, ms[i] = row.ms, acpu[i] = row.acpu, amem[i] = row.amem, flags[i] = row.flags;
   }
   eng_->Check(b200s_snapshot_begin(eng_->ctx(), h_->generation, n_, 0, n_), "snapshot_begin");
   eng_->Check(b200s_snapshot_lvrb(eng_->ctx(), ca.data(), cs.data(), ma.data(), ms.data(), acpu.data(), amem.data(),

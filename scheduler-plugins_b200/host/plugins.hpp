@@ -53,7 +53,29 @@ struct Handle {
   std::map<std::string, bool> nrt_not_fresh;                                   // CachedNRTInfo.Fresh == false
   std::map<std::string, std::shared_ptr<AppGroup>> app_groups;
   std::map<std::string, std::shared_ptr<NetworkTopology>> network_topologies;
-  void Touch() { ++generation; }
+  // Upstream's cache refreshes its snapshot node by node (NodeInfo.Generation); TouchNode records which node an
+  // event changed so that the plugins rewrite that row of the resident columns instead of re-flattening all of
+  // them.  Touch() = anything else changed (node list, metrics fetch, CRs): everything is re-flattened.
+  void Touch() {
+    ++generation;
+    node_log_.clear();
+    log_base_ = generation;
+  }
+  void TouchNode(int32_t i) {
+    ++generation;
+    if (node_log_.size() >= (1u << 16)) {  // nobody will replay a log this long: start over (= Touch)
+      node_log_.clear();
+      log_base_ = generation;
+      return;
+    }
+    node_log_.emplace_back(generation, i);
+  }
+  // True when every change after generation g is a logged single-node change; *out = those nodes (deduplicated).
+  bool NodesChangedSince(uint64_t g, std::vector<int32_t>* out) const;
+
+ private:
+  std::vector<std::pair<uint64_t, int32_t>> node_log_;
+  uint64_t log_base_ = 1;
 };
 
 struct CycleState {
@@ -96,6 +118,14 @@ class Allocatable {
  private:
   Allocatable() = default;
   void EnsureSnapshot();
+  // rewrite only the rows of the nodes touched since snap_gen_; false = re-flatten everything
+  bool PatchSnapshot();
+  int64_t patched_rows_ = 0;
+
+ public:
+  int64_t PatchedRows() const { return patched_rows_; }  // rows rewritten through b200s_snapshot_patch_* so far
+
+ private:
   std::shared_ptr<CycleResult> Run(const Pod& pod, const std::vector<NodeInfo>* feasible);
   std::shared_ptr<Handle> h_;
   std::unique_ptr<Engine> eng_;
@@ -125,6 +155,19 @@ class TargetLoadPacking {
  private:
   TargetLoadPacking() = default;
   void EnsureSnapshot();
+  bool PatchSnapshot();
+  int64_t patched_rows_ = 0;
+
+ public:
+  int64_t PatchedRows() const { return patched_rows_; }  // rows rewritten through b200s_snapshot_patch_* so far
+
+ private:
+  struct Row {
+    double util = 0;
+    int64_t cap = 0, missing = 0;
+    uint8_t flags = 0;
+  };
+  Row FlattenRow(const NodeInfo& ni) const;
   std::shared_ptr<CycleResult> Run(const Pod& pod);
   std::shared_ptr<Handle> h_;
   std::unique_ptr<Engine> eng_;
@@ -151,6 +194,19 @@ class LoadVariationRiskBalancing {
  private:
   LoadVariationRiskBalancing() = default;
   void EnsureSnapshot();
+  bool PatchSnapshot();
+  int64_t patched_rows_ = 0;
+
+ public:
+  int64_t PatchedRows() const { return patched_rows_; }  // rows rewritten through b200s_snapshot_patch_* so far
+
+ private:
+  struct Row {
+    double ca = 0, cs = 0, ma = 0, ms = 0;
+    int64_t acpu = 0, amem = 0;
+    uint8_t flags = 0;
+  };
+  Row FlattenRow(const NodeInfo& ni) const;
   std::shared_ptr<CycleResult> Run(const Pod& pod);
   std::shared_ptr<Handle> h_;
   std::unique_ptr<Engine> eng_;

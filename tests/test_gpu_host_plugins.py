@@ -341,3 +341,65 @@ def test_network_overhead_filter(H):
     fh, no = netoh_fixture(H, pods_placed)
     st = no.filter(H.CycleState(), make_pod(H, {}), fh.node_infos[0])
     assert st.code == H.Code.Error and "failed to read from cycleState" in st.message
+
+
+# ------------------------------------------------------------------ incremental snapshot
+def _scores(p, H, pod, fh, pre=True):
+    state = H.CycleState()
+    if pre:
+        assert p.pre_score(state, pod, fh.node_infos).is_success()
+    out = []
+    for ni in fh.node_infos:
+        s, st = p.score(state, pod, ni)
+        assert st.is_success()
+        out.append(s)
+    return out
+
+
+def test_incremental_snapshot_allocatable(H):
+    """A node event touches one NodeInfo: the plugin rewrites that row (b200s_snapshot_patch_allocatable) and
+    scores exactly like a plugin instance that flattens the changed cluster from scratch."""
+    nodes = [make_node(H, f"machine{i}", {"cpu": f"{1000 * (i % 7 + 1)}m", "memory": str((i % 5 + 1) << 30)}) for i in range(40)]
+    fh = handle_with(H, nodes)
+    p = H.Allocatable.new(None, fh)
+    pod = make_pod(H, {})
+    before = _scores(p, H, pod, fh)
+    assert p.patched_rows() == 0
+    for i, cpu in ((3, "64000m"), (17, "100m"), (3, "48000m")):
+        nodes[i].allocatable = H.resource_list({"cpu": cpu, "memory": str(1 << 30)})
+        fh.touch_node(i)
+    after = _scores(p, H, pod, fh)
+    assert p.patched_rows() == 2                      # nodes 3 and 17, once each
+    assert after != before
+    assert after == _scores(H.Allocatable.new(None, fh), H, pod, fh)
+    fh.touch()                                        # a list-level change re-flattens everything
+    assert _scores(p, H, pod, fh) == after and p.patched_rows() == 2
+    for i in range(20):                               # too many rows for a patch to pay off: bulk path
+        fh.touch_node(i)
+    assert _scores(p, H, pod, fh) == after and p.patched_rows() == 2
+
+
+def test_incremental_snapshot_trimaran_bind(H):
+    """handler.go:131-167: a bind adds the pod to ScheduledPodsCache[node]; only that node's missing-utilisation
+    changes, so TargetLoadPacking patches one row.  LoadVariationRiskBalancing follows node allocatable changes."""
+    nodes = [make_node(H, f"node-{i}", {"cpu": "4000m", "memory": "8Gi"}) for i in range(12)]
+    fh = handle_with(H, nodes)
+    wm = watcher(H, {f"node-{i}": [("CPU", "AVG", 10.0 + 5 * i), ("CPU", "STD", 2.0), ("Memory", "AVG", 30.0), ("Memory", "STD", 3.0)]
+                     for i in range(12)})
+    wm.window_end = 1000
+    fh.metrics = wm
+    tlp = H.TargetLoadPacking.new(H.TargetLoadPackingArgs(), fh)
+    lvrb = H.LoadVariationRiskBalancing.new(H.LoadVariationRiskBalancingArgs(), fh)
+    pod = make_pod(H, {"containers": [{"requests": {"cpu": "500m", "memory": "1Gi"}, "limits": {}}]})
+    t0, l0 = _scores(tlp, H, pod, fh), _scores(lvrb, H, pod, fh)
+    bound = make_pod(H, {"containers": [{"requests": {"cpu": "1000m"}, "limits": {"cpu": "1000m"}}]}, name="bound")
+    fh.scheduled_pods_cache = {"node-4": [H.ScheduledPodInfo(995, bound)]}
+    fh.touch_node(4)
+    nodes[9].allocatable = H.resource_list({"cpu": "2000m", "memory": "4Gi"})
+    fh.touch_node(9)
+    t1, l1 = _scores(tlp, H, pod, fh), _scores(lvrb, H, pod, fh)
+    assert tlp.patched_rows() == 2 and lvrb.patched_rows() == 2
+    assert t1[4] != t0[4] and [s for i, s in enumerate(t1) if i != 4] == [s for i, s in enumerate(t0) if i != 4]
+    assert l1[9] != l0[9] and [s for i, s in enumerate(l1) if i != 9] == [s for i, s in enumerate(l0) if i != 9]
+    assert t1 == _scores(H.TargetLoadPacking.new(H.TargetLoadPackingArgs(), fh), H, pod, fh)
+    assert l1 == _scores(H.LoadVariationRiskBalancing.new(H.LoadVariationRiskBalancingArgs(), fh), H, pod, fh)

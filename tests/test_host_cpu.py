@@ -74,3 +74,27 @@ def test_no_cpu_fallback(H):
     with pytest.raises(RuntimeError) as ei:
         H.Allocatable.new(None, H.Handle())
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_handle_node_change_log(H):
+    """Per-node generations (upstream NodeInfo.Generation): a plugin may patch rows only when every change since
+    its snapshot is a logged single-node change."""
+    h = H.Handle()
+    n = H.Node()
+    n.name = "n0"
+    h.node_infos = [H.NodeInfo(n) for _ in range(4)]
+    g0 = h.generation
+    assert h.nodes_changed_since(g0) == []
+    h.touch_node(2); h.touch_node(0); h.touch_node(2)
+    assert h.nodes_changed_since(g0) == [0, 2]
+    assert h.nodes_changed_since(g0 + 1) == [0, 2]
+    assert h.nodes_changed_since(g0 + 2) == [2]
+    h.touch_node(7)                                  # index outside the list: not patchable
+    assert h.nodes_changed_since(g0) is None
+    h.touch()                                        # list-level change: everything before it is stale
+    g1 = h.generation
+    assert h.nodes_changed_since(g0) is None and h.nodes_changed_since(g1) == []
+    h.touch_node(1)
+    h.generation = h.generation + 1                  # moved without a log entry
+    assert h.nodes_changed_since(g1) is None
+    assert h.nodes_changed_since(h.generation + 5) is None
