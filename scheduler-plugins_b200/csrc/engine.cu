@@ -29,17 +29,37 @@ int upload_col(b200s_ctx* c, DevBuf& dst, size_t dst_off_elems, const T* src, in
   return B200S_OK;
 }
 
-// NRT thread-slot permutation: warps of the P x N kernel get nodes of one control-flow class (flags, zone count)
-// so pod-scope and container-scope nodes do not serialise inside a warp.  Stable counting sort over the host
-// mirror of the class keys: equal-class nodes keep their order, so runs stay coalesced.
+// NRT thread-slot permutation.  Major key: the control-flow class (flags, zone count), so that pod-scope and
+// container-scope nodes do not serialise inside a warp.  Minor key: how much the node's roomiest zone has left of
+// resource slots 0 and 1 -- whether a request fits a zone is what decides Filter, so lanes of a warp tend to agree
+// and the Score branch (taken only by surviving pairs) runs with full warps.  The permutation only shapes the
+// schedule; results never depend on it.
+uint64_t nrt_sort_key(uint8_t node_flags, uint8_t nz, int Z, int R, const uint8_t* zmask, const int64_t* avail,
+                      size_t zstride, size_t rstride) {  // zmask[z * zstride], avail[(z * R + r) * rstride]
+  int64_t cap[2] = {0, 0};
+  for (int z = 0; z < Z && z < nz; ++z)
+    for (int r = 0; r < 2 && r < R; ++r)
+      if ((zmask[(size_t)z * zstride] >> r) & 1u) cap[r] = std::max(cap[r], avail[((size_t)z * R + r) * rstride]);
+  const uint64_t q0 = (uint64_t)std::min<int64_t>(std::max<int64_t>(cap[0], 0) / 1000, 0xFFFFF);
+  const uint64_t q1 = (uint64_t)std::min<int64_t>((std::max<int64_t>(cap[1], 0) / 1000) >> 28, 0xFFFFF);
+  return ((uint64_t)(((uint32_t)node_flags << 8) | nz) << 40) | (q0 << 20) | q1;
+}
+inline uint32_t nrt_class_of(uint64_t key) { return (uint32_t)(key >> 40); }
+
 int upload_nrt_perm(b200s_ctx* c) {
-  const size_t np = c->Npad;
-  std::vector<int32_t> perm(np);
-  std::vector<uint32_t> start(65537, 0);
-  for (int i = 0; i < c->N; ++i) start[(size_t)c->nrt_key_h[i] + 1]++;
-  for (size_t k = 1; k <= 65536; ++k) start[k] += start[k - 1];
-  for (int i = 0; i < c->N; ++i) perm[start[c->nrt_key_h[i]]++] = i;
-  for (size_t i = c->N; i < np; ++i) perm[i] = (int32_t)i;
+  const size_t np = c->Npad, n = (size_t)std::max(c->N, 0);
+  // stable LSD radix sort of (key, node) over the 56 key bits, 4 passes of 14 bits
+  std::vector<int32_t> perm(np), tmp(n);
+  for (size_t i = 0; i < np; ++i) perm[i] = (int32_t)i;
+  std::vector<uint32_t> start((1u << 14) + 1);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int sh = 14 * pass;
+    std::fill(start.begin(), start.end(), 0u);
+    for (size_t i = 0; i < n; ++i) start[((c->nrt_key_h[i] >> sh) & 0x3FFF) + 1]++;
+    for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+    for (size_t i = 0; i < n; ++i) tmp[start[(c->nrt_key_h[perm[i]] >> sh) & 0x3FFF]++] = perm[i];
+    std::copy(tmp.begin(), tmp.end(), perm.begin());
+  }
   B200S_CUDA_TRY(c, c->nrt_perm.ensure(np * 4));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(c->nrt_perm.p, perm.data(), np * 4, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // perm dies at return
@@ -437,7 +457,9 @@ int b200s_snapshot_nrt(b200s_ctx* c, const b200s_nrt_nodes* nn) {
   for (int i = 0; i < Z * R; ++i)
     B200S_TRY(upload_col<int64_t>(c, c->nrt_avail, (size_t)i * np, nn->avail + (size_t)i * c->N, c->N, c->Npad));
   c->nrt_key_h.resize((size_t)std::max(c->N, 0));
-  for (int i = 0; i < c->N; ++i) c->nrt_key_h[i] = (uint16_t)(((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]);
+  for (int i = 0; i < c->N; ++i)
+    c->nrt_key_h[i] = nrt_sort_key(nn->node_flags[i], nn->n_zones_node[i], Z, R, nn->zone_res_mask + i, nn->avail + i,
+                                   (size_t)c->N, (size_t)c->N);
   B200S_TRY(upload_nrt_perm(c));
   c->nrt_has_cost = nn->cost != nullptr;
   if (nn->cost) {
@@ -588,12 +610,13 @@ int b200s_snapshot_patch_nrt(b200s_ctx* c, int32_t count, const int32_t* node_id
   if (nn->cost)
     for (int i = 0; i < Z * Z; ++i) p.add<int32_t>(c->nrt_cost, (size_t)i * np, nn->cost + (size_t)i * cnt);
   B200S_TRY(p.run(node_idx));
-  for (int i : p.keep) {  // class keys behind the thread permutation
-    const uint16_t key = (uint16_t)(((uint32_t)nn->node_flags[i] << 8) | nn->n_zones_node[i]);
-    if (c->nrt_key_h[node_idx[i]] != key) {
-      c->nrt_key_h[node_idx[i]] = key;
-      c->nrt_perm_dirty = true;
-    }
+  for (int i : p.keep) {  // sort keys behind the thread permutation
+    const uint64_t key = nrt_sort_key(nn->node_flags[i], nn->n_zones_node[i], Z, R, nn->zone_res_mask + i, nn->avail + i,
+                                      cnt, cnt);
+    // a node that changed class must move (warps are class-pure); a node whose free capacity drifted stays where
+    // it is until the next full upload -- the order within a class is only a hint
+    if (nrt_class_of(c->nrt_key_h[node_idx[i]]) != nrt_class_of(key)) c->nrt_perm_dirty = true;
+    c->nrt_key_h[node_idx[i]] = key;
   }
   return B200S_OK;
 }

@@ -131,7 +131,9 @@ struct b200s_ctx {
   uint8_t nrt_res_flags[B200S_NRT_MAX_RES] = {0};
   b200s::DevBuf nrt_node_flags, nrt_max_numa, nrt_nz, nrt_node_res_mask, nrt_zone_res_mask, nrt_avail,
       nrt_cost, nrt_perm;  // nrt_perm [Npad] int32: thread slot -> node, nodes grouped by control-flow class
-  std::vector<uint16_t> nrt_key_h;  // [N] host mirror of the control-flow class (flags << 8 | zones) behind nrt_perm
+  // [N] host mirror of the sort key behind nrt_perm: control-flow class (flags << 8 | zones) in bits 40..55, then
+  // the largest zone's availability of resource slots 0 and 1 (20 bits each, quantised)
+  std::vector<uint64_t> nrt_key_h;
   bool nrt_perm_dirty = false;
   bool nrt_cfg = false;
   int nrt_strategy = B200S_NRT_LEAST_ALLOCATED;

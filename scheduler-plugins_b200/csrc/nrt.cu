@@ -92,8 +92,12 @@ __device__ __forceinline__ int64_t f2i(double x) {
 }
 // floor(a*100/cv) for 0 <= a <= cv (quotient in 0..100): fp32 estimate + exact integer fix-up instead of
 // a 64-bit division; identical to Go's (a*100)/cv.  Absurdly large capacities keep the wrapping Go path.
+// generic path of div100 (quantities beyond 2^52 or out-of-range numerators): kept out of line so that the 16
+// unrolled (zone, resource) call sites stay small
+__device__ __noinline__ int64_t div100_slow(int64_t a, int64_t cv) { return go_div(wrap_mul(a, 100), cv); }
+
 __device__ __forceinline__ int64_t div100(int64_t a, int64_t cv) {
-  if (cv >= (1ll << 52) || a < 0 || a > cv) return go_div(wrap_mul(a, 100), cv);
+  if (cv >= (1ll << 52) || a < 0 || a > cv) return div100_slow(a, cv);
   const int64_t num = a * 100;
   int64_t q = (int64_t)__float2int_rd(__fdividef(__ll2float_rn(num), __ll2float_rn(cv)));
   int64_t rem = num - q * cv;
@@ -218,6 +222,8 @@ __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, 
     weight_sum = wrap_add(weight_sum, cfg.w[r]);
   }
   if (weight_sum == 0) return 0;
+  // sum of (score <= 100) x weight over the weight sum: both fit 31 bits unless the weights are absurd
+  if ((uint64_t)(node_score | weight_sum) < (1ull << 31)) return (int64_t)((uint32_t)node_score / (uint32_t)weight_sum);
   return go_div(node_score, weight_sum);
 }
 
@@ -486,6 +492,9 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
   __syncthreads();
   if (!in) return;
   const int word = n >> 6;
+  // The warp walks the pods of the tile together: pod data is a shared-memory broadcast and every branch on it is
+  // warp-uniform.  (Measured alternative: per-lane work lists of the surviving pods keep all lanes busy but turn
+  // those broadcasts and uniform branches into divergent ones: 14.5 ms instead of 11.5 ms at c4.)
   for (int pp = 0; pp < pend; ++pp) {
     const int p = p0 + pp;
     const PodS<R>& pod = sp[pp];
