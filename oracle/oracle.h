@@ -65,6 +65,29 @@ void orc_lvrb_batch(const double* cpu_avg, const double* cpu_std, const double* 
                     const int64_t* req_cpu, const int64_t* req_mem, int P, double margin, double sens,
                     int64_t* out, int pitch);
 
+/* ---- Trimaran Peaks + LowRiskOverCommitment (trimaran2.c; see its header for the parity note) ---- */
+double orc_go_exp(double x);
+int64_t orc_peaks_score(double util_pct, int64_t cap_milli, uint8_t flags, double k1, double k2, int64_t pod_cpu_milli);
+void orc_peaks_normalize(int64_t* scores, int n);
+void orc_peaks_batch(const double* util, const int64_t* cap, const uint8_t* flags, const double* k1, const double* k2,
+                     int N, const int64_t* pod_cpu, int P, const uint64_t* feasible, int words, int64_t* out, int pitch);
+double orc_incbet(double a, double b, double x);
+double orc_lowrisk_risk_load(int stats_ok, double util, double std, double capacity_f, int64_t capacity,
+                             int64_t req_minus_pod, int64_t lim_minus_pod, int64_t window);
+double orc_lowrisk_compute_risk(int stats_ok, double util, double std, double capacity_f, int64_t capacity,
+                                int64_t node_req, int64_t node_lim, int64_t pod_req, int64_t pod_lim, int64_t window,
+                                double weight);
+int64_t orc_lowrisk_score(double cpu_avg, double cpu_std, double mem_avg, double mem_std, int64_t alloc_cpu_milli,
+                          int64_t alloc_mem_bytes, uint8_t flags, int64_t node_req_cpu, int64_t node_req_mem,
+                          int64_t node_lim_cpu, int64_t node_lim_mem, int64_t pod_req_cpu, int64_t pod_req_mem,
+                          int64_t pod_lim_cpu, int64_t pod_lim_mem, int64_t window, double w_cpu, double w_mem);
+void orc_lowrisk_batch(const double* cpu_avg, const double* cpu_std, const double* mem_avg, const double* mem_std,
+                       const int64_t* alloc_cpu, const int64_t* alloc_mem, const uint8_t* flags,
+                       const int64_t* node_req_cpu, const int64_t* node_req_mem, const int64_t* node_lim_cpu,
+                       const int64_t* node_lim_mem, int N, const int64_t* pod_req_cpu, const int64_t* pod_req_mem,
+                       const int64_t* pod_lim_cpu, const int64_t* pod_lim_mem, int P, int64_t window, double w_cpu,
+                       double w_mem, int64_t* out, int pitch);
+
 /* ---- NetworkOverhead (pkg/networkaware/networkoverhead) ---- */
 #define ORC_NETOH_MISSING INT64_MIN
 typedef struct {

@@ -29,6 +29,19 @@ def lib() -> C.CDLL:
                                                            C.c_double, C.c_double]
         _lib.orc_lvrb_compute_score.restype = C.c_double
         _lib.orc_lvrb_compute_score.argtypes = [C.c_double] * 6
+        _lib.orc_go_exp.restype = C.c_double
+        _lib.orc_go_exp.argtypes = [C.c_double]
+        _lib.orc_peaks_score.restype = C.c_int64
+        _lib.orc_peaks_score.argtypes = [C.c_double, C.c_int64, C.c_uint8, C.c_double, C.c_double, C.c_int64]
+        _lib.orc_incbet.restype = C.c_double
+        _lib.orc_incbet.argtypes = [C.c_double] * 3
+        _lib.orc_lowrisk_risk_load.restype = C.c_double
+        _lib.orc_lowrisk_risk_load.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_int64]
+        _lib.orc_lowrisk_compute_risk.restype = C.c_double
+        _lib.orc_lowrisk_compute_risk.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double] + [C.c_int64] * 6 + [C.c_double]
+        _lib.orc_lowrisk_score.restype = C.c_int64
+        _lib.orc_lowrisk_score.argtypes = [C.c_double] * 4 + [C.c_int64, C.c_int64, C.c_uint8] + [C.c_int64] * 9 + [C.c_double] * 2
     return _lib
 
 
@@ -127,6 +140,74 @@ def lvrb_batch(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, 
     out = np.zeros((P, pitch), dtype=np.int64)
     lib().orc_lvrb_batch(*[_p(x) for x in f], *[_p(x) for x in i], _p(fl), C.c_int(N), _p(rc), _p(rm), C.c_int(P),
                          C.c_double(margin), C.c_double(sens), _p(out), C.c_int(pitch))
+    return out
+
+
+# ---- Trimaran Peaks + LowRiskOverCommitment -----------------------------------------------------
+def go_exp(x) -> float:
+    return float(lib().orc_go_exp(x))
+
+
+def peaks_score(util, cap, flags, k1, k2, pod_cpu) -> int:
+    return int(lib().orc_peaks_score(util, cap, flags, k1, k2, pod_cpu))
+
+
+def peaks_normalize(scores):
+    s = _c(scores, np.int64).copy()
+    lib().orc_peaks_normalize(_p(s), C.c_int(len(s)))
+    return s
+
+
+def peaks_batch(util, cap, flags, k1, k2, pod_cpu, feasible_words=None, pitch=None):
+    util = _c(util, np.float64); cap = _c(cap, np.int64); flags = _c(flags, np.uint8)
+    k1 = _c(k1, np.float64); k2 = _c(k2, np.float64); pod_cpu = _c(pod_cpu, np.int64)
+    N, P = len(util), len(pod_cpu)
+    pitch = pitch or N
+    out = np.zeros((P, pitch), dtype=np.int64)
+    fw = None if feasible_words is None else _c(feasible_words, np.uint64)
+    words = 0 if fw is None else fw.shape[1]
+    lib().orc_peaks_batch(_p(util), _p(cap), _p(flags), _p(k1), _p(k2), C.c_int(N), _p(pod_cpu), C.c_int(P), _p(fw),
+                          C.c_int(words), _p(out), C.c_int(pitch))
+    return out
+
+
+def incbet(a, b, x) -> float:
+    return float(lib().orc_incbet(a, b, x))
+
+
+def lowrisk_risk_load(stats_ok, util, std, capacity_f, capacity, req_minus_pod, lim_minus_pod, window=5) -> float:
+    return float(lib().orc_lowrisk_risk_load(int(stats_ok), util, std, capacity_f, capacity, req_minus_pod,
+                                             lim_minus_pod, window))
+
+
+def lowrisk_compute_risk(stats_ok, util, std, capacity_f, capacity, node_req, node_lim, pod_req, pod_lim, window=5,
+                         weight=0.5) -> float:
+    return float(lib().orc_lowrisk_compute_risk(int(stats_ok), util, std, capacity_f, capacity, node_req, node_lim,
+                                                pod_req, pod_lim, window, weight))
+
+
+def lowrisk_score(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, node_req_cpu, node_req_mem,
+                  node_lim_cpu, node_lim_mem, pod_req_cpu, pod_req_mem, pod_lim_cpu, pod_lim_mem, window=5, w_cpu=0.5,
+                  w_mem=0.5) -> int:
+    return int(lib().orc_lowrisk_score(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, node_req_cpu,
+                                       node_req_mem, node_lim_cpu, node_lim_mem, pod_req_cpu, pod_req_mem,
+                                       pod_lim_cpu, pod_lim_mem, window, w_cpu, w_mem))
+
+
+def lowrisk_batch(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, flags, node_req_cpu, node_req_mem,
+                  node_lim_cpu, node_lim_mem, pod_req_cpu, pod_req_mem, pod_lim_cpu, pod_lim_mem, window=5, w_cpu=0.5,
+                  w_mem=0.5, pitch=None):
+    f = [_c(x, np.float64) for x in (cpu_avg, cpu_std, mem_avg, mem_std)]
+    i = [_c(x, np.int64) for x in (alloc_cpu, alloc_mem)]
+    fl = _c(flags, np.uint8)
+    nd = [_c(x, np.int64) for x in (node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem)]
+    pd = [_c(x, np.int64) for x in (pod_req_cpu, pod_req_mem, pod_lim_cpu, pod_lim_mem)]
+    N, P = len(fl), len(pd[0])
+    pitch = pitch or N
+    out = np.zeros((P, pitch), dtype=np.int64)
+    lib().orc_lowrisk_batch(*[_p(x) for x in f], *[_p(x) for x in i], _p(fl), *[_p(x) for x in nd], C.c_int(N),
+                            *[_p(x) for x in pd], C.c_int(P), C.c_int64(window), C.c_double(w_cpu), C.c_double(w_mem),
+                            _p(out), C.c_int(pitch))
     return out
 
 
