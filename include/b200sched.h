@@ -69,7 +69,9 @@ typedef enum {
   B200S_PLUGIN_LVRB = 2,             /* LoadVariationRiskBalancing */
   B200S_PLUGIN_NRT = 3,              /* NodeResourceTopologyMatch */
   B200S_PLUGIN_NETWORK_OVERHEAD = 4, /* NetworkOverhead */
-  B200S_PLUGIN_COUNT = 5
+  B200S_PLUGIN_PEAKS = 5,            /* Trimaran Peaks */
+  B200S_PLUGIN_LOW_RISK = 6,         /* Trimaran LowRiskOverCommitment */
+  B200S_PLUGIN_COUNT = 7
 } b200s_plugin;
 
 typedef enum { B200S_OUT_I64 = 0, B200S_OUT_U8 = 1 } b200s_out_dtype;
@@ -151,6 +153,23 @@ int b200s_snapshot_lvrb(b200s_ctx* ctx, const double* cpu_avg, const double* cpu
                         const int64_t* alloc_cpu_milli, const int64_t* alloc_mem_bytes,
                         const uint8_t* flags);
 
+/* Peaks (pkg/trimaran/peaks/peaks.go:103-146).  flags as for TLP (B200S_TLP_HAS_METRICS, B200S_TLP_CPU_FOUND) but
+ * cpu_util_pct is the FIRST CPU metric with operator Average|Latest (:117-126 breaks at the first match; TLP keeps
+ * the last).  cap_milli = Node.Status.Capacity cpu (:131).  k1, k2 = the node's entry in PeaksArgs.NodePowerModel,
+ * 0 when it has none (getPowerModel :193-199; k0 does not enter the score). */
+int b200s_snapshot_peaks(b200s_ctx* ctx, const double* cpu_util_pct, const int64_t* cap_milli, const uint8_t* flags,
+                         const double* k1, const double* k2);
+
+/* LowRiskOverCommitment (pkg/trimaran/lowriskovercommitment/lowriskovercommitment.go:105-254).  The first seven
+ * columns are those of LVRB (GetResourceData averages / deviations, Allocatable cpu milli and memory bytes,
+ * B200S_LVRB_* flags).  node_req_* / node_lim_* = requests and limits summed over the pods already on the node,
+ * each pod's limits raised to its requests first (GetNodeRequestsAndLimits, resourcestats.go:160-228) -- i.e.
+ * NodeRequestMinusPod / NodeLimitMinusPod before the capacity cap. */
+int b200s_snapshot_low_risk(b200s_ctx* ctx, const double* cpu_avg, const double* cpu_std, const double* mem_avg,
+                            const double* mem_std, const int64_t* alloc_cpu_milli, const int64_t* alloc_mem_bytes,
+                            const uint8_t* flags, const int64_t* node_req_cpu_milli, const int64_t* node_req_mem_bytes,
+                            const int64_t* node_lim_cpu_milli, const int64_t* node_lim_mem_bytes);
+
 /* NodeResourceTopologyMatch.  Dense padded encoding of the per-node NRT object
  * as createNUMANodeList / TopologyManagerFromNodeResourceTopology see it
  * (pluginhelpers.go:105-161, nodeconfig/topologymanager.go:78-161).  Quantities
@@ -225,6 +244,9 @@ int b200s_snapshot_patch_network_overhead(b200s_ctx* ctx, int32_t count, const i
 int b200s_config_allocatable(b200s_ctx* ctx, int mode, int32_t n_res, const int64_t* weights);
 int b200s_config_tlp(b200s_ctx* ctx, int64_t target_utilization_pct);
 int b200s_config_lvrb(b200s_ctx* ctx, double safe_variance_margin, double safe_variance_sensitivity);
+/* LowRiskOverCommitmentArgs: SmoothingWindowSize (defaults.go:70, > 0) and RiskLimitWeights[cpu], [memory] in [0, 1] */
+int b200s_config_low_risk(b200s_ctx* ctx, int64_t smoothing_window_size, double risk_limit_weight_cpu,
+                          double risk_limit_weight_mem);
 /* weights[r] per resource slot of the NRT dictionary; values < 1 mean 1 (score.go:49-60) */
 int b200s_config_nrt(b200s_ctx* ctx, int strategy, int32_t n_res, const int64_t* weights);
 /* NetworkOverhead: want_counts != 0 also keeps PreFilterState.satisfiedMap / violatedMap
@@ -278,6 +300,10 @@ typedef struct {
   const int64_t* lvrb_req_mem_bytes;  /* [P] or NULL */
   const b200s_nrt_pods* nrt;          /* or NULL */
   const b200s_netoh_pods* netoh;      /* or NULL */
+  const int64_t* peaks_pod_cpu_milli; /* [P] GetResourceRequestQuantity(pod, cpu).MilliValue() (peaks.go:113-114) or NULL */
+  /* [4][P]: request cpu milli, request memory bytes, limit cpu milli, limit memory bytes of the pending pod
+   * (CreatePodResourcesStateData, lowriskovercommitment.go:257-267: limits raised to requests) or NULL */
+  const int64_t* low_risk_pod;
 } b200s_pod_batch;
 
 int b200s_pods_upload(b200s_ctx* ctx, const b200s_pod_batch* batch);

@@ -210,7 +210,12 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
     c->mask_override = cur;
     B200S_TRY(alloc_eval(c, B200S_OUT_U8));
   }
+  if (mask & (1u << B200S_PLUGIN_PEAKS)) {  // NormalizeScore over what the filters left, like Allocatable
+    c->mask_override = cur;
+    B200S_TRY(peaks_eval(c, B200S_OUT_U8));
+  }
   c->mask_override = nullptr;
+  if (mask & (1u << B200S_PLUGIN_LOW_RISK)) B200S_TRY(lowrisk_eval(c, B200S_OUT_U8));
   if (mask & (1u << B200S_PLUGIN_TLP)) B200S_TRY(tlp_eval(c, B200S_OUT_U8));
   if (mask & (1u << B200S_PLUGIN_LVRB)) B200S_TRY(lvrb_eval(c, B200S_OUT_U8));
 

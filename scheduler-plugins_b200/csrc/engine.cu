@@ -269,7 +269,10 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->norm_params,     &c->raw_scores,       &c->total,            &c->total_feas,
                     &c->topk_local,      &c->topk_all,         &c->topk_final,       &c->netoh_counts,
                     &c->netoh_pair_id,   &c->netoh_pair_r,     &c->netoh_pair_z,     &c->netoh_pair_cost,
-                    &c->netoh_pair_sv,   &c->nrt_perm,         &c->topk_slices};
+                    &c->netoh_pair_sv,   &c->nrt_perm,         &c->topk_slices,      &c->peaks_util,
+                    &c->peaks_cap,       &c->peaks_flags,      &c->peaks_k,          &c->lowrisk_f64,
+                    &c->lowrisk_i64,     &c->lowrisk_flags,    &c->lowrisk_load,     &c->peaks_pod_cpu,
+                    &c->lowrisk_pod};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();
@@ -363,7 +366,7 @@ int b200s_snapshot_begin(b200s_ctx* c, uint64_t generation, int32_t n_nodes, int
   c->Npad = round_up(n_nodes > 0 ? n_nodes : 1, B200S_NODE_ALIGN);
   c->node_off = node_offset;
   c->Nglobal = n_nodes_global;
-  c->has_alloc = c->has_tlp = c->has_lvrb = c->has_nrt = c->has_netoh = false;
+  c->has_alloc = c->has_tlp = c->has_lvrb = c->has_nrt = c->has_netoh = c->has_peaks = c->has_lowrisk = false;
   for (auto& o : c->out) o.valid = false;
   c->total_valid = c->topk_valid = false;
   return B200S_OK;
@@ -425,6 +428,51 @@ int b200s_snapshot_lvrb(b200s_ctx* c, const double* cpu_avg, const double* cpu_s
   B200S_TRY(upload_col<uint8_t>(c, c->lvrb_flags, 0, flags, c->N, c->Npad));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->has_lvrb = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_peaks(b200s_ctx* c, const double* util, const int64_t* cap, const uint8_t* flags, const double* k1,
+                         const double* k2) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!util || !cap || !flags || !k1 || !k2) return c->set_err(B200S_ERR_INVALID, "snapshot_peaks: null column");
+  const size_t np = c->Npad;
+  B200S_CUDA_TRY(c, c->peaks_util.ensure(np * 8));
+  B200S_CUDA_TRY(c, c->peaks_cap.ensure(np * 8));
+  B200S_CUDA_TRY(c, c->peaks_flags.ensure(np));
+  B200S_CUDA_TRY(c, c->peaks_k.ensure(2 * np * 8));
+  B200S_TRY(upload_col<double>(c, c->peaks_util, 0, util, c->N, c->Npad));
+  B200S_TRY(upload_col<int64_t>(c, c->peaks_cap, 0, cap, c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->peaks_flags, 0, flags, c->N, c->Npad));
+  B200S_TRY(upload_col<double>(c, c->peaks_k, 0 * np, k1, c->N, c->Npad));
+  B200S_TRY(upload_col<double>(c, c->peaks_k, 1 * np, k2, c->N, c->Npad));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->has_peaks = true;
+  return B200S_OK;
+}
+
+int b200s_snapshot_low_risk(b200s_ctx* c, const double* cpu_avg, const double* cpu_std, const double* mem_avg,
+                            const double* mem_std, const int64_t* alloc_cpu, const int64_t* alloc_mem,
+                            const uint8_t* flags, const int64_t* node_req_cpu, const int64_t* node_req_mem,
+                            const int64_t* node_lim_cpu, const int64_t* node_lim_mem) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_open(c));
+  if (!cpu_avg || !cpu_std || !mem_avg || !mem_std || !alloc_cpu || !alloc_mem || !flags || !node_req_cpu ||
+      !node_req_mem || !node_lim_cpu || !node_lim_mem)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_low_risk: null column");
+  const size_t np = c->Npad;
+  B200S_CUDA_TRY(c, c->lowrisk_f64.ensure(4 * np * 8));
+  B200S_CUDA_TRY(c, c->lowrisk_i64.ensure(6 * np * 8));
+  B200S_CUDA_TRY(c, c->lowrisk_flags.ensure(np));
+  const double* f[4] = {cpu_avg, cpu_std, mem_avg, mem_std};
+  const int64_t* iv[6] = {alloc_cpu, alloc_mem, node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem};
+  for (int k = 0; k < 4; ++k) B200S_TRY(upload_col<double>(c, c->lowrisk_f64, k * np, f[k], c->N, c->Npad));
+  for (int k = 0; k < 6; ++k) B200S_TRY(upload_col<int64_t>(c, c->lowrisk_i64, k * np, iv[k], c->N, c->Npad));
+  B200S_TRY(upload_col<uint8_t>(c, c->lowrisk_flags, 0, flags, c->N, c->Npad));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->has_lowrisk = true;
   return B200S_OK;
 }
 
@@ -673,6 +721,21 @@ int b200s_config_lvrb(b200s_ctx* c, double margin, double sens) {
   return B200S_OK;
 }
 
+int b200s_config_low_risk(b200s_ctx* c, int64_t window, double w_cpu, double w_mem) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (window <= 0) return c->set_err(B200S_ERR_INVALID, "config_low_risk: smoothingWindowSize must be positive");
+  if (!(w_cpu >= 0 && w_cpu <= 1) || !(w_mem >= 0 && w_mem <= 1))
+    return c->set_err(B200S_ERR_INVALID, "config_low_risk: riskLimitWeights must be in [0, 1]");
+  c->lowrisk_window = window;
+  c->lowrisk_w_cpu = w_cpu;
+  c->lowrisk_w_mem = w_mem;
+  c->lowrisk_cfg = true;
+  c->lowrisk_cfg_gen++;
+  c->out[B200S_PLUGIN_LOW_RISK].valid = false;
+  return B200S_OK;
+}
+
 int b200s_config_network_overhead(b200s_ctx* c, int want_counts, int apply_own_filter) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
@@ -758,6 +821,10 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     up.add(&c->lvrb_req_cpu, b->lvrb_req_cpu_milli, (size_t)P * 8);
     up.add(&c->lvrb_req_mem, b->lvrb_req_mem_bytes, (size_t)P * 8);
   }
+  c->has_peaks_pods = b->peaks_pod_cpu_milli != nullptr;
+  if (c->has_peaks_pods && P > 0) up.add(&c->peaks_pod_cpu, b->peaks_pod_cpu_milli, (size_t)P * 8);
+  c->has_lowrisk_pods = b->low_risk_pod != nullptr;
+  if (c->has_lowrisk_pods && P > 0) up.add(&c->lowrisk_pod, b->low_risk_pod, (size_t)P * 4 * 8);
   c->has_nrt_pods = b->nrt != nullptr;
   if (b->nrt && P > 0) {
     const b200s_nrt_pods* q = b->nrt;
@@ -815,6 +882,8 @@ static int eval_locked(b200s_ctx* c, b200s_plugin plugin, b200s_out_dtype dtype)
     case B200S_PLUGIN_LVRB: return lvrb_eval(c, dtype);
     case B200S_PLUGIN_NRT: return nrt_eval(c, dtype);
     case B200S_PLUGIN_NETWORK_OVERHEAD: return netoh_eval(c, dtype);
+    case B200S_PLUGIN_PEAKS: return peaks_eval(c, dtype);
+    case B200S_PLUGIN_LOW_RISK: return lowrisk_eval(c, dtype);
     default: return c->set_err(B200S_ERR_INVALID, "eval: unknown plugin");
   }
 }

@@ -124,6 +124,22 @@ struct b200s_ctx {
   bool lvrb_cfg = false;
   double lvrb_margin = 1.0, lvrb_sens = 1.0;
 
+  // Peaks
+  bool has_peaks = false;
+  b200s::DevBuf peaks_util, peaks_cap, peaks_flags, peaks_k;  // peaks_k [2][Npad] f64: k1, k2
+
+  // LowRiskOverCommitment
+  bool has_lowrisk = false;
+  b200s::DevBuf lowrisk_f64;   // [4][Npad] cpuAvg cpuStd memAvg memStd
+  b200s::DevBuf lowrisk_i64;   // [6][Npad] allocCpu allocMem nodeReqCpu nodeReqMem nodeLimCpu nodeLimMem
+  b200s::DevBuf lowrisk_flags;
+  b200s::DevBuf lowrisk_load;  // [2][Npad] f64 riskLoad (cpu, memory): depends on the node only, derived per snapshot
+  uint64_t lowrisk_prepared_key = ~0ull;
+  uint64_t lowrisk_cfg_gen = 0;
+  bool lowrisk_cfg = false;
+  int64_t lowrisk_window = 5;
+  double lowrisk_w_cpu = 0.5, lowrisk_w_mem = 0.5;
+
   // NodeResourceTopologyMatch
   bool has_nrt = false;
   int nrt_Z = 0, nrt_R = 0;
@@ -171,7 +187,8 @@ struct b200s_ctx {
     return has_feasible ? feasible_in.as<uint64_t>() : nullptr;
   }
   bool has_tlp_pods = false, has_lvrb_pods = false, has_nrt_pods = false, has_netoh_pods = false;
-  b200s::DevBuf tlp_pod_cpu, lvrb_req_cpu, lvrb_req_mem;
+  bool has_peaks_pods = false, has_lowrisk_pods = false;
+  b200s::DevBuf tlp_pod_cpu, lvrb_req_cpu, lvrb_req_mem, peaks_pod_cpu, lowrisk_pod;
   b200s::DevBuf nrt_pod_qos, nrt_pod_flags, nrt_pod_ninit, nrt_pod_napp, nrt_pod_kind, nrt_pod_req_mask,
       nrt_pod_req;
   b200s::DevBuf netoh_equal, netoh_dep_off, netoh_deps;
@@ -239,6 +256,8 @@ int tlp_eval(b200s_ctx* c, int dtype);
 int lvrb_eval(b200s_ctx* c, int dtype);
 int nrt_eval(b200s_ctx* c, int dtype);
 int netoh_eval(b200s_ctx* c, int dtype);
+int peaks_eval(b200s_ctx* c, int dtype);
+int lowrisk_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
 int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint64_t* mismatches);
 

@@ -14,8 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200sched.so")
 
-PLUGIN_ALLOCATABLE, PLUGIN_TLP, PLUGIN_LVRB, PLUGIN_NRT, PLUGIN_NETWORK_OVERHEAD = range(5)
-PLUGIN_COUNT = 5
+(PLUGIN_ALLOCATABLE, PLUGIN_TLP, PLUGIN_LVRB, PLUGIN_NRT, PLUGIN_NETWORK_OVERHEAD, PLUGIN_PEAKS,
+ PLUGIN_LOW_RISK) = range(7)
+PLUGIN_COUNT = 7
 OUT_I64, OUT_U8 = 0, 1
 ALLOC_LEAST, ALLOC_MOST = 0, 1
 NRT_MOST_ALLOCATED, NRT_BALANCED_ALLOCATION, NRT_LEAST_ALLOCATED, NRT_LEAST_NUMA_NODES = range(4)
@@ -29,6 +30,7 @@ EXPORTS = [
     "b200s_launch_count", "b200s_comm_unique_id", "b200s_comm_init", "b200s_comm_rank", "b200s_comm_world",
     "b200s_snapshot_begin", "b200s_snapshot_allocatable", "b200s_snapshot_tlp", "b200s_snapshot_lvrb",
     "b200s_snapshot_nrt", "b200s_snapshot_network_overhead", "b200s_snapshot_commit",
+    "b200s_snapshot_peaks", "b200s_snapshot_low_risk", "b200s_config_low_risk",
     "b200s_snapshot_patch_begin", "b200s_snapshot_patch_allocatable", "b200s_snapshot_patch_tlp",
     "b200s_snapshot_patch_lvrb", "b200s_snapshot_patch_nrt", "b200s_snapshot_patch_network_overhead",
     "b200s_config_allocatable", "b200s_config_tlp", "b200s_config_lvrb", "b200s_config_nrt",
@@ -65,7 +67,8 @@ class NetohPods(C.Structure):
 class PodBatch(C.Structure):
     _fields_ = [("n_pods", C.c_int32), ("feasible", C.c_void_p), ("tlp_pod_cpu_milli", C.c_void_p),
                 ("lvrb_req_cpu_milli", C.c_void_p), ("lvrb_req_mem_bytes", C.c_void_p),
-                ("nrt", C.POINTER(NrtPods)), ("netoh", C.POINTER(NetohPods))]
+                ("nrt", C.POINTER(NrtPods)), ("netoh", C.POINTER(NetohPods)),
+                ("peaks_pod_cpu_milli", C.c_void_p), ("low_risk_pod", C.c_void_p)]
 
 
 NETOH_DEP_DTYPE = np.dtype([("host_node", "<i4"), ("host_region", "<u2"), ("host_zone", "<u2"),
@@ -253,6 +256,26 @@ class Engine:
         self._chk(self.lib.b200s_snapshot_network_overhead(self.ctx, _ptr(a), _ptr(b), C.c_int32(K), _ptr(zc),
                                                            _ptr(rc_)))
 
+    def snapshot_peaks(self, cpu_util_pct, cap_milli, flags, k1, k2):
+        n = (self.N,)
+        a = _arr(cpu_util_pct, np.float64, n); b = _arr(cap_milli, np.int64, n); c = _arr(flags, np.uint8, n)
+        d = _arr(k1, np.float64, n); e = _arr(k2, np.float64, n)
+        self._chk(self.lib.b200s_snapshot_peaks(self.ctx, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(e)))
+
+    def snapshot_low_risk(self, cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu_milli, alloc_mem_bytes, flags,
+                          node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem):
+        n = (self.N,)
+        f = [_arr(x, np.float64, n) for x in (cpu_avg, cpu_std, mem_avg, mem_std)]
+        i = [_arr(x, np.int64, n) for x in (alloc_cpu_milli, alloc_mem_bytes)]
+        fl = _arr(flags, np.uint8, n)
+        nd = [_arr(x, np.int64, n) for x in (node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem)]
+        self._chk(self.lib.b200s_snapshot_low_risk(self.ctx, *[_ptr(x) for x in f], *[_ptr(x) for x in i], _ptr(fl),
+                                                   *[_ptr(x) for x in nd]))
+
+    def config_low_risk(self, smoothing_window_size=5, w_cpu=0.5, w_mem=0.5):
+        self._chk(self.lib.b200s_config_low_risk(self.ctx, C.c_int64(smoothing_window_size), C.c_double(w_cpu),
+                                                 C.c_double(w_mem)))
+
     def snapshot_commit(self):
         self._chk(self.lib.b200s_snapshot_commit(self.ctx))
 
@@ -327,7 +350,7 @@ class Engine:
 
     # -- pods -----------------------------------------------------------------------------
     def make_batch(self, n_pods, feasible=None, tlp_pod_cpu_milli=None, lvrb_req_cpu_milli=None,
-                   lvrb_req_mem_bytes=None, nrt=None, netoh=None):
+                   lvrb_req_mem_bytes=None, nrt=None, netoh=None, peaks_pod_cpu_milli=None, low_risk_pod=None):
         """Builds the b200s_pod_batch struct; returns (struct, keepalive list)."""
         P = int(n_pods)
         keep = []
@@ -349,6 +372,8 @@ class Engine:
         b.tlp_pod_cpu_milli = col(tlp_pod_cpu_milli, np.int64, (P,))
         b.lvrb_req_cpu_milli = col(lvrb_req_cpu_milli, np.int64, (P,))
         b.lvrb_req_mem_bytes = col(lvrb_req_mem_bytes, np.int64, (P,))
+        b.peaks_pod_cpu_milli = col(peaks_pod_cpu_milli, np.int64, (P,))
+        b.low_risk_pod = col(low_risk_pod, np.int64, (4, P))  # req cpu, req mem, limit cpu, limit mem
         if nrt is not None:
             Cn, R = NRT_MAX_CONT, self.nrt_R
             s = NrtPods(col(nrt["qos"], np.uint8, (P,)), col(nrt["flags"], np.uint8, (P,)),
@@ -411,7 +436,8 @@ class Engine:
         return int(self.lib.b200s_device_scores(self.ctx, C.c_int(plugin)) or 0)
 
     def eval_combined(self, plugin_mask, weights, k=1, write_total=False):
-        w = _arr(weights, np.int64, (PLUGIN_COUNT,))
+        w = np.zeros(PLUGIN_COUNT, dtype=np.int64)  # indexed by plugin id; shorter lists cover the first plugins
+        w[:len(weights)] = np.asarray(weights, dtype=np.int64)
         self._chk(self.lib.b200s_eval_combined(self.ctx, C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k),
                                                C.c_int(1 if write_total else 0)))
         self._k = k

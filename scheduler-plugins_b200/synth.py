@@ -70,6 +70,39 @@ def gen_trimaran(seed: int, nodes: dict) -> dict:
                 tlp_flags=tlp_flags, lvrb_flags=lvrb_flags)
 
 
+def gen_trimaran2(seed: int, nodes: dict, P: int) -> dict:
+    """Peaks power models and LowRiskOverCommitment request/limit sums, on top of gen_nodes / gen_trimaran."""
+    g = np.random.default_rng([seed, 77])
+    N = nodes["N"]
+    # power = k0 + k1 * exp(k2 * util%): the shape of the reference's sample model (peaks_test.go:81-87), per node
+    k1 = -np.round(g.uniform(40, 140, N) * 4096) / 4096
+    k2 = -np.round(g.uniform(0.01, 0.12, N) * 65536) / 65536
+    no_model = g.random(N) < 0.03  # getPowerModel: nodes without an entry score with {0, 0, 0}
+    k1[no_model] = 0
+    k2[no_model] = 0
+    cap_c, cap_m = nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]
+    # pods already on the node: requests between 10 % and 130 % of capacity (the cap branch), limits >= requests,
+    # some nodes not overcommitted at all (limit < capacity: the conditioning branch), some empty
+    fr = g.uniform(0.1, 1.3, (2, N))
+    over = g.uniform(1.0, 2.5, (2, N))
+    req_c = (cap_c * fr[0]).astype(np.int64) // 50 * 50
+    req_m = (cap_m * fr[1]).astype(np.int64) >> 20 << 20
+    lim_c = (req_c * over[0]).astype(np.int64) // 50 * 50
+    lim_m = (req_m * over[1]).astype(np.int64) >> 20 << 20
+    empty = g.random(N) < 0.05
+    for a in (req_c, req_m, lim_c, lim_m):
+        a[empty] = 0
+    pr_c = g.choice(np.array([0, 100, 250, 500, 1000, 2000, 4000]), size=P).astype(np.int64)
+    pr_m = (g.choice(np.array([0, 128, 256, 1024, 4096]), size=P) << 20).astype(np.int64)
+    pl_c = np.maximum(pr_c, g.choice(np.array([0, 500, 2000, 8000]), size=P)).astype(np.int64)  # SetMaxLimits
+    pl_m = np.maximum(pr_m, (g.choice(np.array([0, 512, 8192]), size=P) << 20)).astype(np.int64)
+    be = g.random(P) < 0.1  # best-effort pods score 0 everywhere
+    for a in (pr_c, pr_m, pl_c, pl_m):
+        a[be] = 0
+    return dict(k1=k1, k2=k2, node_req_cpu=req_c, node_req_mem=req_m, node_lim_cpu=lim_c, node_lim_mem=lim_m,
+                low_risk_pod=np.stack([pr_c, pr_m, pl_c, pl_m]), peaks_pod_cpu_milli=pr_c.copy())
+
+
 def gen_feasible_words(seed: int, P: int, N: int, npad: int, k_or: int = 3) -> np.ndarray:
     """Upstream feasibility (what the filters before the Score phase left) as packed words
     [P][npad/64] uint64, bit j of word w = node 64*w+j.  Each bit is the OR of k_or fair bits:

@@ -7,6 +7,7 @@ and DESIGN.md's per-kernel roofline table.
   c1  128 x 1 000     Allocatable Least
   c2  10k x 50k       Allocatable Most + NormalizeScore
   c3  10k x 50k       TargetLoadPacking, LoadVariationRiskBalancing
+  c3b 10k x 50k       Peaks (2 passes), LowRiskOverCommitment
   c4  5k x 20k x 4    NodeResourceTopologyMatch Filter + Score (all four strategies)
   c5s 50k x 25k       the per-GPU shard of c5 (50k x 200k over 8 GPUs): all five + combined top-1
 """
@@ -26,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--configs", default="c1,c2,c3,c4,c5s")
+    ap.add_argument("--configs", default="c1,c2,c3,c3b,c4,c5s")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import __graft_entry__ as g
@@ -100,6 +101,22 @@ def main():
                         lvrb_req_mem_bytes=pods["req_mem_bytes"])
         time_plugin(eng, "c3", E.PLUGIN_TLP, "TargetLoadPacking", P, N)
         time_plugin(eng, "c3", E.PLUGIN_LVRB, "LoadVariationRiskBalancing", P, N)
+    if "c3b" in cfgs:  # the rest of the Trimaran family on the c3 shape
+        P, N = 10_000, 50_000
+        seed = synth.BASE_SEED + 3
+        nodes = synth.gen_nodes(seed, N)
+        tri, t2 = synth.gen_trimaran(seed, nodes), synth.gen_trimaran2(seed, nodes, P)
+        eng.snapshot_begin(N)
+        eng.snapshot_peaks(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["tlp_flags"], t2["k1"], t2["k2"])
+        eng.snapshot_low_risk(tri["cpu_avg"], tri["cpu_std"], tri["mem_avg"], tri["mem_std"], nodes["alloc_cpu_milli"],
+                              nodes["alloc_mem_bytes"], tri["lvrb_flags"], t2["node_req_cpu"], t2["node_req_mem"],
+                              t2["node_lim_cpu"], t2["node_lim_mem"])
+        eng.snapshot_commit()
+        eng.config_low_risk(5, 0.5, 0.5)
+        eng.pods_upload(P, feasible=synth.gen_feasible_words(seed, P, N, eng.Npad),
+                        peaks_pod_cpu_milli=t2["peaks_pod_cpu_milli"], low_risk_pod=t2["low_risk_pod"])
+        time_plugin(eng, "c3b", E.PLUGIN_PEAKS, "Peaks", P, N)
+        time_plugin(eng, "c3b", E.PLUGIN_LOW_RISK, "LowRiskOverCommitment", P, N)
     if "c4" in cfgs:
         P, N = 5_000, 20_000
         seed = synth.BASE_SEED + 4
