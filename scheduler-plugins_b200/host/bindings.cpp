@@ -57,7 +57,8 @@ PYBIND11_MODULE(_b200host, m) {
   py::class_<NodeInfo>(m, "NodeInfo")
       .def(py::init<>())
       .def(py::init([](std::shared_ptr<Node> n) { return NodeInfo{std::move(n)}; }))
-      .def_readwrite("node", &NodeInfo::node);
+      .def_readwrite("node", &NodeInfo::node)
+      .def_readwrite("pods", &NodeInfo::pods);
   py::class_<Metric>(m, "Metric")
       .def(py::init([](std::string t, std::string o, double v) { return Metric{std::move(t), std::move(o), v}; }))
       .def_readwrite("type", &Metric::type)
@@ -172,6 +173,24 @@ PYBIND11_MODULE(_b200host, m) {
       .def("pre_score", &LoadVariationRiskBalancing::PreScore)
       .def("score", &LoadVariationRiskBalancing::Score)
       .def("patched_rows", &LoadVariationRiskBalancing::PatchedRows);
+  py::class_<PowerModel>(m, "PowerModel")
+      .def(py::init([](double k0, double k1, double k2) { return PowerModel{k0, k1, k2}; }));
+  py::class_<PeaksArgs>(m, "PeaksArgs").def(py::init<>()).def_readwrite("node_power_model", &PeaksArgs::node_power_model);
+  py::class_<Peaks>(m, "Peaks")
+      .def_static("new", &Peaks::New)
+      .def("name", &Peaks::Name)
+      .def("pre_score", &Peaks::PreScore)
+      .def("score", &Peaks::Score);
+  py::class_<LowRiskOverCommitmentArgs>(m, "LowRiskOverCommitmentArgs")
+      .def(py::init<>())
+      .def_readwrite("smoothing_window_size", &LowRiskOverCommitmentArgs::smoothing_window_size)
+      .def_readwrite("risk_limit_weight_cpu", &LowRiskOverCommitmentArgs::risk_limit_weight_cpu)
+      .def_readwrite("risk_limit_weight_memory", &LowRiskOverCommitmentArgs::risk_limit_weight_memory);
+  py::class_<LowRiskOverCommitment>(m, "LowRiskOverCommitment")
+      .def_static("new", &LowRiskOverCommitment::New)
+      .def("name", &LowRiskOverCommitment::Name)
+      .def("pre_score", &LowRiskOverCommitment::PreScore)
+      .def("score", &LowRiskOverCommitment::Score);
   py::class_<NodeResourceTopologyMatchArgs>(m, "NodeResourceTopologyMatchArgs")
       .def(py::init<>())
       .def_readwrite("scoring_strategy", &NodeResourceTopologyMatchArgs::scoring_strategy)

@@ -166,7 +166,8 @@ int64_t PodPredictedCPU(const Pod& p, int64_t default_milli, double multiplier) 
   return total;
 }
 
-void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) {
+// GetEffectiveResource: resourcestats.go:124-146 (framework.Resource.Add takes MilliValue for cpu, Value for memory)
+static void EffectiveResource(const Pod& p, bool limits, int64_t* cpu_milli, int64_t* mem_bytes) {
   int64_t cpu = 0, mem = 0;
   auto get = [](const ResourceList& r, const char* k, int64_t* out) {
     auto it = r.find(k);
@@ -176,12 +177,14 @@ void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) 
   };
   int64_t v;
   for (auto& c : p.containers) {
-    if (get(c.requests, ResourceCPU, &v)) cpu += v;
-    if (get(c.requests, ResourceMemory, &v)) mem += QuantityValue(v);
+    const ResourceList& rl = limits ? c.limits : c.requests;
+    if (get(rl, ResourceCPU, &v)) cpu += v;
+    if (get(rl, ResourceMemory, &v)) mem += QuantityValue(v);
   }
   for (auto& c : p.init_containers) {
-    if (get(c.requests, ResourceCPU, &v)) cpu = std::max(cpu, v);
-    if (get(c.requests, ResourceMemory, &v)) mem = std::max(mem, QuantityValue(v));
+    const ResourceList& rl = limits ? c.limits : c.requests;
+    if (get(rl, ResourceCPU, &v)) cpu = std::max(cpu, v);
+    if (get(rl, ResourceMemory, &v)) mem = std::max(mem, QuantityValue(v));
   }
   if (p.has_overhead) {
     if (get(p.overhead, ResourceCPU, &v)) cpu += v;
@@ -189,6 +192,25 @@ void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) 
   }
   *cpu_milli = cpu;
   *mem_bytes = mem;
+}
+void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) { EffectiveResource(p, false, cpu_milli, mem_bytes); }
+void GetResourceLimits(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) { EffectiveResource(p, true, cpu_milli, mem_bytes); }
+
+int64_t GetResourceRequestQuantityCPU(const Pod& p) {
+  int64_t total = 0;
+  for (auto& c : p.containers) {
+    auto it = c.requests.find(ResourceCPU);
+    if (it != c.requests.end()) total += it->second;
+  }
+  for (auto& c : p.init_containers) {
+    auto it = c.requests.find(ResourceCPU);
+    if (it != c.requests.end() && total < it->second) total = it->second;
+  }
+  if (p.has_overhead) {
+    auto it = p.overhead.find(ResourceCPU);
+    if (it != p.overhead.end() && total != 0) total += it->second;
+  }
+  return total;
 }
 
 void GetResourceData(const std::vector<Metric>& ms, const std::string& type, double* avg, double* std_, bool* valid) {

@@ -57,6 +57,7 @@ struct Node {
 
 struct NodeInfo {
   std::shared_ptr<Node> node;  // Node() == nil is representable
+  std::vector<std::shared_ptr<Pod>> pods;  // GetPods(): the pods already on the node
   const Node* GetNode() const { return node.get(); }
 };
 
@@ -150,6 +151,11 @@ ResourceList GetPodEffectiveRequest(const Pod& p);         // pkg/util/resource.
 int64_t PredictUtilisation(const Container& c, int64_t default_milli, double multiplier);
 int64_t PodPredictedCPU(const Pod& p, int64_t default_milli, double multiplier);  // targetloadpacking.go:122-129
 void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes);  // resourcestats.go:110-146
+void GetResourceLimits(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes);     // resourcestats.go:117-122
+// resource.GetResourceRequestQuantity(pod, cpu).MilliValue() [k8s.io/kubernetes/pkg/api/v1/resource, upstream]:
+// sum of the app containers' requests, raised to the largest init container request, plus the pod overhead when
+// the total is non-zero (peaks.go:113-114)
+int64_t GetResourceRequestQuantityCPU(const Pod& p);
 // GetResourceData: resourcestats.go:89-107
 void GetResourceData(const std::vector<Metric>& m, const std::string& type, double* avg, double* std_, bool* valid);
 

@@ -458,6 +458,189 @@ std::pair<int64_t, Status> LoadVariationRiskBalancing::Score(CycleState& state, 
   return Lookup(c, nodeInfo);
 }
 
+// =============================================================== Peaks
+std::unique_ptr<Peaks> Peaks::New(const PeaksArgs& args, std::shared_ptr<Handle> h) {
+  std::unique_ptr<Peaks> p(new Peaks());
+  p->h_ = std::move(h);
+  p->args_ = args;
+  p->eng_ = std::make_unique<Engine>(p->h_->device);
+  return p;
+}
+
+void Peaks::EnsureSnapshot() {
+  if (snap_gen_ == h_->generation && n_ == (int32_t)h_->node_infos.size()) return;
+  const auto& nodes = h_->node_infos;
+  n_ = (int32_t)nodes.size();
+  npad_ = NPad(n_);
+  index_ = IndexOf(nodes);
+  const int m = std::max(n_, 1);
+  std::vector<double> util(m, 0), k1(m, 0), k2(m, 0);
+  std::vector<int64_t> cap(m, 0);
+  std::vector<uint8_t> flags(m, 0);
+  const WatcherMetrics* wm = h_->metrics.get();
+  for (int32_t i = 0; i < n_; ++i) {
+    const Node* nd = nodes[i].GetNode();
+    if (!nd) continue;
+    cap[i] = Get(nd->capacity, ResourceCPU);  // Status.Capacity, peaks.go:131
+    auto pm = args_.node_power_model.find(nd->name);  // getPowerModel :193-199: missing -> {0, 0, 0}
+    if (pm != args_.node_power_model.end()) k1[i] = pm->second.k1, k2[i] = pm->second.k2;
+    if (!wm || !wm->has_map) continue;
+    auto it = wm->node_metrics.find(nd->name);
+    if (it == wm->node_metrics.end()) continue;
+    flags[i] |= B200S_TLP_HAS_METRICS;
+    for (auto& mt : it->second.metrics)  // the FIRST matching entry wins, :117-126
+      if (mt.type == "CPU" && (mt.op == "AVG" || mt.op == "Latest")) {
+        util[i] = mt.value;
+        flags[i] |= B200S_TLP_CPU_FOUND;
+        break;
+      }
+  }
+  eng_->Check(b200s_snapshot_begin(eng_->ctx(), h_->generation, n_, 0, n_), "snapshot_begin");
+  eng_->Check(b200s_snapshot_peaks(eng_->ctx(), util.data(), cap.data(), flags.data(), k1.data(), k2.data()), "snapshot_peaks");
+  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  snap_gen_ = h_->generation;
+}
+
+std::shared_ptr<CycleResult> Peaks::Run(const Pod& pod, const std::vector<NodeInfo>* feasible) {
+  auto c = std::make_shared<CycleResult>();
+  try {
+    EnsureSnapshot();
+    c->index = index_;
+    c->scores.assign(npad_, 0);
+    const int64_t cpu = GetResourceRequestQuantityCPU(pod);  // :113-114
+    std::vector<uint64_t> words;
+    b200s_pod_batch b;
+    memset(&b, 0, sizeof(b));
+    b.n_pods = 1;
+    b.peaks_pod_cpu_milli = &cpu;
+    if (feasible) {
+      words = FeasibleWords(index_, npad_, NamesOf(*feasible));
+      b.feasible = words.data();
+    }
+    eng_->Check(b200s_score_batch(eng_->ctx(), B200S_PLUGIN_PEAKS, &b, B200S_OUT_U8, c->scores.data(), nullptr, nullptr),
+                "score_batch(Peaks)");
+  } catch (const std::exception& e) {
+    c->engine_error = e.what();
+  }
+  return c;
+}
+
+Status Peaks::PreScore(CycleState& state, const Pod& pod, const std::vector<NodeInfo>& nodes) {
+  auto c = Run(pod, &nodes);
+  state.data[std::string("PreScore") + Name_] = c;
+  return c->engine_error.empty() ? Status{} : ErrorStatus(c->engine_error);
+}
+
+std::pair<int64_t, Status> Peaks::Score(CycleState& state, const Pod& pod, const NodeInfo& nodeInfo) {
+  if (!nodeInfo.GetNode()) return {0, ErrorStatus("node not found")};
+  auto c = Read<CycleResult>(state, std::string("PreScore") + Name_);
+  if (!c) {  // PreScore not called: every node of the snapshot is in the list
+    c = Run(pod, nullptr);
+    state.data[std::string("PreScore") + Name_] = c;
+  }
+  return Lookup(c, nodeInfo);
+}
+
+// =============================================================== LowRiskOverCommitment
+std::unique_ptr<LowRiskOverCommitment> LowRiskOverCommitment::New(const LowRiskOverCommitmentArgs& args,
+                                                                  std::shared_ptr<Handle> h) {
+  std::unique_ptr<LowRiskOverCommitment> p(new LowRiskOverCommitment());
+  p->h_ = std::move(h);
+  p->args_ = args;
+  // SetDefaults_LowRiskOverCommitmentArgs, apis/config/v1/defaults.go:170-183
+  if (p->args_.smoothing_window_size <= 0) p->args_.smoothing_window_size = 5;
+  auto fix = [](double& w) {
+    if (!(w >= 0 && w <= 1)) w = 0.5;
+  };
+  fix(p->args_.risk_limit_weight_cpu);
+  fix(p->args_.risk_limit_weight_memory);
+  p->eng_ = std::make_unique<Engine>(p->h_->device);
+  p->eng_->Check(b200s_config_low_risk(p->eng_->ctx(), p->args_.smoothing_window_size, p->args_.risk_limit_weight_cpu,
+                                       p->args_.risk_limit_weight_memory),
+                 "config_low_risk");
+  return p;
+}
+
+void LowRiskOverCommitment::EnsureSnapshot() {
+  if (snap_gen_ == h_->generation && n_ == (int32_t)h_->node_infos.size()) return;
+  const auto& nodes = h_->node_infos;
+  n_ = (int32_t)nodes.size();
+  npad_ = NPad(n_);
+  index_ = IndexOf(nodes);
+  const int m = std::max(n_, 1);
+  std::vector<double> ca(m, 0), cs(m, 0), ma(m, 0), ms(m, 0);
+  std::vector<int64_t> acpu(m, 0), amem(m, 0), rc(m, 0), rm(m, 0), lc(m, 0), lm(m, 0);
+  std::vector<uint8_t> flags(m, 0);
+  const WatcherMetrics* wm = h_->metrics.get();
+  for (int32_t i = 0; i < n_; ++i) {
+    const Node* nd = nodes[i].GetNode();
+    if (!nd) continue;
+    acpu[i] = Get(nd->allocatable, ResourceCPU);                    // resourcestats.go:170-175
+    amem[i] = QuantityValue(Get(nd->allocatable, ResourceMemory));
+    for (auto& p : nodes[i].pods) {  // GetNodeRequestsAndLimits :181-206 without the pending pod
+      if (!p) continue;
+      int64_t qc, qm, xc, xm;
+      GetResourceRequested(*p, &qc, &qm);
+      GetResourceLimits(*p, &xc, &xm);
+      xc = std::max(xc, qc), xm = std::max(xm, qm);  // SetMaxLimits :230-246
+      rc[i] += qc, rm[i] += qm, lc[i] += xc, lm[i] += xm;
+    }
+    if (!wm || !wm->has_map) continue;
+    auto it = wm->node_metrics.find(nd->name);
+    if (it == wm->node_metrics.end()) continue;
+    flags[i] |= B200S_LVRB_HAS_METRICS;
+    bool ok;
+    GetResourceData(it->second.metrics, "CPU", &ca[i], &cs[i], &ok);
+    if (ok) flags[i] |= B200S_LVRB_CPU_OK;
+    GetResourceData(it->second.metrics, "Memory", &ma[i], &ms[i], &ok);
+    if (ok) flags[i] |= B200S_LVRB_MEM_OK;
+  }
+  eng_->Check(b200s_snapshot_begin(eng_->ctx(), h_->generation, n_, 0, n_), "snapshot_begin");
+  eng_->Check(b200s_snapshot_low_risk(eng_->ctx(), ca.data(), cs.data(), ma.data(), ms.data(), acpu.data(), amem.data(),
+                                      flags.data(), rc.data(), rm.data(), lc.data(), lm.data()),
+              "snapshot_low_risk");
+  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  snap_gen_ = h_->generation;
+}
+
+std::shared_ptr<CycleResult> LowRiskOverCommitment::Run(const Pod& pod) {
+  auto c = std::make_shared<CycleResult>();
+  try {
+    EnsureSnapshot();
+    c->index = index_;
+    c->scores.assign(npad_, 0);
+    int64_t v[4];  // CreatePodResourcesStateData :257-267
+    GetResourceRequested(pod, &v[0], &v[1]);
+    GetResourceLimits(pod, &v[2], &v[3]);
+    v[2] = std::max(v[2], v[0]), v[3] = std::max(v[3], v[1]);
+    b200s_pod_batch b;
+    memset(&b, 0, sizeof(b));
+    b.n_pods = 1;
+    b.low_risk_pod = v;
+    eng_->Check(b200s_score_batch(eng_->ctx(), B200S_PLUGIN_LOW_RISK, &b, B200S_OUT_U8, c->scores.data(), nullptr, nullptr),
+                "score_batch(LowRiskOverCommitment)");
+  } catch (const std::exception& e) {
+    c->engine_error = e.what();
+  }
+  return c;
+}
+
+Status LowRiskOverCommitment::PreScore(CycleState& state, const Pod& pod, const std::vector<NodeInfo>&) {
+  auto c = Run(pod);
+  state.data[std::string("PreScore") + Name_] = c;
+  return c->engine_error.empty() ? Status{} : ErrorStatus(c->engine_error);
+}
+
+std::pair<int64_t, Status> LowRiskOverCommitment::Score(CycleState& state, const Pod& pod, const NodeInfo& nodeInfo) {
+  if (!nodeInfo.GetNode()) return {0, ErrorStatus("node not found")};
+  auto c = Read<CycleResult>(state, std::string("PreScore") + Name_);
+  if (!c) {  // recalculating, :113-118
+    c = Run(pod);
+    state.data[std::string("PreScore") + Name_] = c;
+  }
+  return Lookup(c, nodeInfo);
+}
+
 // =============================================================== NodeResourceTopologyMatch
 std::unique_ptr<TopologyMatch> TopologyMatch::New(const NodeResourceTopologyMatchArgs& args, std::shared_ptr<Handle> h) {
   std::unique_ptr<TopologyMatch> p(new TopologyMatch());

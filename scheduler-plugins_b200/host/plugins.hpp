@@ -216,6 +216,62 @@ class LoadVariationRiskBalancing {
   int32_t n_ = 0, npad_ = 0;
 };
 
+// Trimaran Peaks (pkg/trimaran/peaks/peaks.go).  As with NodeResourcesAllocatable, Score returns the value already
+// normalised over the list PreScore saw and NormalizeScore is a no-op: the pipeline Score -> NormalizeScore yields
+// exactly what the reference's pipeline yields (its raw Score values are only an intermediate).
+struct PowerModel {
+  double k0 = 0, k1 = 0, k2 = 0;  // power = k0 + k1 * e^(k2 * utilisation), apis/config/types.go:301-307
+};
+struct PeaksArgs {
+  std::map<std::string, PowerModel> node_power_model;
+};
+class Peaks {
+ public:
+  static constexpr const char* Name_ = "Peaks";
+  static std::unique_ptr<Peaks> New(const PeaksArgs& args, std::shared_ptr<Handle> h);
+  std::string Name() const { return Name_; }
+  Status PreScore(CycleState& state, const Pod& pod, const std::vector<NodeInfo>& nodes);
+  std::pair<int64_t, Status> Score(CycleState& state, const Pod& pod, const NodeInfo& nodeInfo);
+  Status NormalizeScore(CycleState&, const Pod&, std::vector<NodeScore>&) { return {}; }
+
+ private:
+  Peaks() = default;
+  void EnsureSnapshot();
+  std::shared_ptr<CycleResult> Run(const Pod& pod, const std::vector<NodeInfo>* feasible);
+  std::shared_ptr<Handle> h_;
+  std::unique_ptr<Engine> eng_;
+  PeaksArgs args_;
+  uint64_t snap_gen_ = 0;
+  std::map<std::string, int32_t> index_;
+  int32_t n_ = 0, npad_ = 0;
+};
+
+// Trimaran LowRiskOverCommitment (pkg/trimaran/lowriskovercommitment/lowriskovercommitment.go)
+struct LowRiskOverCommitmentArgs {
+  int64_t smoothing_window_size = 5;                      // defaults.go:70
+  double risk_limit_weight_cpu = 0.5, risk_limit_weight_memory = 0.5;  // defaults.go:72-77
+};
+class LowRiskOverCommitment {
+ public:
+  static constexpr const char* Name_ = "LowRiskOverCommitment";
+  static std::unique_ptr<LowRiskOverCommitment> New(const LowRiskOverCommitmentArgs& args, std::shared_ptr<Handle> h);
+  std::string Name() const { return Name_; }
+  Status PreScore(CycleState& state, const Pod& pod, const std::vector<NodeInfo>& nodes);
+  std::pair<int64_t, Status> Score(CycleState& state, const Pod& pod, const NodeInfo& nodeInfo);
+  Status NormalizeScore(CycleState&, const Pod&, std::vector<NodeScore>&) { return {}; }  // :150-152
+
+ private:
+  LowRiskOverCommitment() = default;
+  void EnsureSnapshot();
+  std::shared_ptr<CycleResult> Run(const Pod& pod);
+  std::shared_ptr<Handle> h_;
+  std::unique_ptr<Engine> eng_;
+  LowRiskOverCommitmentArgs args_;
+  uint64_t snap_gen_ = 0;
+  std::map<std::string, int32_t> index_;
+  int32_t n_ = 0, npad_ = 0;
+};
+
 // ---------------------------------------------------------------- NodeResourceTopologyMatch
 struct NodeResourceTopologyMatchArgs {
   std::string scoring_strategy = "LeastAllocated";  // defaults.go:84-87

@@ -403,3 +403,99 @@ def test_incremental_snapshot_trimaran_bind(H):
     assert l1[9] != l0[9] and [s for i, s in enumerate(l1) if i != 9] == [s for i, s in enumerate(l0) if i != 9]
     assert t1 == _scores(H.TargetLoadPacking.new(H.TargetLoadPackingArgs(), fh), H, pod, fh)
     assert l1 == _scores(H.LoadVariationRiskBalancing.new(H.LoadVariationRiskBalancingArgs(), fh), H, pod, fh)
+
+
+# ------------------------------------------------------------------ Trimaran Peaks / LowRiskOverCommitment
+def test_peaks_score_table(H, oracle):
+    """peaks_test.go:174-426: Score then NormalizeScore (a no-op in the mirror: Score is already normalised over
+    the PreScore list).  With one node in the list a non-zero raw score normalises to 100 (max == min), zero to 0."""
+    g = load("peaks.json")
+    m = g["power_model"]["node-1"]
+    args = H.PeaksArgs()
+    args.node_power_model = {"node-1": H.PowerModel(m["k0"], m["k1"], m["k2"])}
+    pods = {
+        "Pod with Requests": {"containers": [{"requests": {"cpu": "1", "memory": "2"}}]},
+        "No CPU metrics found": {"containers": [{"requests": {"cpu": "1", "memory": "2"}}]},
+        "Pod with Overhead": {"overhead": {"cpu": "0"}},
+        "Pod with above node resource capacity": {"containers": [{"limits": {"cpu": "2000m"}, "requests": {}}]},
+        "No watcher response for node": {"containers": [{"limits": {"cpu": "2000m"}, "requests": {}}]},
+        "404 resp from watcher": {},
+    }
+    metrics = {
+        "Pod with Requests": {"node-1": [("CPU", "Latest", 0.0)]},
+        "No CPU metrics found": {"node-1": [("Memory", "Latest", 0.0)]},
+        "Pod with Overhead": {"node-1": [("CPU", "Latest", 0.0)]},
+        "Pod with above node resource capacity": {"node-1": [("CPU", "Latest", 100.0)]},
+        "No watcher response for node": {},
+        "404 resp from watcher": None,
+    }
+    for case in g["score_cases"]:
+        fh = handle_with(H, [make_node(H, "node-1", {"cpu": "1000m", "memory": "1Gi"})])
+        fh.metrics = watcher(H, metrics[case["name"]])
+        p = H.Peaks.new(args, fh)
+        pod = make_pod(H, pods[case["name"]])
+        state = H.CycleState()
+        assert p.pre_score(state, pod, fh.node_infos).is_success()
+        score, status = p.score(state, pod, fh.node_infos[0])
+        raw = oracle.peaks_score(case["util"], case["cap_milli"], case["flags"], m["k1"], m["k2"], case["pod_cpu_milli"])
+        assert status.is_success() and score == oracle.peaks_normalize([raw])[0], case["name"]
+        assert score == (100 if case["name"] == "Pod with Requests" else 0)
+
+
+def test_peaks_first_metric_and_normalize_over_prescore_list(H, oracle):
+    """:117-126 the FIRST CPU Average|Latest metric wins (TargetLoadPacking keeps the last); NormalizeScore runs
+    over the nodes upstream handed to PreScore, nodes without a power model score with {0, 0, 0}."""
+    nodes = [make_node(H, f"node-{i}", {"cpu": "4000m"}) for i in range(5)]
+    fh = handle_with(H, nodes)
+    fh.metrics = watcher(H, {f"node-{i}": [("CPU", "AVG", 10.0 * (i + 1)), ("CPU", "Latest", 90.0)] for i in range(5)})
+    args = H.PeaksArgs()
+    args.node_power_model = {f"node-{i}": H.PowerModel(400.0, -90.0 - i, -0.07) for i in range(4)}  # node-4: no model
+    p = H.Peaks.new(args, fh)
+    pod = make_pod(H, {"containers": [{"requests": {"cpu": "500m"}}], "init": [{"requests": {"cpu": "800m"}}],
+                       "overhead": {"cpu": "100m"}})  # max(500, 800) + 100 = 900m
+    feasible = [fh.node_infos[i] for i in (0, 1, 3, 4)]
+    state = H.CycleState()
+    assert p.pre_score(state, pod, feasible).is_success()
+    got = [p.score(state, pod, ni)[0] for ni in feasible]
+    raw = [oracle.peaks_score(10.0 * (i + 1), 4000, 3, (-90.0 - i) if i < 4 else 0.0, -0.07 if i < 4 else 0.0, 900)
+           for i in (0, 1, 3, 4)]
+    assert got == list(oracle.peaks_normalize(raw)) and len(set(got)) >= 3
+
+
+def test_low_risk_over_commitment(H, oracle):
+    """lowriskovercommitment_test.go:140-245 'new node' (best-effort pod -> 0) and a node that already runs pods
+    (GetNodeRequestsAndLimits: limits raised to requests per pod, requests capped by capacity)."""
+    fh = handle_with(H, [make_node(H, "node-1", {"cpu": "1000m", "memory": "1Gi"})])
+    fh.metrics = watcher(H, {"node-1": [("CPU", "AVG", 20.0)]})
+    p = H.LowRiskOverCommitment.new(H.LowRiskOverCommitmentArgs(), fh)
+    assert p.name() == "LowRiskOverCommitment"
+    state, pod = H.CycleState(), make_pod(H, {})
+    assert p.pre_score(state, pod, fh.node_infos).is_success()
+    score, status = p.score(state, pod, fh.node_infos[0])
+    assert status.is_success() and score == 0
+
+    nodes = [make_node(H, f"node-{i}", {"cpu": "4000m", "memory": "8Gi"}) for i in range(3)]
+    running = [make_pod(H, {"containers": [{"requests": {"cpu": "1500m", "memory": "2Gi"}, "limits": {"cpu": "1000m", "memory": "6Gi"}}]}, name="a"),
+               make_pod(H, {"containers": [{"requests": {"cpu": "500m"}, "limits": {"cpu": "3000m", "memory": "1Gi"}}],
+                            "init": [{"requests": {"memory": "3Gi"}, "limits": {}}]}, name="b")]
+    infos = [H.NodeInfo(n) for n in nodes]
+    infos[0].pods = running
+    infos[1].pods = running[:1]
+    fh = H.Handle()
+    fh.node_infos = infos
+    fh.metrics = watcher(H, {f"node-{i}": [("CPU", "AVG", 35.0), ("CPU", "STD", 6.0), ("Memory", "AVG", 50.0), ("Memory", "STD", 4.0)]
+                             for i in range(2)})  # node-2 has no metrics -> 0
+    args = H.LowRiskOverCommitmentArgs()
+    args.risk_limit_weight_cpu = 0.3
+    p = H.LowRiskOverCommitment.new(args, fh)
+    pod = make_pod(H, {"containers": [{"requests": {"cpu": "1000m", "memory": "1Gi"}, "limits": {"cpu": "2000m"}}]})
+    got = [p.score(H.CycleState(), pod, ni)[0] for ni in fh.node_infos]
+    G = 1 << 30
+    sums = [  # per node: req cpu, req mem, lim cpu, lim mem (limits raised to requests per pod)
+        (1500 + 500, 2 * G + 3 * G, 1500 + 3000, 6 * G + 3 * G),
+        (1500, 2 * G, 1500, 6 * G),
+        (0, 0, 0, 0),
+    ]
+    want = [oracle.lowrisk_score(35.0, 6.0, 50.0, 4.0, 4000, 8 * G, 7 if i < 2 else 0, *sums[i], 1000, G, 2000, G, 5, 0.3, 0.5)
+            for i in range(3)]
+    assert got == want and got[2] == 0 and len(set(got)) == 3
