@@ -20,6 +20,9 @@
  *                             Filter          pkg/networkaware/networkoverhead/networkoverhead.go:326
  *                             Score           pkg/networkaware/networkoverhead/networkoverhead.go:362
  *                             NormalizeScore  pkg/networkaware/networkoverhead/networkoverhead.go:389
+ *   Peaks                     Score           pkg/trimaran/peaks/peaks.go:103
+ *                             NormalizeScore  pkg/trimaran/peaks/peaks.go:152
+ *   LowRiskOverCommitment     Score           pkg/trimaran/lowriskovercommitment/lowriskovercommitment.go:105
  *   upstream RunScorePlugins weight/sum + selectHost (restated; not in tree)
  *
  * Data model
