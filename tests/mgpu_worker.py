@@ -63,6 +63,18 @@ def main():
     got_topk = eng.fetch_topk()
     for p in range(P):
         assert [(int(e["score"]), int(e["node"])) for e in got_topk[p]] == want_topk[p], (rank, p)
+    # --- Peaks: NormalizeScore's min/max over the feasible set crosses the shards (one all-reduce between the passes)
+    nodes = d["nodes"]
+    tri, t2 = synth.gen_trimaran(seed, nodes), synth.gen_trimaran2(seed, nodes, P)
+    sl = slice(off, off + cnt)
+    eng.snapshot_begin(cnt, node_offset=off, n_nodes_global=N)
+    eng.snapshot_peaks(tri["cpu_avg"][sl], nodes["cap_cpu_milli"][sl], tri["tlp_flags"][sl], t2["k1"][sl], t2["k2"][sl])
+    eng.snapshot_commit()
+    eng.pods_upload(P, feasible=feas, peaks_pod_cpu_milli=t2["peaks_pod_cpu_milli"])
+    eng.eval(E.PLUGIN_PEAKS)
+    want = orc.peaks_batch(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["tlp_flags"], t2["k1"], t2["k2"],
+                           t2["peaks_pod_cpu_milli"], feas_full, pitch=E.npad_of(N))
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_PEAKS)[:, :cnt], want[:, sl]), f"rank {rank}: sharded Peaks differs"
     dist.barrier()
     if rank == 0:
         print(f"mgpu ok: world={world} P={P} N={N} shards={sharding.shard_bounds(N, world)}")
