@@ -235,6 +235,14 @@ int b200s_snapshot_patch_tlp(b200s_ctx* ctx, int32_t count, const int32_t* node_
 int b200s_snapshot_patch_lvrb(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const double* cpu_avg,
                               const double* cpu_std, const double* mem_avg, const double* mem_std,
                               const int64_t* alloc_cpu_milli, const int64_t* alloc_mem_bytes, const uint8_t* flags);
+int b200s_snapshot_patch_peaks(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const double* cpu_util_pct,
+                               const int64_t* cap_milli, const uint8_t* flags, const double* k1, const double* k2);
+/* a bind / pod deletion changes one node's request and limit sums (GetNodeRequestsAndLimits) */
+int b200s_snapshot_patch_low_risk(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const double* cpu_avg,
+                                  const double* cpu_std, const double* mem_avg, const double* mem_std,
+                                  const int64_t* alloc_cpu_milli, const int64_t* alloc_mem_bytes, const uint8_t* flags,
+                                  const int64_t* node_req_cpu_milli, const int64_t* node_req_mem_bytes,
+                                  const int64_t* node_lim_cpu_milli, const int64_t* node_lim_mem_bytes);
 /* rows->n_zones / n_res must equal the resident snapshot's; rows->res_flags is ignored; rows->cost must be
  * non-NULL iff the snapshot has costs. */
 int b200s_snapshot_patch_nrt(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const b200s_nrt_nodes* rows);

@@ -634,6 +634,45 @@ int b200s_snapshot_patch_lvrb(b200s_ctx* c, int32_t count, const int32_t* node_i
   return p.run(node_idx);
 }
 
+int b200s_snapshot_patch_peaks(b200s_ctx* c, int32_t count, const int32_t* node_idx, const double* util,
+                               const int64_t* cap, const uint8_t* flags, const double* k1, const double* k2) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_peaks, "snapshot_patch_peaks"));
+  if (!util || !cap || !flags || !k1 || !k2) return c->set_err(B200S_ERR_INVALID, "snapshot_patch_peaks: null column");
+  const size_t np = c->Npad;
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  p.add<double>(c->peaks_util, 0, util);
+  p.add<int64_t>(c->peaks_cap, 0, cap);
+  p.add<uint8_t>(c->peaks_flags, 0, flags);
+  p.add<double>(c->peaks_k, 0 * np, k1);
+  p.add<double>(c->peaks_k, 1 * np, k2);
+  return p.run(node_idx);
+}
+
+int b200s_snapshot_patch_low_risk(b200s_ctx* c, int32_t count, const int32_t* node_idx, const double* cpu_avg,
+                                  const double* cpu_std, const double* mem_avg, const double* mem_std,
+                                  const int64_t* alloc_cpu, const int64_t* alloc_mem, const uint8_t* flags,
+                                  const int64_t* node_req_cpu, const int64_t* node_req_mem, const int64_t* node_lim_cpu,
+                                  const int64_t* node_lim_mem) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_lowrisk, "snapshot_patch_low_risk"));
+  if (!cpu_avg || !cpu_std || !mem_avg || !mem_std || !alloc_cpu || !alloc_mem || !flags || !node_req_cpu ||
+      !node_req_mem || !node_lim_cpu || !node_lim_mem)
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_low_risk: null column");
+  const size_t np = c->Npad;
+  Patch p(c, count);
+  B200S_TRY(p.prepare(node_idx));
+  const double* f[4] = {cpu_avg, cpu_std, mem_avg, mem_std};
+  const int64_t* iv[6] = {alloc_cpu, alloc_mem, node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem};
+  for (int k = 0; k < 4; ++k) p.add<double>(c->lowrisk_f64, k * np, f[k]);
+  for (int k = 0; k < 6; ++k) p.add<int64_t>(c->lowrisk_i64, k * np, iv[k]);
+  p.add<uint8_t>(c->lowrisk_flags, 0, flags);
+  return p.run(node_idx);  // the per-node risk columns are re-derived at the next eval (keyed by the snapshot serial)
+}
+
 int b200s_snapshot_patch_nrt(b200s_ctx* c, int32_t count, const int32_t* node_idx, const b200s_nrt_nodes* nn) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);

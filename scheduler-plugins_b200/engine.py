@@ -33,6 +33,7 @@ EXPORTS = [
     "b200s_snapshot_peaks", "b200s_snapshot_low_risk", "b200s_config_low_risk",
     "b200s_snapshot_patch_begin", "b200s_snapshot_patch_allocatable", "b200s_snapshot_patch_tlp",
     "b200s_snapshot_patch_lvrb", "b200s_snapshot_patch_nrt", "b200s_snapshot_patch_network_overhead",
+    "b200s_snapshot_patch_peaks", "b200s_snapshot_patch_low_risk",
     "b200s_config_allocatable", "b200s_config_tlp", "b200s_config_lvrb", "b200s_config_nrt",
     "b200s_config_network_overhead", "b200s_fetch_network_overhead_raw", "b200s_fetch_network_overhead_counts",
     "b200s_pods_upload", "b200s_eval", "b200s_fetch_scores", "b200s_fetch_feasible", "b200s_fetch_reasons",
@@ -308,6 +309,24 @@ class Engine:
         fl = _arr(flags, np.uint8, m)
         self._chk(self.lib.b200s_snapshot_patch_lvrb(self.ctx, C.c_int32(len(idx)), _ptr(idx),
                                                      *[_ptr(x) for x in f], *[_ptr(x) for x in i], _ptr(fl)))
+
+    def snapshot_patch_peaks(self, node_idx, cpu_util_pct, cap_milli, flags, k1, k2):
+        idx = self._idx(node_idx); m = (len(idx),)
+        a = _arr(cpu_util_pct, np.float64, m); b = _arr(cap_milli, np.int64, m); c = _arr(flags, np.uint8, m)
+        d = _arr(k1, np.float64, m); e = _arr(k2, np.float64, m)
+        self._chk(self.lib.b200s_snapshot_patch_peaks(self.ctx, C.c_int32(len(idx)), _ptr(idx), _ptr(a), _ptr(b),
+                                                      _ptr(c), _ptr(d), _ptr(e)))
+
+    def snapshot_patch_low_risk(self, node_idx, cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu_milli, alloc_mem_bytes,
+                                flags, node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem):
+        idx = self._idx(node_idx); m = (len(idx),)
+        f = [_arr(x, np.float64, m) for x in (cpu_avg, cpu_std, mem_avg, mem_std)]
+        i = [_arr(x, np.int64, m) for x in (alloc_cpu_milli, alloc_mem_bytes)]
+        fl = _arr(flags, np.uint8, m)
+        nd = [_arr(x, np.int64, m) for x in (node_req_cpu, node_req_mem, node_lim_cpu, node_lim_mem)]
+        self._chk(self.lib.b200s_snapshot_patch_low_risk(self.ctx, C.c_int32(len(idx)), _ptr(idx),
+                                                         *[_ptr(x) for x in f], *[_ptr(x) for x in i], _ptr(fl),
+                                                         *[_ptr(x) for x in nd]))
 
     def snapshot_patch_nrt(self, node_idx, rows: dict):
         """rows: the dict of snapshot_nrt with every [..][N] array cut down to [..][len(node_idx)]."""

@@ -183,3 +183,48 @@ def test_patch_state_errors(eng, engine_mod):
     eng.config_allocatable(0, W_DEFAULT)
     eng.pods_upload(1)
     eng.eval(E.PLUGIN_ALLOCATABLE)
+
+
+def test_patch_trimaran2(eng, engine_mod, oracle):
+    """Peaks / LowRiskOverCommitment rows (a bind changes a node's request and limit sums): patched == re-flattened.
+    LowRisk compares two CUDA results (full vs patched), so it is exact despite the libm/CUDA tolerance."""
+    E = engine_mod
+    P, N, seed = 24, 1500, synth.BASE_SEED + 65
+    na, nb = synth.gen_nodes(seed, N), synth.gen_nodes(seed + 1, N)
+    ta, tb = synth.gen_trimaran(seed, na), synth.gen_trimaran(seed + 1, nb)
+    a2, b2 = synth.gen_trimaran2(seed, na, P), synth.gen_trimaran2(seed + 1, nb, P)
+    idx, decoy, uniq = pick_rows(seed, N)
+    m = lambda x, y: merged(x, y, uniq)  # noqa: E731
+    peaks_cols = lambda n, t, t2: (t["cpu_avg"], n["cap_cpu_milli"], t["tlp_flags"], t2["k1"], t2["k2"])  # noqa: E731
+    lr_cols = lambda n, t, t2: (t["cpu_avg"], t["cpu_std"], t["mem_avg"], t["mem_std"], n["alloc_cpu_milli"],  # noqa: E731
+                                n["alloc_mem_bytes"], t["lvrb_flags"], t2["node_req_cpu"], t2["node_req_mem"],
+                                t2["node_lim_cpu"], t2["node_lim_mem"])
+    pa, pb, la, lb = peaks_cols(na, ta, a2), peaks_cols(nb, tb, b2), lr_cols(na, ta, a2), lr_cols(nb, tb, b2)
+    pods = dict(peaks_pod_cpu_milli=a2["peaks_pod_cpu_milli"], low_risk_pod=a2["low_risk_pod"])
+
+    def evaluate():
+        eng.pods_upload(P, **pods)
+        eng.eval(E.PLUGIN_PEAKS)
+        eng.eval(E.PLUGIN_LOW_RISK)
+        return eng.fetch_scores(E.PLUGIN_PEAKS), eng.fetch_scores(E.PLUGIN_LOW_RISK)
+
+    eng.config_low_risk(5, 0.5, 0.5)
+    eng.snapshot_begin(N)  # reference run: the merged snapshot uploaded in full
+    eng.snapshot_peaks(*[m(x, y) for x, y in zip(pa, pb)])
+    eng.snapshot_low_risk(*[m(x, y) for x, y in zip(la, lb)])
+    eng.snapshot_commit()
+    want_peaks, want_lr = evaluate()
+    eng.snapshot_begin(N)  # A in full, evaluated (derives the risk columns of A), then patched with B's rows
+    eng.snapshot_peaks(*pa)
+    eng.snapshot_low_risk(*la)
+    eng.snapshot_commit()
+    before_peaks, before_lr = evaluate()
+    eng.snapshot_patch_begin(3)
+    eng.snapshot_patch_peaks(idx, *[rows(x, idx, decoy) for x in pb])
+    eng.snapshot_patch_low_risk(idx, *[rows(x, idx, decoy) for x in lb])
+    eng.snapshot_commit()
+    got_peaks, got_lr = evaluate()
+    assert np.array_equal(got_peaks, want_peaks) and np.array_equal(got_lr, want_lr)
+    assert not np.array_equal(before_peaks, want_peaks) and not np.array_equal(before_lr, want_lr)
+    assert np.array_equal(got_peaks, oracle.peaks_batch(*[m(x, y) for x, y in zip(pa, pb)], a2["peaks_pod_cpu_milli"],
+                                                        None, pitch=eng.Npad))
