@@ -100,3 +100,73 @@ def test_two_rank_sharded_normalize_and_topk(oracle):
     for p in range(P):
         order = np.lexsort((np.arange(N), -want[p]))[:K]
         assert list(folded[p]["node"]) == list(order) and list(folded[p]["score"]) == list(want[p][order])
+
+
+def _peaks_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as orc
+    from scheduler_plugins_b200 import engine as E
+    from scheduler_plugins_b200 import sharding, synth
+
+    nodes = synth.gen_nodes(321, N)
+    tri, t2 = synth.gen_trimaran(321, nodes), synth.gen_trimaran2(321, nodes, P)
+    feas = E.unpack_bits(synth.gen_feasible_words(321, P, N, E.npad_of(N)), N)
+    off, cnt = sharding.shard_bounds(N, world)[rank]
+    sl = slice(off, off + cnt)
+    # raw Peaks scores of this shard, local min/max over the feasible nodes, the exchange, then NormalizeScore
+    raw = np.array([[orc.peaks_score(tri["cpu_avg"][n], int(nodes["cap_cpu_milli"][n]), int(tri["tlp_flags"][n]),
+                                     t2["k1"][n], t2["k2"][n], int(t2["peaks_pod_cpu_milli"][p]))
+                     for n in range(off, off + cnt)] for p in range(P)], dtype=np.int64)
+    f = feas[:, sl].astype(bool)
+    big = np.iinfo(np.int64)
+    lo = torch.from_numpy(np.where(f, raw, big.max).min(axis=1))
+    hi = torch.from_numpy(np.where(f, raw, big.min).max(axis=1))
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = np.zeros_like(raw)
+    for p in range(P):
+        l, h = int(lo[p]), int(hi[p])
+        for i in np.nonzero(f[p])[0]:
+            s = int(raw[p, i])
+            if l == 0 and h == 0:
+                out[p, i] = s
+            elif h != l:
+                out[p, i] = 100 - int(100.0 * float(s - l) / float(h - l))
+            else:
+                out[p, i] = 100
+    q.put((out, off, cnt))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_peaks_normalize(oracle):
+    """Peaks.NormalizeScore (peaks.go:152-168) over a node-sharded list: per-shard min/max + one exchange == unsharded."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from scheduler_plugins_b200 import engine as E
+    from scheduler_plugins_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_peaks_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nodes = synth.gen_nodes(321, N)
+    tri, t2 = synth.gen_trimaran(321, nodes), synth.gen_trimaran2(321, nodes, P)
+    want = oracle.peaks_batch(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["tlp_flags"], t2["k1"], t2["k2"],
+                              t2["peaks_pod_cpu_milli"], synth.gen_feasible_words(321, P, N, E.npad_of(N)), pitch=N)
+    got = np.zeros((P, N), dtype=np.int64)
+    for out, off, cnt in res:
+        got[:, off:off + cnt] = out
+    assert np.array_equal(got, want)
