@@ -411,8 +411,21 @@ struct NrtPodCols {
   const int64_t* req;       // [P][9][Rs]
 };
 
+// tuning knobs (defaults = the measured best; overridable with -D for A/B builds)
+#ifndef B200S_NRT_MIN_BLOCKS
+#define B200S_NRT_MIN_BLOCKS 3
+#endif
+#ifndef B200S_NRT_POD_UNROLL
+#define B200S_NRT_POD_UNROLL 1
+#endif
+#ifndef B200S_NRT_PT
+#define B200S_NRT_PT 32
+#endif
+#define B200S_PRAGMA(x) _Pragma(#x)
+#define B200S_UNROLL(n) B200S_PRAGMA(unroll n)
+
 template <int Z, int R, int SC, class OutT, int PT>
-__global__ void __launch_bounds__(128, (Z <= 4 ? 3 : 1))
+__global__ void __launch_bounds__(128, (Z <= 4 ? B200S_NRT_MIN_BLOCKS : 1))
 nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict__ upstream, int words, int N,
            int Npad, int P, OutT* __restrict__ out, uint32_t* __restrict__ feas_out32, uint8_t* __restrict__ reasons) {
   __shared__ PodS<R> sp[PT];
@@ -495,6 +508,7 @@ nrt_kernel(NrtNodeCols nc, NrtPodCols pc, NrtCfg cfg, const uint64_t* __restrict
   // The warp walks the pods of the tile together: pod data is a shared-memory broadcast and every branch on it is
   // warp-uniform.  (Measured alternative: per-lane work lists of the surviving pods keep all lanes busy but turn
   // those broadcasts and uniform branches into divergent ones: 14.5 ms instead of 11.5 ms at c4.)
+  B200S_UNROLL(B200S_NRT_POD_UNROLL)
   for (int pp = 0; pp < pend; ++pp) {
     const int p = p0 + pp;
     const PodS<R>& pod = sp[pp];
@@ -526,7 +540,7 @@ __global__ void nrt_feas_kernel(const uint8_t* __restrict__ reasons, int N, int 
 
 template <int Z, int R, int SC>
 int launch_sc(b200s_ctx* c, int dtype, const NrtNodeCols& nc, const NrtPodCols& pc, const NrtCfg& cfg) {
-  constexpr int PT = 16;
+  constexpr int PT = (R <= 4 ? B200S_NRT_PT : 16);
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
   const uint64_t* up = c->upstream_mask();

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200sched.so")
+# B200S_LIB selects another build of the same library (A/B experiments with tuning knobs); never a fallback
+LIB_PATH = os.environ.get("B200S_LIB") or os.path.join(_HERE, "lib", "libb200sched.so")
 
 (PLUGIN_ALLOCATABLE, PLUGIN_TLP, PLUGIN_LVRB, PLUGIN_NRT, PLUGIN_NETWORK_OVERHEAD, PLUGIN_PEAKS,
  PLUGIN_LOW_RISK) = range(7)
