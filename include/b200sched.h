@@ -360,7 +360,10 @@ int b200s_fetch_total_feasible(b200s_ctx* ctx, uint64_t* out, size_t bytes);
 
 /* ---- the per-call convenience the Go shim uses from PreScore ---------------- */
 /* upload + eval + fetch in one call, HOST buffers in and out.  scores_out has
- * P*Npad elements of `dtype`; feasible_out / reasons_out may be NULL. */
+ * P*Npad elements of `dtype`; feasible_out / reasons_out may be NULL.
+ * A large batch (>= 96 MB of scores) of a score-only plugin (Allocatable, TLP, LVRB, Peaks) with both optional
+ * outputs NULL is pipelined in pod chunks -- the D2H of one chunk overlaps the H2D of the next -- and leaves NO
+ * engine-resident result behind: b200s_fetch_* and b200s_device_* fail until the next b200s_eval. */
 int b200s_score_batch(b200s_ctx* ctx, b200s_plugin plugin, const b200s_pod_batch* batch,
                       b200s_out_dtype dtype, void* scores_out, uint64_t* feasible_out,
                       uint8_t* reasons_out);

@@ -289,6 +289,9 @@ void b200s_shutdown(b200s_ctx* c) {
   if (c->pods_stage) cudaFreeHost(c->pods_stage);
   c->patch_dev.release();
   if (c->patch_stage) cudaFreeHost(c->patch_stage);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (cudaEvent_t e : {c->ev_kernels, c->ev_d2h, c->ev_h2d})
+    if (e) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1043,16 +1046,80 @@ int b200s_debug_div_check(b200s_ctx* c, const double* x, const double* d, int32_
   return debug_div_check(c, x, d, n, mismatches);
 }
 
+// Large batches of the score-only plugins travel in pod chunks: per chunk the inputs go in on the main stream, the
+// kernels run, and the scores leave on a second stream -- so chunk i's D2H overlaps chunk i+1's H2D (the two PCIe
+// directions) instead of the whole mask going in before the first score byte comes out.  Pods are independent
+// (every normalisation is per pod), so chunking cannot change a result.
+static int score_batch_chunked(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,
+                               void* scores_out, int chunks) {
+  if (!c->d2h_stream) {
+    B200S_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_kernels, cudaEventDisableTiming));
+    B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming));
+    B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
+  }
+  const int P = batch->n_pods;
+  const size_t words = (size_t)(c->Npad / 64), esz = dtype == B200S_OUT_I64 ? 8 : 1;
+  const int step = (P + chunks - 1) / chunks;
+  int rc = B200S_OK;
+  for (int i0 = 0, k = 0; i0 < P && rc == B200S_OK; i0 += step, ++k) {
+    b200s_pod_batch sub = *batch;
+    sub.n_pods = std::min(step, P - i0);
+    if (batch->feasible) sub.feasible = batch->feasible + (size_t)i0 * words;
+    if (batch->tlp_pod_cpu_milli) sub.tlp_pod_cpu_milli = batch->tlp_pod_cpu_milli + i0;
+    if (batch->lvrb_req_cpu_milli) sub.lvrb_req_cpu_milli = batch->lvrb_req_cpu_milli + i0;
+    if (batch->lvrb_req_mem_bytes) sub.lvrb_req_mem_bytes = batch->lvrb_req_mem_bytes + i0;
+    if (batch->peaks_pod_cpu_milli) sub.peaks_pod_cpu_milli = batch->peaks_pod_cpu_milli + i0;
+    sub.nrt = nullptr;
+    sub.netoh = nullptr;
+    sub.low_risk_pod = nullptr;  // [4][P] layout: not sliceable by pointer offset
+    // the pinned staging block of the small pod columns is re-used: the previous chunk's copy must have left it
+    if (k > 0) B200S_CUDA_TRY(c, cudaEventSynchronize(c->ev_h2d));
+    rc = pods_upload_locked(c, &sub);
+    if (rc != B200S_OK) break;
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_h2d, c->stream));
+    if (k > 0) B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_d2h, 0));  // the score matrix is re-used too
+    rc = eval_locked(c, plugin, dtype);
+    if (rc != B200S_OK) break;
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_kernels, c->stream));
+    B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_kernels, 0));
+    const size_t bytes = (size_t)sub.n_pods * c->Npad * esz;
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(static_cast<char*>(scores_out) + (size_t)i0 * c->Npad * esz,
+                                      c->out[plugin].scores.p, bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_d2h, c->d2h_stream));
+  }
+  return rc;
+}
+
 int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,
                       void* scores_out, uint64_t* feasible_out, uint8_t* reasons_out) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
-  // one stream, one synchronisation at the very end: H2D copies, kernels and D2H copies are queued back to back
+  // one synchronisation at the very end: H2D copies, kernels and D2H copies are queued back to back
   struct Defer {
     b200s_ctx* c;
     explicit Defer(b200s_ctx* x) : c(x) { c->defer_sync = true; }
     ~Defer() { c->defer_sync = false; }
   } defer(c);
+  const bool score_only = plugin == B200S_PLUGIN_ALLOCATABLE || plugin == B200S_PLUGIN_TLP ||
+                          plugin == B200S_PLUGIN_LVRB || plugin == B200S_PLUGIN_PEAKS;
+  const size_t esz = dtype == B200S_OUT_I64 ? 8 : 1;
+  const size_t out_bytes = batch && batch->n_pods > 0 ? (size_t)batch->n_pods * c->Npad * esz : 0;
+  constexpr size_t kChunkBytes = (size_t)48 << 20;
+  if (score_only && batch && scores_out && !feasible_out && !reasons_out && c->snap_valid &&
+      (dtype == B200S_OUT_I64 || dtype == B200S_OUT_U8) && out_bytes >= 2 * kChunkBytes && batch->n_pods >= 64) {
+    const int chunks = (int)std::min<size_t>(std::min<size_t>(16, (size_t)batch->n_pods / 32), out_bytes / kChunkBytes);
+    int rc = score_batch_chunked(c, plugin, batch, dtype, scores_out, std::max(chunks, 2));
+    cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->d2h_stream);
+    // the engine-resident matrices hold the last chunk only: nothing may be fetched from them afterwards
+    c->pods_valid = false;
+    for (auto& o : c->out) o.valid = false;
+    c->total_valid = c->topk_valid = false;
+    if (rc != B200S_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return c->set_err(B200S_ERR_CUDA, std::string("score_batch: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return B200S_OK;
+  }
   int rc = pods_upload_locked(c, batch);
   if (rc == B200S_OK) rc = eval_locked(c, plugin, dtype);
   size_t elems = (size_t)c->P * c->Npad;

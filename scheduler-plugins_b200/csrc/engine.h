@@ -78,6 +78,10 @@ struct Comm;  // NCCL communicator wrapper (comm.cu)
 struct b200s_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // b200s_score_batch pipelines a large batch in pod chunks: the D2H of chunk i runs here while the main stream
+  // already copies chunk i+1's inputs in (PCIe is full duplex) -- created on first use
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;

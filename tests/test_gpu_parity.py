@@ -326,3 +326,42 @@ def test_network_overhead_generic_normalize(eng, engine_mod, oracle):
                                    net["score_equally"], net["dep_offset"], net["deps"], None, pitch=eng.Npad)
     assert np.array_equal(eng.fetch_feasible(E.PLUGIN_NETWORK_OVERHEAD), wf)
     assert np.array_equal(eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD), ws)
+
+
+def test_score_batch_chunked_pipeline(eng, engine_mod, oracle):
+    """b200s_score_batch splits a large batch of a score-only plugin into pod chunks (D2H of chunk i overlaps H2D of
+    chunk i+1): the host matrix must equal the unchunked upload + eval + fetch, and the engine-resident matrices are
+    invalidated afterwards."""
+    E = engine_mod
+    P, N, seed = 3000, 20_000, synth.BASE_SEED + 9
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    eng.snapshot_begin(N)
+    eng.snapshot_allocatable([nodes["alloc_cpu_milli"], nodes["alloc_mem_bytes"]])
+    eng.snapshot_tlp(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"])
+    eng.snapshot_commit()
+    eng.config_allocatable(1, W_DEFAULT)
+    eng.config_tlp(40)
+    feas = synth.gen_feasible_words(seed, P, N, eng.Npad)
+    cols = dict(feasible=feas, tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"])
+    for plugin, dtype, npdt in ((E.PLUGIN_ALLOCATABLE, E.OUT_I64, np.int64), (E.PLUGIN_TLP, E.OUT_I64, np.int64),
+                                (E.PLUGIN_ALLOCATABLE, E.OUT_U8, np.uint8)):
+        eng.pods_upload(P, **cols)
+        eng.eval(plugin, dtype)
+        want = eng.fetch_scores(plugin, dtype)
+        batch, keep = eng.make_batch(P, **cols)
+        got = np.full((P, eng.Npad), 77, dtype=npdt)
+        eng.score_batch(plugin, batch, dtype, got)
+        assert got.nbytes >= (96 << 20) or dtype == E.OUT_U8  # the int64 cases take the chunked path
+        assert np.array_equal(got, want)
+        if got.nbytes >= (96 << 20):
+            with pytest.raises(E.B200SError):  # only the last chunk is resident: fetching would be wrong, so it fails
+                eng.fetch_scores(plugin, dtype)
+    # rows spot-checked against the oracle as well
+    rows = [0, 1499, 2999]
+    want_rows = oracle.tlp_batch(tri["cpu_avg"], nodes["cap_cpu_milli"], tri["missing_milli"], tri["tlp_flags"],
+                                 pods["tlp_pod_cpu_milli"][rows], 40, pitch=eng.Npad)
+    got = np.zeros((P, eng.Npad), dtype=np.int64)
+    batch, keep = eng.make_batch(P, **cols)
+    eng.score_batch(E.PLUGIN_TLP, batch, E.OUT_I64, got)
+    assert np.array_equal(got[rows], want_rows)
