@@ -184,26 +184,35 @@ template <int Z, int R, int SC>
 __device__ __forceinline__ int64_t strategy_score(const Zones<Z, R>& zs, int z, const NrtCfg& cfg, uint32_t req_mask,
                                                   const int64_t* req, const int64_t* reqv) {
   if constexpr (SC == 1) {
+    // fractions of every requested resource first (independent divisions, statically indexed), one exit test after
     double fr[R];
-    int n = 0;
+    bool over = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+      fr[r] = 0;
       if (!((req_mask >> r) & 1u)) continue;
       const int64_t cap = ((zs.zmask[z] >> r) & 1u) ? zs.avail[z][r] : 0;
       const int64_t cv = qty_value(cap);
-      const double f = cv == 0 ? 1.0 : (double)reqv[r] / (double)cv;
-      if (f > 1) return 0;
-      fr[n++] = f;
+      const double q = (double)reqv[r] / (double)(cv == 0 ? 1 : cv);
+      const double f = cv == 0 ? 1.0 : q;
+      over |= f > 1;
+      fr[r] = f;
     }
-    double sum = 0;
-    for (int i = 0; i < n; ++i) sum += fr[i];
+    if (over) return 0;
+    const int n = __popc(req_mask & ((1u << R) - 1u));
+    double sum = 0;  // summation in resource-slot order over the requested resources, as before
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((req_mask >> r) & 1u) sum += fr[r];
     const double mean = sum / (double)n;
     double ss = 0, comp = 0;
-    for (int i = 0; i < n; ++i) {
-      const double d = fr[i] - mean;
-      ss += d * d;
-      comp += d;
-    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((req_mask >> r) & 1u) {
+        const double d = fr[r] - mean;
+        ss += d * d;
+        comp += d;
+      }
     const double variance = (ss - comp * comp / (double)n) / ((double)n - 1);
     return f2i((1 - variance) * 100.0);
   }
