@@ -246,6 +246,15 @@ int b200s_snapshot_patch_low_risk(b200s_ctx* ctx, int32_t count, const int32_t* 
 /* rows->n_zones / n_res must equal the resident snapshot's; rows->res_flags is ignored; rows->cost must be
  * non-NULL iff the snapshot has costs. */
 int b200s_snapshot_patch_nrt(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const b200s_nrt_nodes* rows);
+/* OverReserve cache (pkg/noderesourcetopology/cache/overreserve.go:101-127, store.go:129-160): a pod assumed on a
+ * node is deducted from EVERY zone of that node that lists the resource -- available = available < q ? 0 :
+ * available - q -- until the node's NRT is resynced.  deduct [R][count] = the quantities to take off (for several
+ * assumed pods: their per-resource sum, which gives the same result as the reference's pod-by-pod loop for
+ * non-negative quantities), res_mask[count] bit r = the resource is a key of some assumed pod's request map.
+ * Cumulative and in place; a resync is a b200s_snapshot_patch_nrt of the row followed by the deduction of what is
+ * still assumed.  node_idx must not repeat. */
+int b200s_snapshot_patch_nrt_deduct(b200s_ctx* ctx, int32_t count, const int32_t* node_idx, const uint8_t* res_mask,
+                                    const int64_t* deduct);
 /* labels only (ids into the resident name dictionary); a changed cost table needs the full call */
 int b200s_snapshot_patch_network_overhead(b200s_ctx* ctx, int32_t count, const int32_t* node_idx,
                                           const uint16_t* region_id, const uint16_t* zone_id);

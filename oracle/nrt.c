@@ -407,3 +407,21 @@ void orc_nrt_batch(const orc_nrt_nodes_soa* ns, int N, const orc_nrt_pods_soa* p
     }
   }
 }
+
+/* resourceStore.UpdateNRT: pkg/noderesourcetopology/cache/store.go:129-160 -- the OverReserve cache's pessimistic
+ * deduction of ONE assumed pod's effective request from EVERY zone that lists the resource (GetCachedNRTCopy,
+ * overreserve.go:101-127, applies it once per assumed pod of the node).  avail [Z][R] in place; zmask[z] bit r = zone
+ * lists r; req_mask bit r = r is a key of the pod's request map. */
+void orc_nrt_overreserve_deduct(int64_t* avail, const uint8_t* zmask, int Z, int R, uint8_t req_mask, const int64_t* req) {
+  for (int z = 0; z < Z; ++z)
+    for (int r = 0; r < R; ++r) {
+      if (!((zmask[z] >> r) & 1)) continue;   /* the zone does not report the resource */
+      if (!((req_mask >> r) & 1)) continue;    /* :141-147 the pod does not ask for it */
+      int64_t* a = &avail[z * R + r];
+      if (*a < req[r]) {                       /* :148-155 "cannot decrement resource": zeroed */
+        *a = 0;
+        continue;
+      }
+      *a -= req[r];                            /* :157 */
+    }
+}

@@ -65,6 +65,9 @@ void orc_lvrb_batch(const double* cpu_avg, const double* cpu_std, const double* 
                     const int64_t* req_cpu, const int64_t* req_mem, int P, double margin, double sens,
                     int64_t* out, int pitch);
 
+/* OverReserve cache deduction of one assumed pod (cache/store.go:129-160); see nrt.c */
+void orc_nrt_overreserve_deduct(int64_t* avail, const uint8_t* zmask, int Z, int R, uint8_t req_mask, const int64_t* req);
+
 /* ---- Trimaran Peaks + LowRiskOverCommitment (trimaran2.c; see its header for the parity note) ---- */
 double orc_go_exp(double x);
 int64_t orc_peaks_score(double util_pct, int64_t cap_milli, uint8_t flags, double k1, double k2, int64_t pod_cpu_milli);

@@ -115,6 +115,20 @@ __global__ void patch_scatter_kernel(const unsigned char* __restrict__ stage, co
   }
 }
 
+// OverReserve deduction (cache/store.go:129-160): one thread per (row, zone, resource) cell
+__global__ void nrt_deduct_kernel(const int32_t* __restrict__ idx, const uint8_t* __restrict__ res_mask,
+                                  const int64_t* __restrict__ deduct, int count, int Z, int R, size_t npad,
+                                  const uint8_t* __restrict__ zmask, int64_t* __restrict__ avail) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * Z * R) return;
+  const int i = t / (Z * R), z = (t / R) % Z, r = t % R;
+  const size_t n = (size_t)idx[i];
+  if (!((zmask[(size_t)z * npad + n] >> r) & 1u) || !((res_mask[i] >> r) & 1u)) return;
+  int64_t* a = avail + ((size_t)z * R + r) * npad + n;
+  const int64_t q = deduct[(size_t)r * count + i], v = *a;
+  *a = v < q ? 0 : v - q;
+}
+
 // Collects the columns of one patch call, packs them behind the index list and launches the scatter.
 // Repeated indices: rows are de-duplicated on the host (last wins) so that the scatter has no write race.
 struct Patch {
@@ -708,6 +722,47 @@ int b200s_snapshot_patch_nrt(b200s_ctx* c, int32_t count, const int32_t* node_id
     if (nrt_class_of(c->nrt_key_h[node_idx[i]]) != nrt_class_of(key)) c->nrt_perm_dirty = true;
     c->nrt_key_h[node_idx[i]] = key;
   }
+  return B200S_OK;
+}
+
+int b200s_snapshot_patch_nrt_deduct(b200s_ctx* c, int32_t count, const int32_t* node_idx, const uint8_t* res_mask,
+                                    const int64_t* deduct) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  B200S_TRY(require_patching(c, c->has_nrt, "snapshot_patch_nrt_deduct"));
+  if (count < 0 || (count > 0 && (!node_idx || !res_mask || !deduct)))
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt_deduct: bad count / null column");
+  if (count == 0) return B200S_OK;
+  std::vector<int32_t> seen(node_idx, node_idx + count);
+  std::sort(seen.begin(), seen.end());
+  if (seen.front() < 0 || seen.back() >= c->N || std::adjacent_find(seen.begin(), seen.end()) != seen.end())
+    return c->set_err(B200S_ERR_INVALID, "snapshot_patch_nrt_deduct: node index out of range or repeated");
+  const int Z = c->nrt_Z, R = c->nrt_R;
+  auto up8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+  const size_t o_idx = 0, o_mask = up8((size_t)count * 4), o_ded = o_mask + up8((size_t)count),
+               total = o_ded + (size_t)R * count * 8;
+  if (total > c->patch_stage_cap) {
+    if (c->patch_stage) cudaFreeHost(c->patch_stage);
+    c->patch_stage = nullptr;
+    c->patch_stage_cap = 0;
+    B200S_CUDA_TRY(c, cudaHostAlloc(&c->patch_stage, total * 2, cudaHostAllocDefault));
+    c->patch_stage_cap = total * 2;
+  }
+  B200S_CUDA_TRY(c, c->patch_dev.ensure(total));
+  char* st = static_cast<char*>(c->patch_stage);
+  memcpy(st + o_idx, node_idx, (size_t)count * 4);
+  memcpy(st + o_mask, res_mask, (size_t)count);
+  memcpy(st + o_ded, deduct, (size_t)R * count * 8);
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(c->patch_dev.p, st, total, cudaMemcpyHostToDevice, c->stream));
+  const char* dev = c->patch_dev.as<char>();
+  const int cells = count * Z * R;
+  nrt_deduct_kernel<<<(cells + 255) / 256, 256, 0, c->stream>>>(
+      reinterpret_cast<const int32_t*>(dev + o_idx), reinterpret_cast<const uint8_t*>(dev + o_mask),
+      reinterpret_cast<const int64_t*>(dev + o_ded), count, Z, R, (size_t)c->Npad, c->nrt_zone_res_mask.as<uint8_t>(),
+      c->nrt_avail.as<int64_t>());
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the staging block is re-used by the next patch call
+  c->launches++;
   return B200S_OK;
 }
 

@@ -34,7 +34,7 @@ EXPORTS = [
     "b200s_snapshot_peaks", "b200s_snapshot_low_risk", "b200s_config_low_risk",
     "b200s_snapshot_patch_begin", "b200s_snapshot_patch_allocatable", "b200s_snapshot_patch_tlp",
     "b200s_snapshot_patch_lvrb", "b200s_snapshot_patch_nrt", "b200s_snapshot_patch_network_overhead",
-    "b200s_snapshot_patch_peaks", "b200s_snapshot_patch_low_risk",
+    "b200s_snapshot_patch_peaks", "b200s_snapshot_patch_low_risk", "b200s_snapshot_patch_nrt_deduct",
     "b200s_config_allocatable", "b200s_config_tlp", "b200s_config_lvrb", "b200s_config_nrt",
     "b200s_config_network_overhead", "b200s_fetch_network_overhead_raw", "b200s_fetch_network_overhead_counts",
     "b200s_pods_upload", "b200s_eval", "b200s_fetch_scores", "b200s_fetch_feasible", "b200s_fetch_reasons",
@@ -345,6 +345,12 @@ class Engine:
         s = NrtNodes(Z, R, None, *[_ptr(keep[k]) for k in ("node_flags", "max_numa", "n_zones_node",
                                                            "node_res_mask", "zone_res_mask", "avail", "cost")])
         self._chk(self.lib.b200s_snapshot_patch_nrt(self.ctx, C.c_int32(m), _ptr(idx), C.byref(s)))
+
+    def snapshot_patch_nrt_deduct(self, node_idx, res_mask, deduct):
+        """OverReserve: deduct[R][count] off every zone of the listed nodes that reports the resource."""
+        idx = self._idx(node_idx); m = len(idx)
+        rm = _arr(res_mask, np.uint8, (m,)); d = _arr(deduct, np.int64, (self.nrt_R, m))
+        self._chk(self.lib.b200s_snapshot_patch_nrt_deduct(self.ctx, C.c_int32(m), _ptr(idx), _ptr(rm), _ptr(d)))
 
     def snapshot_patch_network_overhead(self, node_idx, region_id, zone_id):
         idx = self._idx(node_idx); m = (len(idx),)

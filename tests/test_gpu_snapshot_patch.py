@@ -228,3 +228,56 @@ def test_patch_trimaran2(eng, engine_mod, oracle):
     assert not np.array_equal(before_peaks, want_peaks) and not np.array_equal(before_lr, want_lr)
     assert np.array_equal(got_peaks, oracle.peaks_batch(*[m(x, y) for x, y in zip(pa, pb)], a2["peaks_pod_cpu_milli"],
                                                         None, pitch=eng.Npad))
+
+
+def test_patch_nrt_overreserve_deduct(eng, engine_mod):
+    """OverReserve cache (cache/store.go:129-160): assumed pods are taken off every zone of their node on the device;
+    Filter + Score afterwards equal the oracle run on the NRT the reference's GetCachedNRTCopy would hand out."""
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+    from oracle import pyoracle_nrt
+
+    E = engine_mod
+    P, N, Z, seed = 32, 900, 4, synth.BASE_SEED + 66
+    nodes, pods = synth.gen_nrt(seed, N, P, Z=Z)
+    R = nodes["n_res"]
+    eng.snapshot_begin(N)
+    eng.snapshot_nrt(nodes)
+    eng.snapshot_commit()
+    eng.config_nrt(2, [1, 1, 1, 1])
+    eng.pods_upload(P, nrt=pods)
+    eng.eval(E.PLUGIN_NRT)
+    before = eng.fetch_reasons(E.PLUGIN_NRT)
+    g = np.random.default_rng(seed)
+    idx = np.sort(g.choice(N, size=120, replace=False)).astype(np.int32)
+    # 1..3 assumed pods per node; summed per resource for the engine, applied pod by pod for the oracle
+    target = dict(nodes)
+    target["avail"] = np.array(nodes["avail"], copy=True)
+    res_mask = np.zeros(len(idx), np.uint8)
+    deduct = np.zeros((R, len(idx)), np.int64)
+    for j, n in enumerate(idx):
+        a = np.ascontiguousarray(target["avail"][:, :, n])
+        zm = np.ascontiguousarray(nodes["zone_res_mask"][:, n])
+        for _ in range(int(g.integers(1, 4))):
+            m = int(g.integers(1, 16))
+            q = np.array([g.integers(0, 9) * 1000, g.integers(0, 17) << 30, g.integers(0, 3) << 29, g.integers(0, 5) * 1000],
+                         dtype=np.int64) * np.array([1, 1000, 1000, 1])
+            orc.lib().orc_nrt_overreserve_deduct(C.c_void_p(a.ctypes.data), C.c_void_p(zm.ctypes.data), C.c_int(Z),
+                                                 C.c_int(R), C.c_uint8(m), C.c_void_p(q.ctypes.data))
+            res_mask[j] |= m
+            for r in range(R):
+                if (m >> r) & 1:
+                    deduct[r, j] += q[r]
+        target["avail"][:, :, n] = a
+    eng.snapshot_patch_begin(2)
+    with pytest.raises(E.B200SError):  # a repeated node would race
+        eng.snapshot_patch_nrt_deduct([5, 5], [1, 1], np.zeros((R, 2), np.int64))
+    eng.snapshot_patch_nrt_deduct(idx, res_mask, deduct)
+    eng.snapshot_commit()
+    eng.eval(E.PLUGIN_NRT)
+    ws, wf, wr = pyoracle_nrt.nrt_batch(target, pods, 2, [1, 1, 1, 1], None, pitch=eng.Npad)
+    assert np.array_equal(eng.fetch_reasons(E.PLUGIN_NRT), wr)
+    assert np.array_equal(eng.fetch_feasible(E.PLUGIN_NRT), wf)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_NRT), ws)
+    assert (wr != before).any()  # the deduction turned fits into rejects

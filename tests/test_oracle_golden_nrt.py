@@ -90,3 +90,51 @@ def test_effective_request_and_predictors():
     assert eff["cpu"] == 4000 + 100 and eff["memory"] == (2 << 30) * 1000
     assert F.tlp_pod_cpu(pod) == 2000 + 750 + 100  # limit wins; request * 1.5 rounded; + overhead
     assert F.lvrb_pod_request(pod) == (4100, 2 << 30)
+
+
+# ------------------------------------------------------------------ OverReserve cache deduction (cache/store.go)
+def _deduct(avail, zmask, req_mask, req):
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+
+    a = np.ascontiguousarray(avail, dtype=np.int64).copy()
+    zm = np.ascontiguousarray(zmask, dtype=np.uint8)
+    rq = np.ascontiguousarray(req, dtype=np.int64)
+    Z, R = a.shape
+    orc.lib().orc_nrt_overreserve_deduct(C.c_void_p(a.ctypes.data), C.c_void_p(zm.ctypes.data), C.c_int(Z), C.c_int(R),
+                                         C.c_uint8(req_mask), C.c_void_p(rq.ctypes.data))
+    return a
+
+
+def test_overreserve_update_nrt_golden():
+    """store_test.go:457-567 TestResourceStoreUpdate: zones {cpu 20, memory 32Gi} and {cpu 20, memory 32Gi, nic 8};
+    the assumed pod's effective request is cpu 18, memory 6Gi, nic 2 -> cpu 2 / 2, memory 26Gi / 26Gi, nic 6."""
+    Gi = 1 << 30
+    avail = [[20_000, 32 * Gi * 1000, 0], [20_000, 32 * Gi * 1000, 8_000]]  # milli-units; slot 2 = the nic
+    got = _deduct(avail, [0b011, 0b111], 0b111, [18_000, 6 * Gi * 1000, 2_000])
+    assert got.tolist() == [[2_000, 26 * Gi * 1000, 0], [2_000, 26 * Gi * 1000, 6_000]]
+
+
+def test_overreserve_deduct_clamps_and_sums():
+    # "cannot decrement resource" zeroes the cell (:148-155); a resource the pod does not ask for is left alone
+    got = _deduct([[5, 7], [1, 7]], [0b11, 0b11], 0b01, [3, 99])
+    assert got.tolist() == [[2, 7], [0, 7]]
+    # pod-by-pod application (any order) == one deduction of the per-resource sum, for non-negative quantities:
+    # the identity b200s_snapshot_patch_nrt_deduct relies on
+    g = np.random.default_rng(5)
+    for _ in range(300):
+        Z, R, k = 3, 4, int(g.integers(1, 5))
+        avail = g.integers(0, 50, (Z, R))
+        zmask = g.integers(0, 16, Z).astype(np.uint8)
+        reqs = g.integers(0, 30, (k, R))
+        masks = g.integers(0, 16, k)
+        seq = avail.copy()
+        for j in g.permutation(k):
+            seq = _deduct(seq, zmask, int(masks[j]), reqs[j])
+        tot = np.zeros(R, dtype=np.int64)
+        for j in range(k):
+            for r in range(R):
+                if (masks[j] >> r) & 1:
+                    tot[r] += reqs[j][r]
+        assert np.array_equal(seq, _deduct(avail, zmask, int(np.bitwise_or.reduce(masks)), tot))
