@@ -1,0 +1,89 @@
+"""Extracts the `scopeEqualsContainerTests` table of the reference's NodeResourceTopologyMatch integration test
+(test/integration/noderesourcetopology_test.go:1742-2034, expanded by parseTestUserEntry :2158-2251) into
+tests/golden/nrt_integration.json.  Run in the build container (the reference tree is not on the GPU box):
+    python tests/golden/extract_nrt_integration.py
+Each entry: containers' resource maps (limits for Guaranteed pods -- the API server defaults requests to limits --
+or requests for Burstable ones), the expected node set (empty = unschedulable) and the failure message."""
+import json
+import os
+import re
+
+SRC = "/root/reference/test/integration/noderesourcetopology_test.go"
+NAMES = {"cpu": "cpu", "memory": "memory", "hugepages2Mi": "hugepages-2Mi", "nicResourceName": "vendor/nic1",
+         "ephemeralStorage": "ephemeral-storage"}
+
+
+def block(text, start):
+    """text[start] == '{' -> index one past the matching '}' (strings are skipped)."""
+    depth, i, in_str = 0, start, False
+    while i < len(text):
+        ch = text[i]
+        if in_str:
+            if ch == "\\":
+                i += 1
+            elif ch == '"':
+                in_str = False
+        elif ch == '"':
+            in_str = True
+        elif ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+    raise ValueError("unbalanced braces")
+
+
+def maps_of(entry, field):
+    m = re.search(field + r":\s*\[\]map\[string\]string\{", entry)
+    if not m:
+        return []
+    start = entry.index("{", m.end() - 1)
+    body = entry[start + 1:block(entry, start) - 1]
+    out = []
+    for mm in re.finditer(r"\{([^{}]*)\}", body):
+        out.append({NAMES[k]: v for k, v in re.findall(r"(\w+):\s*\"([^\"]*)\"", mm.group(1))})
+    return out
+
+
+def main():
+    text = open(SRC).read()
+    m = re.search(r"scopeEqualsContainerTests := \[\]nrtTestUserEntry\{", text)
+    start = text.index("{", m.end() - 1)
+    table = text[start + 1:block(text, start) - 1]
+    cases, i = [], 0
+    while True:
+        j = table.find("{", i)
+        if j < 0:
+            break
+        end = block(table, j)
+        entry = table[j:end]
+        i = end
+        desc = re.search(r"description:\s*\"((?:[^\"\\]|\\.)*)\"", entry).group(1)
+        err = re.search(r"errMsg:\s*\"([^\"]*)\"", entry)
+        exp = re.search(r"expectedNodes:\s*\[\]string\{([^}]*)\}", entry)
+        expected = re.findall(r"\"([^\"]+)\"", exp.group(1)) if exp else (["fake-node-1"] if not err else [])
+        cases.append(dict(name=desc, init=maps_of(entry, "initCntReq"), containers=maps_of(entry, "cntReq"),
+                          burstable=bool(re.search(r"isBurstable:\s*true", entry)), expected_nodes=expected,
+                          err_msg=err.group(1) if err else ""))
+    zone = lambda c, m_, h, n: {"cpu": c, "memory": m_, "hugepages-2Mi": h, "vendor/nic1": n}  # noqa: E731
+    doc = {
+        "source": "test/integration/noderesourcetopology_test.go:1742-2034 (scopeEqualsContainerTests) with the fixed "
+                  "NRT objects of parseTestUserEntry :2176-2228 and the node capacity of :215-222; profile: Filter + "
+                  "Score enabled, ScoringStrategy MostAllocated (:176-181)",
+        "node_capacity": {"cpu": "64", "memory": "128Gi", "pods": "32", "hugepages-2Mi": "896Mi", "vendor/nic1": "48",
+                          "ephemeral-storage": "32Gi"},
+        "attributes": {"topologyManagerPolicy": "single-numa-node", "topologyManagerScope": "container"},
+        "nrts": {"fake-node-1": [zone("30", "60Gi", "384Mi", "16"), zone("32", "64Gi", "512Mi", "32")],
+                 "fake-node-2": [zone("0", "0", "0", "0"), zone("0", "0", "0", "0")]},
+        "cases": cases,
+    }
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nrt_integration.json")
+    with open(out, "w") as f:
+        json.dump(doc, f, indent=1)
+    print(f"{len(cases)} cases -> {out}")
+
+
+if __name__ == "__main__":
+    main()

@@ -160,3 +160,59 @@ def test_low_risk_over_commitment_integration(H):
     p = H.LowRiskOverCommitment.new(args, fh)
     placed = schedule(H, fh, p, [pod("pod-3", 500, 1000)])
     assert placed[0][1] == "node-1" and placed[0][2] == {"node-1"}
+
+
+# ------------------------------------------------------------------ NodeResourceTopologyMatch, scope = container
+def _nrt_integration():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "nrt_integration.json")) as f:
+        return json.load(f)
+
+
+NRT_MSG = {"cannot align container", "cannot align init container", "cannot align sidecar container", "cannot align pod"}
+
+
+@pytest.mark.parametrize("case", _nrt_integration()["cases"], ids=lambda c: c["name"][:70])
+def test_topology_match_integration(H, case):
+    """test/integration/noderesourcetopology_test.go:1742-2251: Filter + Score (MostAllocated) on two nodes; the pod
+    must land on one of the expected nodes, or stay pending with the expected Filter message on every node.  Pods are
+    built from LIMITS for Guaranteed cases; the API server defaults requests to limits, restated here."""
+    from test_gpu_host_plugins import nrt_handle
+
+    g = _nrt_integration()
+    cap = {k: v for k, v in g["node_capacity"].items()}
+    nodes = []
+    for name, zones in g["nrts"].items():
+        nodes.append(dict(name=name, node_extra=cap, policies=[], attributes=g["attributes"],
+                          zones=[dict(name=f"node-{i}", resources={r: dict(capacity=q, available=q) for r, q in z.items()})
+                                 for i, z in enumerate(zones)]))
+    fh = nrt_handle(H, nodes)
+    args = H.NodeResourceTopologyMatchArgs()
+    args.scoring_strategy = "MostAllocated"
+    tm = H.TopologyMatch.new(args, fh)
+
+    def cont(m):
+        return {"requests": dict(m), "limits": {} if case["burstable"] else dict(m)}
+
+    pod = make_pod(H, {"init": [cont(m) for m in case["init"]], "containers": [cont(m) for m in case["containers"]]})
+    state = H.CycleState()
+    feasible, messages = [], []
+    for ni in fh.node_infos:
+        st = tm.filter(state, pod, ni)
+        if st.is_success():
+            feasible.append(ni)
+        else:
+            assert st.code == H.Code.Unschedulable
+            messages.append(st.message)
+    if not case["expected_nodes"]:
+        assert not feasible and any(m.startswith(case["err_msg"]) for m in messages), messages
+        return
+    assert feasible
+    scores = {ni.node.name: tm.score(state, pod, ni)[0] for ni in feasible}
+    best = max(scores.values())
+    winners = {n for n, s in scores.items() if s == best}
+    assert winners <= set(case["expected_nodes"]), (scores, case["expected_nodes"])
