@@ -216,3 +216,61 @@ def test_topology_match_integration(H, case):
     best = max(scores.values())
     winners = {n for n, s in scores.items() if s == best}
     assert winners <= set(case["expected_nodes"]), (scores, case["expected_nodes"])
+
+
+def _nrt_integration_full():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "nrt_integration_full.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _nrt_integration_full()["cases"], ids=lambda c: c["name"][:80])
+def test_topology_match_integration_full(H, case):
+    """test/integration/noderesourcetopology_test.go:239-1741: every scoring strategy (the pod's schedulerName picks
+    the profile), pod and container scope, TopologyPolicies and Attributes forms, zone costs for LeastNUMANodes, nodes
+    without an NRT object.  Expected: the node the pod lands on (any of the set), or nowhere."""
+    g = _nrt_integration_full()
+    cap = {k: str(v) for k, v in g["node_capacity"].items()}
+    nodes = [make_node(H, n, cap) for n in ("fake-node-1", "fake-node-2")]
+    fh = handle_with(H, nodes)
+    nrts = {}
+    for n in case["nrts"]:
+        t = H.NodeResourceTopology()
+        t.name = n["name"]
+        t.topology_policies = n["policies"]
+        t.attributes = n["attributes"]
+        zs = []
+        for z in n["zones"]:
+            zz = H.Zone()
+            zz.name, zz.type = z["name"], "Node"
+            zz.resources = {r: H.ZoneResource(H.parse_quantity(q["capacity"]), H.parse_quantity(q["available"]))
+                            for r, q in z["resources"].items()}
+            zz.costs = z["costs"]
+            zs.append(zz)
+        t.zones = zs
+        nrts[n["name"]] = t
+    fh.nrts = nrts
+    (spec,) = case["pods"]
+    args = H.NodeResourceTopologyMatchArgs()
+    args.scoring_strategy = spec["strategy"]
+    tm = H.TopologyMatch.new(args, fh)
+
+    def cont(c):  # the API server defaults a container's requests to its limits
+        req = dict(c["requests"]) or dict(c["limits"])
+        return {"requests": req, "limits": dict(c["limits"])}
+
+    pod = make_pod(H, {"init": [cont(c) for c in spec["init"]], "containers": [cont(c) for c in spec["containers"]]})
+    state = H.CycleState()
+    feasible = [ni for ni in fh.node_infos if tm.filter(state, pod, ni).is_success()]
+    if not case["expected_nodes"]:
+        assert not feasible
+        return
+    assert feasible
+    scores = {ni.node.name: tm.score(state, pod, ni)[0] for ni in feasible}
+    best = max(scores.values())
+    winners = {n for n, s in scores.items() if s == best}
+    assert winners <= set(case["expected_nodes"]), (scores, case["expected_nodes"])
