@@ -274,3 +274,49 @@ def test_topology_match_integration_full(H, case):
     best = max(scores.values())
     winners = {n for n, s in scores.items() if s == best}
     assert winners <= set(case["expected_nodes"]), (scores, case["expected_nodes"])
+
+
+def test_network_overhead_integration(H):
+    """test/integration/networkoverhead_test.go:140-306: AppGroup basic (p1 -> p2 -> p3), NetworkTopology nt-test, eight
+    labelled nodes; p1, p2, p3 are created in that order and each must be scheduled (the Go test accepts any node).
+    Replayed stronger: PreFilter / Filter / Score / NormalizeScore per pod with the pods placed so far in the lister;
+    every node passes Filter, and a pod whose dependency is already placed lands where the cost to it is lowest."""
+    from test_gpu_host_plugins import AG, SEL, netoh_fixture
+
+    def cycle(fh, no, sel, placed):
+        pod = make_pod(H, {"containers": [{"requests": {"memory": "50"}}]}, name=f"{sel}-test-1", labels={AG: "basic", SEL: sel})
+        state = H.CycleState()
+        assert no.pre_filter(state, pod, fh.node_infos).is_success()
+        feasible = [ni for ni in fh.node_infos if no.filter(state, pod, ni).is_success()]
+        assert feasible
+        scores = []
+        for ni in feasible:
+            s, st = no.score(state, pod, ni)
+            assert st.is_success()
+            scores.append(H.NodeScore(ni.node.name, s))
+        st, scores = no.normalize_score(state, pod, scores)
+        assert st.is_success()
+        best = max(x.score for x in scores)
+        winners = sorted(x.name for x in scores if x.score == best)
+        pod.node_name = winners[0]
+        placed.append(pod)
+        fh.pods = placed
+        fh.touch()
+        return len(feasible), winners
+
+    # the Go test's order: no pod ever finds one of its dependencies placed -> every node passes and ties
+    fh, no = netoh_fixture(H, [])
+    placed = []
+    for sel in ("p1", "p2", "p3"):
+        assert cycle(fh, no, sel, placed) == (8, [f"n-{i}" for i in range(1, 9)])
+    assert len(placed) == 3
+    # dependency-first order (what the AppGroup's topology order exists for): the dependent pod follows its dependency
+    fh, no = netoh_fixture(H, [])
+    placed, hosts = [], {}
+    for sel in ("p3", "p2", "p1"):
+        n_feasible, winners = cycle(fh, no, sel, placed)
+        hosts[sel] = winners[0]
+        if sel == "p3":
+            assert n_feasible == 8 and len(winners) == 8
+        else:
+            assert winners == [hosts["p3" if sel == "p2" else "p2"]], (sel, winners)  # same node: cost 0
