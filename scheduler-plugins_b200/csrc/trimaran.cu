@@ -118,14 +118,15 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
     for (int j = 0; j < NPT; ++j) {
       double predicted = 0;
       if (ncap[j] != 0) predicted = div_inv(100 * (base[j] + pc + miss[j]), ncap[j], rcap[j]);  // :170-173
-      double s;
-      if (predicted > t) {
-        const double num = t * (100 - predicted);
-        s = predicted > 100 ? 0.0 : go_round(fast_t ? div_inv(num, hundred_minus_t, r_hmt) : num / hundred_minus_t);  // :174-181
-      } else {
-        const double num = hundred_minus_t * predicted;
-        s = go_round((fast_t ? div_inv(num, t, r_t) : num / t) + t);  // :183-184
-      }
+      // both branches of :174-184 are a division by a launch invariant followed by math.Round: evaluate them as ONE
+      // straight-line chain with the operands selected (same operations on the same values, no divergent paths)
+      const bool over = predicted > t;
+      const double num = over ? t * (100 - predicted) : hundred_minus_t * predicted;
+      const double d = over ? hundred_minus_t : t, r = over ? r_hmt : r_t;
+      double quo = fast_t ? div_inv(num, d, r) : num / d;
+      quo = over ? quo : quo + t;                       // :183
+      double s = go_round(quo);
+      s = (over && predicted > 100) ? 0.0 : s;          // :175-177
       q[j] = ((ok >> j) & 1u) ? go_f2i(s) : 0;
     }
     Store<OutT, NPT>::put64(orow, q);
