@@ -9,7 +9,8 @@
 //            least_numa.go:35-233, subtractFromNUMAs numaresources.go:184-215
 // The reference re-parses zone names and deep-copies every Quantity map per (pod,node) call; here
 // a node's zones x resources block (exact milli-units) is loaded ONCE into registers and reused
-// for the whole pod tile.  One thread owns one node; a warp's ballot is half a feasibility word.
+// for the whole pod tile.  One thread owns one node (through the class/capacity-sorted permutation); the
+// feasibility words are rebuilt from the reason codes by nrt_feas_kernel.
 // Kernels are instantiated for the common shapes (<=2 zones x <=4 resources, <=4 x <=4, <=8 x <=8)
 // so the zone/resource loops unroll and the working copy used by the container-scope state
 // machine stays in registers.
