@@ -166,6 +166,15 @@ __device__ __forceinline__ double lvrb_res_score(const LvrbNode& nd, double req)
   double risk = (mu + nd.sigma) / 2;
   return (1. - risk) * 100.0;
 }
+// Same, for a node whose avg / sigma / capacity are finite (checked once per node): mu cannot be NaN, so the
+// NaN-propagating clamps of Go's builtin min/max reduce to the hardware min/max.
+__device__ __forceinline__ double lvrb_res_score_finite(const LvrbNode& nd, double req) {
+  const double mu = fmax(fmin(div_inv(nd.avg + req, nd.cap, nd.rcap), 1.0), 0.0);
+  return (1. - (mu + nd.sigma) / 2) * 100.0;
+}
+__device__ __forceinline__ bool lvrb_finite(const LvrbNode& nd) {
+  return nd.cap > 0 && nd.cap < CUDART_INF && nd.avg == nd.avg && nd.sigma == nd.sigma;
+}
 
 template <class OutT, int NPT, int PT>
 __global__ void __launch_bounds__(256)
@@ -184,6 +193,7 @@ lvrb_kernel(const double* __restrict__ f64, const int64_t* __restrict__ i64, con
     }
   LvrbNode cpu[NPT], mem[NPT];
   uint32_t fl[NPT];
+  bool plain = true;  // every resource this thread scores is finite: the straight-line form applies
   if (nb < Npad) {
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
@@ -193,12 +203,30 @@ lvrb_kernel(const double* __restrict__ f64, const int64_t* __restrict__ i64, con
       mcap *= MEGA;  // resourcestats.go:62-63
       mem[j] = lvrb_node(f64[2 * (size_t)Npad + n], f64[3 * (size_t)Npad + n], mcap, margin, sens);
       fl[j] = n < N ? flags[n] : 0;
+      if ((fl[j] & B200S_LVRB_CPU_OK) && !lvrb_finite(cpu[j])) plain = false;
+      if ((fl[j] & B200S_LVRB_MEM_OK) && !lvrb_finite(mem[j])) plain = false;
     }
   }
   __syncthreads();
   if (nb >= Npad) return;
   const int pend = min(PT, P - p0);
   OutT* orow = out + (size_t)p0 * Npad + nb;
+  if (plain) {
+    for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+      const double rc = s_cpu[pp], rm = s_mem[pp];
+      int64_t q[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        const bool cpu_ok = fl[j] & B200S_LVRB_CPU_OK, mem_ok = fl[j] & B200S_LVRB_MEM_OK;
+        const double cs = cpu_ok ? lvrb_res_score_finite(cpu[j], rc) : 0.0;
+        const double ms = mem_ok ? lvrb_res_score_finite(mem[j], rm) : 0.0;
+        const double total = (mem_ok && cpu_ok) ? fmin(ms, cs) : fmax(ms, cs);  // :113-118, no NaN possible here
+        q[j] = (fl[j] & B200S_LVRB_HAS_METRICS) ? go_f2i(go_round(total)) : 0;
+      }
+      Store<OutT, NPT>::put64(orow, q);
+    }
+    return;
+  }
   for (int pp = 0; pp < pend; ++pp, orow += Npad) {
     const double rc = s_cpu[pp], rm = s_mem[pp];
     int64_t q[NPT];
