@@ -367,6 +367,9 @@ __global__ void lowrisk_node_kernel(const double* __restrict__ f, const int64_t*
 }
 
 // computeRisk minus the node-only half: riskLimit + the weighted sum (:200-206, :251-254)
+// FINITE: load and w are not NaN (checked once per thread), so no NaN can arise and Go's NaN-propagating min/max
+// are the hardware ones
+template <bool FINITE>
 __device__ __forceinline__ double total_risk(int64_t cap, int64_t node_req, int64_t node_lim, int64_t pod_req,
                                              int64_t pod_lim, double load, double w) {
   int64_t request = wrap_add(node_req, pod_req);
@@ -375,6 +378,7 @@ __device__ __forceinline__ double total_risk(int64_t cap, int64_t node_req, int6
   double risk_limit = 0;
   if (limit > cap) risk_limit = (double)wrap_sub(limit, cap) / (double)wrap_sub(limit, request);
   const double total = w * risk_limit + (1 - w) * load;
+  if (FINITE) return fmin(fmax(total, 0.0), 1.0);
   return go_min(go_max(total, 0), 1);
 }
 
@@ -410,6 +414,9 @@ lowrisk_kernel(const int64_t* __restrict__ iv, const uint8_t* __restrict__ flags
   if (nb >= Npad) return;
   const int pend = min(PT, P - p0);
   OutT* orow = out + (size_t)p0 * Npad + nb;
+  bool plain = w_cpu == w_cpu && w_mem == w_mem;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) plain = plain && load_c[j] == load_c[j] && load_m[j] == load_m[j];
   for (int pp = 0; pp < pend; ++pp, orow += Npad) {
     const int64_t pr_c = s_pod[pp][0], pr_m = s_pod[pp][1], pl_c = s_pod[pp][2], pl_m = s_pod[pp][3];
     const bool best_effort = pr_c == 0 && pr_m == 0 && pl_c == 0 && pl_m == 0;  // :122-127
@@ -418,9 +425,17 @@ lowrisk_kernel(const int64_t* __restrict__ iv, const uint8_t* __restrict__ flags
     for (int j = 0; j < NPT; ++j) {
       int64_t s = 0;
       if (!best_effort && ((ok >> j) & 1u)) {
-        const double rc = total_risk(cap_c[j], req_c[j], lim_c[j], pr_c, pl_c, load_c[j], w_cpu);
-        const double rm = total_risk(cap_m[j], req_m[j], lim_m[j], pr_m, pl_m, load_m[j], w_mem);
-        const double rank = 1 - go_max(rc, rm);   // computeRank :163
+        double rc, rm, worst;
+        if (plain) {
+          rc = total_risk<true>(cap_c[j], req_c[j], lim_c[j], pr_c, pl_c, load_c[j], w_cpu);
+          rm = total_risk<true>(cap_m[j], req_m[j], lim_m[j], pr_m, pl_m, load_m[j], w_mem);
+          worst = fmax(rc, rm);
+        } else {
+          rc = total_risk<false>(cap_c[j], req_c[j], lim_c[j], pr_c, pl_c, load_c[j], w_cpu);
+          rm = total_risk<false>(cap_m[j], req_m[j], lim_m[j], pr_m, pl_m, load_m[j], w_mem);
+          worst = go_max(rc, rm);
+        }
+        const double rank = 1 - worst;   // computeRank :163
         s = go_f2i(go_round(rank * 100.0));       // :138-139
       }
       q[j] = s;
