@@ -18,6 +18,22 @@ PYBIND11_MODULE(_b200host, m) {
   m.doc() = "C++ mirror of the scheduler-plugins hot-path plugins over libb200sched.so";
   m.def("parse_quantity", &ParseQuantity);
   m.def("resource_list", &ToRL, "Kubernetes quantity strings -> milli-unit ResourceList");
+  m.def("get_resource_requested", [](const Pod& p) {
+    int64_t c, mm;
+    GetResourceRequested(p, &c, &mm);
+    return std::make_pair(c, mm);
+  });
+  m.def("get_resource_limits", [](const Pod& p) {
+    int64_t c, mm;
+    GetResourceLimits(p, &c, &mm);
+    return std::make_pair(c, mm);
+  });
+  m.def("get_resource_request_quantity_cpu", &GetResourceRequestQuantityCPU);
+  m.def("node_requests_and_limits_of_running_pods", [](const NodeInfo& ni) {
+    int64_t o[4];
+    NodeRequestsAndLimitsOfRunningPods(ni, o);
+    return std::vector<int64_t>(o, o + 4);
+  });
   m.def("pod_qos", [](const Pod& p) { return (int)GetPodQOS(p); });
   m.def("pod_effective_request", &GetPodEffectiveRequest);
   m.def("pod_predicted_cpu", &PodPredictedCPU);

@@ -196,6 +196,18 @@ static void EffectiveResource(const Pod& p, bool limits, int64_t* cpu_milli, int
 void GetResourceRequested(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) { EffectiveResource(p, false, cpu_milli, mem_bytes); }
 void GetResourceLimits(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes) { EffectiveResource(p, true, cpu_milli, mem_bytes); }
 
+void NodeRequestsAndLimitsOfRunningPods(const NodeInfo& ni, int64_t out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (auto& p : ni.pods) {
+    if (!p) continue;
+    int64_t qc, qm, xc, xm;
+    GetResourceRequested(*p, &qc, &qm);
+    GetResourceLimits(*p, &xc, &xm);
+    xc = std::max(xc, qc), xm = std::max(xm, qm);  // SetMaxLimits :230-246
+    out[0] += qc, out[1] += qm, out[2] += xc, out[3] += xm;
+  }
+}
+
 int64_t GetResourceRequestQuantityCPU(const Pod& p) {
   int64_t total = 0;
   for (auto& c : p.containers) {

@@ -156,6 +156,10 @@ void GetResourceLimits(const Pod& p, int64_t* cpu_milli, int64_t* mem_bytes);   
 // sum of the app containers' requests, raised to the largest init container request, plus the pod overhead when
 // the total is non-zero (peaks.go:113-114)
 int64_t GetResourceRequestQuantityCPU(const Pod& p);
+// GetNodeRequestsAndLimits (resourcestats.go:160-228) WITHOUT the pending pod and before the capacity cap: requests
+// and limits summed over the pods already on the node, each pod's limits raised to its requests (SetMaxLimits).
+// out = {request cpu milli, request memory bytes, limit cpu milli, limit memory bytes}
+void NodeRequestsAndLimitsOfRunningPods(const NodeInfo& ni, int64_t out[4]);
 // GetResourceData: resourcestats.go:89-107
 void GetResourceData(const std::vector<Metric>& m, const std::string& type, double* avg, double* std_, bool* valid);
 

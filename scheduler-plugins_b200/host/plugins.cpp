@@ -577,13 +577,10 @@ void LowRiskOverCommitment::EnsureSnapshot() {
     if (!nd) continue;
     acpu[i] = Get(nd->allocatable, ResourceCPU);                    // resourcestats.go:170-175
     amem[i] = QuantityValue(Get(nd->allocatable, ResourceMemory));
-    for (auto& p : nodes[i].pods) {  // GetNodeRequestsAndLimits :181-206 without the pending pod
-      if (!p) continue;
-      int64_t qc, qm, xc, xm;
-      GetResourceRequested(*p, &qc, &qm);
-      GetResourceLimits(*p, &xc, &xm);
-      xc = std::max(xc, qc), xm = std::max(xm, qm);  // SetMaxLimits :230-246
-      rc[i] += qc, rm[i] += qm, lc[i] += xc, lm[i] += xm;
+    {  // GetNodeRequestsAndLimits :181-206 without the pending pod
+      int64_t sums[4];
+      NodeRequestsAndLimitsOfRunningPods(nodes[i], sums);
+      rc[i] = sums[0], rm[i] = sums[1], lc[i] = sums[2], lm[i] = sums[3];
     }
     if (!wm || !wm->has_map) continue;
     auto it = wm->node_metrics.find(nd->name);

@@ -98,3 +98,66 @@ def test_handle_node_change_log(H):
     h.generation = h.generation + 1                  # moved without a log entry
     assert h.nodes_changed_since(g1) is None
     assert h.nodes_changed_since(h.generation + 5) is None
+
+
+# ------------------------------------------------------------------ pkg/trimaran/resourcestats_test.go on the C++ host
+def _pod_rs(init_req, cont_req, init_lim=None, cont_lim=None, overhead_cpu=0):
+    """getPodWithContainersAndOverhead + getPodWithLimits (resourcestats_test.go:605-648): one init container, app
+    containers whose limits default to their requests."""
+    def c(req, lim):
+        return {"requests": {"cpu": f"{req[0]}m", "memory": str(req[1])}, "limits": {"cpu": f"{lim[0]}m", "memory": str(lim[1])}}
+
+    cont_lim = cont_lim or cont_req
+    spec = {"init": [{"requests": {"cpu": f"{init_req[0]}m", "memory": str(init_req[1])},
+                      "limits": {} if init_lim is None else {"cpu": f"{init_lim[0]}m", "memory": str(init_lim[1])}}],
+            "containers": [c(r, l) for r, l in zip(cont_req, cont_lim)], "overhead": {"cpu": f"{overhead_cpu}m"}}
+    return spec
+
+
+def test_get_resource_requested_and_limits_reference_vectors(H):
+    """TestGetResourceRequested / TestGetResourceLimits (resourcestats_test.go:163-257) shapes: sum of the app
+    containers, raised to the largest init container, plus the overhead; memory through Quantity.Value()."""
+    pod = mkpod(H, _pod_rs((100, 2048), [(1000, 512), (500, 1024)], (500, 2048), [(1500, 1024), (500, 1024)]))
+    assert H.get_resource_requested(pod) == (1500, 2048)   # max(1000 + 500, 100), max(512 + 1024, 2048)
+    assert H.get_resource_limits(pod) == (2000, 2048)      # max(1500 + 500, 500), max(1024 + 1024, 2048)
+    with_overhead = mkpod(H, _pod_rs((100, 2048), [(1000, 512), (500, 1024)], overhead_cpu=250))
+    assert H.get_resource_requested(with_overhead) == (1750, 2048)
+    assert H.get_resource_request_quantity_cpu(with_overhead) == 1750   # peaks.go:113: same here (non-zero total)
+    init_heavy = mkpod(H, _pod_rs((4000, 100), [(1000, 512)]))
+    assert H.get_resource_requested(init_heavy) == (4000, 512) and H.get_resource_request_quantity_cpu(init_heavy) == 4000
+
+
+def test_get_node_requests_and_limits_reference_vectors(H):
+    """TestGetNodeRequestsAndLimits (resourcestats_test.go:374-603).  The host flattens NodeRequestMinusPod /
+    NodeLimitMinusPod (sums over the running pods, limits raised to requests); the pending pod and the capacity cap
+    enter on the device -- restated here to reach the reference's five expected Resources."""
+    init_req, cont_req = (100, 2048), [(1000, 512), (500, 1024)]
+    mk = lambda lim: mkpod(H, _pod_rs(init_req, cont_req, (500, 2048), lim))  # noqa: E731
+    pod, pod3, pod4 = mk([(1500, 1024), (500, 1024)]), mk([(1000, 1024), (1000, 2048)]), mk([(1000, 1024), (400, 1024)])
+
+    def node_info(pods):
+        n = H.Node()
+        n.name = "test-node"
+        ni = H.NodeInfo(n)
+        ni.pods = pods
+        return ni
+
+    def expect(pods, pending, cap):
+        rc, rm, lc, lm = H.node_requests_and_limits_of_running_pods(node_info(pods))
+        pr, pl = list(H.get_resource_requested(pending)), list(H.get_resource_limits(pending))
+        pl = [max(a, b) for a, b in zip(pl, pr)]  # SetMaxLimits on the pending pod (:592)
+        return dict(NodeRequest=(min(rc + pr[0], cap[0]), min(rm + pr[1], cap[1])), NodeLimit=(lc + pl[0], lm + pl[1]),
+                    NodeRequestMinusPod=(min(rc, cap[0]), min(rm, cap[1])), NodeLimitMinusPod=(lc, lm))
+
+    big, low = (8000, 6 * 1024), (1600, 6 * 1024)
+    assert expect([mk([(1500, 1024), (500, 1024)])] * 2, pod, big) == dict(
+        NodeRequest=(3 * 1500, 3 * 2048), NodeLimit=(3 * 2000, 3 * 2048), NodeRequestMinusPod=(2 * 1500, 2 * 2048),
+        NodeLimitMinusPod=(2 * 2000, 2 * 2048))                                                    # test-0
+    assert expect([pod3], pod, big) == dict(
+        NodeRequest=(2 * 1500, 2 * 2048), NodeLimit=(2 * 2000, 2 * 2048 + 1024), NodeRequestMinusPod=(1500, 2048),
+        NodeLimitMinusPod=(2000, 2048 + 1024))                                                     # test-1
+    assert expect([], pod, low) == dict(NodeRequest=(1500, 2048), NodeLimit=(2000, 2048), NodeRequestMinusPod=(0, 0),
+                                        NodeLimitMinusPod=(0, 0))                                  # test-2
+    got = expect([], pod4, low)                                                                    # test-3
+    assert got["NodeRequest"] == (1500, 2048) and got["NodeLimit"] == (1500, 2048)  # limits 1400 raised to requests
+    assert got["NodeRequest"][0] <= got["NodeLimit"][0] and got["NodeRequest"][1] <= got["NodeLimit"][1]
