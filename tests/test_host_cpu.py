@@ -161,3 +161,30 @@ def test_get_node_requests_and_limits_reference_vectors(H):
     got = expect([], pod4, low)                                                                    # test-3
     assert got["NodeRequest"] == (1500, 2048) and got["NodeLimit"] == (1500, 2048)  # limits 1400 raised to requests
     assert got["NodeRequest"][0] <= got["NodeLimit"][0] and got["NodeRequest"][1] <= got["NodeLimit"][1]
+
+
+# ------------------------------------------------------------------ pkg/util/resource_test.go on both restatements
+EFFECTIVE_REQUEST_CASES = [  # (containers, init containers, overhead, want) in (cpu milli, memory bytes)
+    ("1 container", [(1, 1)], [], None, (1, 1)),
+    ("2 containers", [(1, 1), (2, 3)], [], None, (3, 4)),
+    ("2 containers and 1 init container", [(1, 1), (2, 3)], [(1, 1)], None, (3, 4)),
+    ("2 containers and 1 init container with large cpu", [(1, 1), (2, 3)], [(10, 1)], None, (10, 4)),
+    ("2 containers and 2 init containers with large cpu or mem", [(1, 1), (2, 3)], [(10, 1), (1, 10)], None, (10, 10)),
+    ("2 containers and 2 init containers with only large cpu", [(1, 1), (2, 3)], [(10, 1), (1, 1)], None, (10, 4)),
+    ("1 container with pod overhead", [(1, 1)], [], (1, 1), (2, 2)),
+    ("2 containers and 1 init container with pod overhead", [(1, 1), (2, 3)], [(1, 1)], (1, 1), (4, 5)),
+]
+
+
+@pytest.mark.parametrize("case", EFFECTIVE_REQUEST_CASES, ids=lambda c: c[0])
+def test_get_pod_effective_request_reference_vectors(H, case):
+    """TestGetPodEffectiveRequest (pkg/util/resource_test.go:34-150; makeResourceList(cpu milli, memory bytes) :25-32):
+    the NRT plugin's pod-scope request -- on the C++ host and on the Python flatten rules the oracle tests use."""
+    _, conts, inits, overhead, want = case
+    rl = lambda c: {"cpu": f"{c[0]}m", "memory": str(c[1])}  # noqa: E731
+    spec = {"containers": [{"requests": rl(c)} for c in conts], "init": [{"requests": rl(c)} for c in inits]}
+    if overhead:
+        spec["overhead"] = rl(overhead)
+    expected = {"cpu": want[0], "memory": want[1] * 1000}  # milli-units
+    assert dict(H.pod_effective_request(mkpod(H, spec))) == expected
+    assert F.pod_effective_request(spec) == expected
