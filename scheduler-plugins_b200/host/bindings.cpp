@@ -18,6 +18,8 @@ PYBIND11_MODULE(_b200host, m) {
   m.doc() = "C++ mirror of the scheduler-plugins hot-path plugins over libb200sched.so";
   m.def("parse_quantity", &ParseQuantity);
   m.def("resource_list", &ToRL, "Kubernetes quantity strings -> milli-unit ResourceList");
+  m.def("is_host_level_resource", &IsHostLevelResource);
+  m.def("is_numa_affine_resource", &IsNUMAAffineResource);
   m.def("get_resource_requested", [](const Pod& p) {
     int64_t c, mm;
     GetResourceRequested(p, &c, &mm);

@@ -188,3 +188,14 @@ def test_get_pod_effective_request_reference_vectors(H, case):
     expected = {"cpu": want[0], "memory": want[1] * 1000}  # milli-units
     assert dict(H.pod_effective_request(mkpod(H, spec))) == expected
     assert F.pod_effective_request(spec) == expected
+
+
+@pytest.mark.parametrize("name,host_level,affine", [
+    ("cpu", False, True), ("memory", False, True), ("hugepages-1Gi", False, True), ("storage", True, False),
+    ("ephemeral-storage", True, False), ("vendor.io/fastest-nic", True, False), ("awesome.com/gpu-for-ai", True, False),
+])
+def test_resource_classes_reference_vectors(H, name, host_level, affine):
+    """TestIsHostLevelResource / TestIsNUMAAffineResource (numaresources_test.go:29-115): the two bits the host puts into
+    the NRT snapshot's res_flags -- on the C++ host and in the Python flatten rules."""
+    assert H.is_host_level_resource(name) is host_level and F.is_host_level(name) is host_level
+    assert H.is_numa_affine_resource(name) is affine and F.is_numa_affine(name) is affine
