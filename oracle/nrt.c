@@ -425,3 +425,33 @@ void orc_nrt_overreserve_deduct(int64_t* avail, const uint8_t* zmask, int Z, int
       *a -= req[r];                            /* :157 */
     }
 }
+
+/* Test entry points for the two subtraction helpers, so that their reference vectors
+ * (numaresources_test.go:117-373 and :375-462) pin them directly and not only through Filter / Score.
+ * avail [Z][R_MAX-wide rows of R used], zmask[z] bit r = zone lists r. */
+int orc_nrt_subtract_from_numa_list(int64_t* avail, const uint8_t* zmask, int Z, int R, const uint8_t* res_flags, int numa_id,
+                                    int qos, uint8_t req_mask, const int64_t* req) {
+  zones_t zs;
+  zs.nz = Z;
+  for (int z = 0; z < Z; ++z) {
+    zs.zmask[z] = zmask[z];
+    for (int r = 0; r < R; ++r) zs.avail[z][r] = avail[z * R + r];
+  }
+  const int ok = subtract_from_numa(&zs, res_flags, R, numa_id, qos, req_mask, req);
+  for (int z = 0; z < Z; ++z)
+    for (int r = 0; r < R; ++r) avail[z * R + r] = zs.avail[z][r];
+  return ok;
+}
+
+void orc_nrt_subtract_from_numas(int64_t* avail, const uint8_t* zmask, int Z, int R, uint32_t zone_mask, uint8_t req_mask,
+                                 const int64_t* req) {
+  zones_t zs;
+  zs.nz = Z;
+  for (int z = 0; z < Z; ++z) {
+    zs.zmask[z] = zmask[z];
+    for (int r = 0; r < R; ++r) zs.avail[z][r] = avail[z * R + r];
+  }
+  subtract_from_numas(&zs, req_mask, req, zone_mask, R);
+  for (int z = 0; z < Z; ++z)
+    for (int r = 0; r < R; ++r) avail[z * R + r] = zs.avail[z][r];
+}

@@ -65,6 +65,11 @@ void orc_lvrb_batch(const double* cpu_avg, const double* cpu_std, const double* 
                     const int64_t* req_cpu, const int64_t* req_mem, int P, double margin, double sens,
                     int64_t* out, int pitch);
 
+/* test entry points of the two NUMA subtraction helpers (numaresources.go:145-182, :184-215) */
+int orc_nrt_subtract_from_numa_list(int64_t* avail, const uint8_t* zmask, int Z, int R, const uint8_t* res_flags, int numa_id,
+                                    int qos, uint8_t req_mask, const int64_t* req);
+void orc_nrt_subtract_from_numas(int64_t* avail, const uint8_t* zmask, int Z, int R, uint32_t zone_mask, uint8_t req_mask,
+                                 const int64_t* req);
 /* OverReserve cache deduction of one assumed pod (cache/store.go:129-160); see nrt.c */
 void orc_nrt_overreserve_deduct(int64_t* avail, const uint8_t* zmask, int Z, int R, uint8_t req_mask, const int64_t* req);
 

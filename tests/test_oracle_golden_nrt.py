@@ -138,3 +138,76 @@ def test_overreserve_deduct_clamps_and_sums():
                 if (masks[j] >> r) & 1:
                     tot[r] += reqs[j][r]
         assert np.array_equal(seq, _deduct(avail, zmask, int(np.bitwise_or.reduce(masks)), tot))
+
+
+# ------------------------------------------------------------------ numaresources_test.go subtraction helpers
+Gi = 1 << 30
+AFFINE, HOST_LEVEL = 1, 2
+QOS_GU, QOS_BU = 0, 1
+
+
+def _sub_list(avail, zmask, res_flags, numa_id, qos, req_mask, req):
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+
+    a = np.ascontiguousarray(avail, dtype=np.int64).copy()
+    Z, R = a.shape
+    zm = np.ascontiguousarray(zmask, dtype=np.uint8)
+    rf = np.ascontiguousarray(res_flags, dtype=np.uint8)
+    rq = np.ascontiguousarray(req, dtype=np.int64)
+    ok = orc.lib().orc_nrt_subtract_from_numa_list(C.c_void_p(a.ctypes.data), C.c_void_p(zm.ctypes.data), C.c_int(Z), C.c_int(R),
+                                                   C.c_void_p(rf.ctypes.data), C.c_int(numa_id), C.c_int(qos),
+                                                   C.c_uint8(req_mask), C.c_void_p(rq.ctypes.data))
+    return bool(ok), a.tolist()
+
+
+SUBTRACT_LIST_CASES = [
+    # slots: 0 cpu (affine), 1 memory (affine), 2 device / hugepages, 3 ephemeral-storage (host level); milli-units
+    ("empty from empty", [[0, 0, 0, 0]], [0b0000], 0, QOS_GU, 0, [0, 0, 0, 0], True, [[0, 0, 0, 0]]),
+    ("inconsistent numaID", [[0, 0, 0, 0]], [0b0000], 2, QOS_GU, 0, [0, 0, 0, 0], True, [[0, 0, 0, 0]]),
+    ("empty from minimal", [[2000, 4 * Gi * 1000, 0, 0]], [0b0011], 0, QOS_GU, 0, [0, 0, 0, 0], True, [[2000, 4 * Gi * 1000, 0, 0]]),
+    ("remove core resources (GU qos)", [[8000, 16 * Gi * 1000, 0, 0]], [0b0011], 0, QOS_GU, 0b0011, [2000, 4 * Gi * 1000, 0, 0],
+     True, [[6000, 12 * Gi * 1000, 0, 0]]),
+    ("remove only devices resources (BU qos)", [[8000, 16 * Gi * 1000, 4000, 0]], [0b0111], 0, QOS_BU, 0b0111,
+     [2000, 4 * Gi * 1000, 2000, 0], True, [[8000, 16 * Gi * 1000, 2000, 0]]),
+    ("skip hostlevel resources (GU qos)", [[8000, 16 * Gi * 1000, 4000, 0]], [0b0111], 0, QOS_GU, 0b1111,
+     [6000, 12 * Gi * 1000, 2000, 1 * Gi * 1000], True, [[2000, 4 * Gi * 1000, 2000, 0]]),
+    ("remove excessive core resources (GU qos)", [[8000, 16 * Gi * 1000, 0, 0]], [0b0011], 0, QOS_GU, 0b0011,
+     [10000, 20 * Gi * 1000, 0, 0], False, None),
+    ("require missing resources (GU qos, device)", [[8000, 16 * Gi * 1000, 0, 0]], [0b0011], 0, QOS_GU, 0b0111,
+     [4000, 8 * Gi * 1000, 2000, 0], True, [[4000, 8 * Gi * 1000, 0, 0]]),
+    ("require missing resources (GU qos, core)", [[8000, 16 * Gi * 1000, 0, 0]], [0b0011], 0, QOS_GU, 0b0111,
+     [4000, 8 * Gi * 1000, 2 * Gi * 1000, 0], True, [[4000, 8 * Gi * 1000, 0, 0]]),
+]
+
+
+@pytest.mark.parametrize("case", SUBTRACT_LIST_CASES, ids=lambda c: c[0])
+def test_subtract_resources_from_numa_node_list_vectors(case):
+    """TestSubtractResourcesFromNUMANodeList (numaresources_test.go:117-373).  In 'remove only devices (BU qos)' the
+    device is slot 2 WITHOUT the affine bit; in 'require missing (core)' slot 2 is hugepages-1Gi (affine, not listed)."""
+    name, avail, zmask, numa_id, qos, req_mask, req, want_ok, want = case
+    flags = [AFFINE, AFFINE, AFFINE if "core)" in name else 0, HOST_LEVEL]
+    ok, got = _sub_list(avail, zmask, flags, numa_id, qos, req_mask, req)
+    assert ok is want_ok
+    if want_ok:
+        assert got == want
+
+
+def test_subtract_from_numas_vectors():
+    """TestSubstractNUMA (numaresources_test.go:375-462): LeastNUMANodes takes the request zone by zone."""
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+
+    def run(avail, zones, req):
+        a = np.ascontiguousarray(avail, dtype=np.int64).copy()
+        zm = np.full(a.shape[0], 0b11, dtype=np.uint8)
+        rq = np.ascontiguousarray(req, dtype=np.int64)
+        mask = sum(1 << z for z in zones)
+        orc.lib().orc_nrt_subtract_from_numas(C.c_void_p(a.ctypes.data), C.c_void_p(zm.ctypes.data), C.c_int(a.shape[0]),
+                                              C.c_int(2), C.c_uint32(mask), C.c_uint8(0b11), C.c_void_p(rq.ctypes.data))
+        return a.tolist()
+
+    assert run([[8000, 10 * Gi * 1000]], [0], [2000, 2 * Gi * 1000]) == [[6000, 8 * Gi * 1000]]                      # simple
+    assert run([[8000, 10 * Gi * 1000]] * 2, [0, 1], [12000, 2 * Gi * 1000]) == [[0, 8 * Gi * 1000], [4000, 10 * Gi * 1000]]
