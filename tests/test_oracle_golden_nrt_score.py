@@ -54,3 +54,33 @@ def test_least_numa_scores(oracle, case):
     # (no filter handler) so every node is scored
     assert not reasons[:len(nodes)].any()
     assert got == case["want"]
+
+
+PARTIAL = [  # TestNodeResourcePartialDataScorePlugin, score_test.go:483-600: (strategy, nodes that keep an NRT, wanted)
+    ("MostAllocated", (), {}), ("LeastAllocated", (), {}), ("BalancedAllocation", (), {}),
+    ("MostAllocated", ("Node1",), {"Node1": 27}), ("LeastAllocated", ("Node1",), {"Node1": 73}),
+    ("BalancedAllocation", ("Node1",), {"Node1": 89}),
+]
+
+
+@pytest.mark.parametrize("strategy,keep,want", PARTIAL, ids=lambda v: str(v))
+def test_partial_nrt_data_scores(oracle, strategy, keep, want):
+    """Nodes whose NRT object is missing score 0 (score.go:83-86); the node that has one is elected with the expected
+    score.  Fixture and pod: defaultNUMANodes + Pod1 of score_test.go (cpu 2, memory 20 MiB, Guaranteed)."""
+    from oracle import pyoracle_nrt
+
+    s = load()["suites"][0]
+    fixture = with_policy(s["nodes"], s["policy_override"])
+    pod = s["cases"][0]["pod"]
+    nodes, nrts = node_objects({"nodes": fixture})
+    nrts = [t if n["name"] in keep else None for n, t in zip(fixture, nrts)]
+    names = F.build_dictionary([pod])
+    sc, feas, reasons = pyoracle_nrt.nrt_batch(F.flatten_nrt_nodes(nodes, nrts, names), F.flatten_nrt_pods([pod], names),
+                                               STRATEGY[strategy])
+    got = {n["name"]: int(sc[0, i]) for i, n in enumerate(fixture)}
+    assert not reasons[0][:len(fixture)].any()                # a node without NRT data passes Filter (filter.go:198-200)
+    for name in got:
+        if name not in keep:
+            assert got[name] == 0
+    for name, score in want.items():
+        assert got[name] == score and max(got.values()) == score
