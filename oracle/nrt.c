@@ -455,3 +455,14 @@ void orc_nrt_subtract_from_numas(int64_t* avail, const uint8_t* zmask, int Z, in
   for (int z = 0; z < Z; ++z)
     for (int r = 0; r < R; ++r) avail[z * R + r] = zs.avail[z][r];
 }
+
+/* Test entry point for numaNodesRequired (least_numa.go:159-208): the zone bitmask that can host the request with the
+ * fewest zones, and whether it is a minimum-distance combination.  Returns the zone count, 0 = cannot fit. */
+int orc_nrt_numa_nodes_required(const orc_nrt_node* nd, const uint8_t* res_flags, int R, int qos, uint8_t req_mask,
+                                const int64_t* req, uint32_t* mask_out, int* is_min) {
+  zones_t zs;
+  load_zones(nd, &zs);
+  *mask_out = 0;
+  *is_min = 0;
+  return numa_nodes_required(nd, &zs, res_flags, R, qos, req_mask, req, mask_out, is_min);
+}
