@@ -55,3 +55,24 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"liboracle|pyoracle|from oracle|import oracle|oracle/", code):
                         bad.append((fn, line.strip()))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_the_example_links():
+    """include/b200sched.h must be usable from C (what cgo compiles): examples/cycle.c passes gcc -std=c11 -pedantic
+    -Werror, links against the built library, and -- on a box without a GPU -- fails loudly with exit code 2."""
+    import subprocess
+    import tempfile
+
+    import torch
+
+    src = os.path.join(ROOT, "examples", "cycle.c")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + inc, src], check=True)
+    libdir = os.path.join(ROOT, "scheduler-plugins_b200", "lib")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "cycle")
+        subprocess.run(["gcc", "-std=c11", "-I" + inc, src, "-L" + libdir, "-lb200sched", "-Wl,-rpath," + libdir, "-o", exe],
+                       check=True)
+        if not torch.cuda.is_available():
+            r = subprocess.run([exe], capture_output=True, text=True)
+            assert r.returncode == 2 and "no CPU fallback" in r.stderr
