@@ -13,8 +13,11 @@ density 0.875, MATRIX output (every pod x node score, the layout the Go framewor
   e2e       same metric through the C-ABI call the Go shim makes (b200s_score_batch): pinned HOST
             buffers in, H2D of the step's inputs, kernels, D2H of the whole score matrix
             (compact u8 transport, values identical to the int64 matrix; the int64 transport is
-            reported beside it as e2e_i64)
+            reported beside it as e2e_i64).  The engine pipelines a batch this large in pod chunks,
+            so the D2H of one chunk overlaps the H2D of the next: the floor is the D2H itself
   cpu_baseline  the CPU oracle (a port of the Go path; Go is not installed) on a bounded sample
+  cycle_latency  BASELINE metric 2: P = 1 wall-clock latency of one cycle through the C-ABI, and the
+            cost of refreshing the snapshot between two cycles (16-row patch vs full re-upload)
 
 `--impl reference` times the CPU path alone (rank 0 only) on all host threads.
 """
