@@ -290,7 +290,7 @@ typedef struct {
   const uint8_t* qos;            /* [P] B200S_QOS_* */
   const uint8_t* flags;          /* [P] B200S_NRT_POD_* */
   const uint8_t* n_init;         /* [P] init containers (first in the container list) */
-  const uint8_t* n_app;          /* [P] app containers */
+  const uint8_t* n_app;          /* [P] app containers; n_init + n_app <= 8, else B200S_ERR_INVALID (flag the pod UNSUPPORTED with zero counts) */
   const uint8_t* cont_kind;      /* [P][C]   B200S_CONT_* */
   const uint8_t* req_mask;       /* [P][C+1] bit r: resource r is a key of the container's Requests; slot C = pod effective request */
   const int64_t* req;            /* [P][C+1][R] milli-units; slot C = GetPodEffectiveRequest (pkg/util/resource.go:51) */
@@ -298,7 +298,7 @@ typedef struct {
 
 typedef struct {
   int32_t host_node;             /* GLOBAL node index of the placed pod's host */
-  uint16_t host_region;          /* name ids of that host's labels */
+  uint16_t host_region;          /* name ids of that host's labels, < n_names of the snapshot (validated at upload) */
   uint16_t host_zone;
   int64_t max_network_cost;      /* DependenciesInfo.MaxNetworkCost */
 } b200s_netoh_dep;               /* one (placed pod, matching dependency) pair; 16 bytes */

@@ -547,6 +547,9 @@ int b200s_snapshot_network_overhead(b200s_ctx* c, const uint16_t* region_id, con
   if (!region_id || !zone_id || !zone_cost || !region_cost || n_names < 1 || n_names > 4096)
     return c->set_err(B200S_ERR_INVALID, "snapshot_network_overhead: bad arguments");
   size_t np = c->Npad, kk = (size_t)n_names * n_names;
+  for (int i = 0; i < c->N; ++i)  // the ids index the two cost tables on the device
+    if (region_id[i] >= n_names || zone_id[i] >= n_names)
+      return c->set_err(B200S_ERR_INVALID, "snapshot_network_overhead: label id outside the name dictionary");
   B200S_CUDA_TRY(c, c->netoh_region.ensure(np * 2));
   B200S_CUDA_TRY(c, c->netoh_zone.ensure(np * 2));
   B200S_CUDA_TRY(c, c->netoh_zone_cost.ensure(kk * 8));
@@ -929,6 +932,9 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     if (!q->qos || !q->flags || !q->n_init || !q->n_app || !q->cont_kind || !q->req_mask || !q->req)
       return c->set_err(B200S_ERR_INVALID, "pods_upload: null NRT pod column");
     const int C = B200S_NRT_MAX_CONT, R = c->nrt_R;
+    for (int p = 0; p < P; ++p)  // the kernels index the container slots with these counts
+      if ((int)q->n_init[p] + (int)q->n_app[p] > C)
+        return c->set_err(B200S_ERR_INVALID, "pods_upload: more than 8 containers (flag the pod UNSUPPORTED and zero its counts)");
     up.add(&c->nrt_pod_qos, q->qos, (size_t)P);
     up.add(&c->nrt_pod_flags, q->flags, (size_t)P);
     up.add(&c->nrt_pod_ninit, q->n_init, (size_t)P);
@@ -943,6 +949,12 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     if (!q->score_equally || !q->dep_offset) return c->set_err(B200S_ERR_INVALID, "pods_upload: null NetworkOverhead column");
     int total = q->dep_offset[P];
     if (total < 0 || (total > 0 && !q->deps)) return c->set_err(B200S_ERR_INVALID, "pods_upload: bad dependency CSR");
+    if (!c->has_netoh) return c->set_err(B200S_ERR_STATE, "pods_upload: NetworkOverhead pods without NetworkOverhead snapshot columns");
+    for (int p = 0; p < P; ++p)
+      if (q->dep_offset[p + 1] < q->dep_offset[p]) return c->set_err(B200S_ERR_INVALID, "pods_upload: dependency offsets must not decrease");
+    for (int i = 0; i < total; ++i)  // host labels index the cost tables on the device
+      if (q->deps[i].host_region >= c->netoh_K || q->deps[i].host_zone >= c->netoh_K)
+        return c->set_err(B200S_ERR_INVALID, "pods_upload: dependency host label id outside the name dictionary");
     up.add(&c->netoh_equal, q->score_equally, (size_t)P);
     up.add(&c->netoh_dep_off, q->dep_offset, (size_t)(P + 1) * 4);
     if (total > 0)
