@@ -79,9 +79,10 @@ def test_lowrisk_risk_load_properties(oracle, util, std, cap, req, lim, window):
 
 @settings(max_examples=60, deadline=None)
 @given(st.integers(0, 2 ** 31 - 1), st.integers(0, 3))
-def test_nrt_more_capacity_never_rejects(oracle, seed, strategy):
-    """filter.go:90-160: availability only enters through `available >= request`, so raising every zone's
-    availability can only turn rejects into passes (accounting errors aside), never the other way."""
+def test_nrt_pod_scope_more_capacity_never_rejects(oracle, seed, strategy):
+    """singleNUMAPodLevelHandler (filter.go:162-173) is ONE resourcesAvailableInAnyNUMANodes call on the
+    pod-effective request, and availability only enters it through `available >= request` (:121-136): on a
+    pod-scope node raising every zone's availability can only turn rejects into passes."""
     from oracle import pyoracle_nrt
 
     N, P = 40, 12
@@ -90,5 +91,24 @@ def test_nrt_more_capacity_never_rejects(oracle, seed, strategy):
     roomy = dict(nodes)
     roomy["avail"] = nodes["avail"] * 2 + (nodes["avail"] > 0) * 1000
     _, f1, r1 = pyoracle_nrt.nrt_batch(roomy, pods, strategy, None, None, pitch=N)
-    passed0 = (r0[:, :N] == 0)
+    pod_scope = (nodes["node_flags"] & 8) != 0
+    passed0 = (r0[:, :N] == 0) & pod_scope[None, :]
     assert (r1[:, :N][passed0] == 0).all()
+
+
+def test_nrt_container_scope_is_not_monotone_in_capacity(oracle):
+    """The container-scope handler (filter.go:39-78) places each app container greedily on the LOWEST fitting
+    NUMA id (:154) and subtracts it there (:68-74), so more capacity can move an early container onto the zone a
+    later one needed: seed 272, pod 3 / node 1 passes on the original node and is rejected on the doubled one.
+    Pins the counter-example that refuted the (wrong) monotonicity property this file used to assert."""
+    from oracle import pyoracle_nrt
+
+    N, P = 40, 12
+    nodes, pods = synth.gen_nrt(272, N, P, Z=4)
+    _, _, r0 = pyoracle_nrt.nrt_batch(nodes, pods, 0, None, None, pitch=N)
+    roomy = dict(nodes)
+    roomy["avail"] = nodes["avail"] * 2 + (nodes["avail"] > 0) * 1000
+    _, _, r1 = pyoracle_nrt.nrt_batch(roomy, pods, 0, None, None, pitch=N)
+    flipped = (r0[:, :N] == 0) & (r1[:, :N] != 0)
+    assert flipped.any()
+    assert not (flipped & ((nodes["node_flags"] & 8) != 0)[None, :]).any()  # only container-scope nodes flip
