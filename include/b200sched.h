@@ -269,6 +269,18 @@ int b200s_config_low_risk(b200s_ctx* ctx, int64_t smoothing_window_size, double 
                           double risk_limit_weight_mem);
 /* weights[r] per resource slot of the NRT dictionary; values < 1 mean 1 (score.go:49-60) */
 int b200s_config_nrt(b200s_ctx* ctx, int strategy, int32_t n_res, const int64_t* weights);
+/* NodeResourceTopologyMatch has two evaluation paths with identical results: the DIRECT kernel evaluates every
+ * (pod, node) pair from scratch as filter.go / score.go do; the BATCHED path (P >= 32, Least/Most/Balanced, <= 4 zones
+ * x <= 4 resource slots, quantities that fit the gcd-scaled 32-bit encoding) builds one score / pod-scope-filter
+ * table per DISTINCT request vector of the batch and expands it.  AUTO picks the batched path whenever it applies.
+ * The knob exists for the parity tests and A/B timing; b200s_nrt_last_path reports what the last eval ran. */
+#define B200S_NRT_PATH_AUTO 0
+#define B200S_NRT_PATH_DIRECT 1
+#define B200S_NRT_PATH_BATCHED 2 /* also for P < 32; still falls back to DIRECT where the path does not apply */
+int b200s_config_nrt_path(b200s_ctx* ctx, int path);
+int b200s_nrt_last_path(b200s_ctx* ctx); /* 0 = none yet, else B200S_NRT_PATH_DIRECT / _BATCHED */
+/* why the last eval declined the batched path ("" if it ran); a static string, valid for the life of the library */
+const char* b200s_nrt_path_note(b200s_ctx* ctx);
 /* NetworkOverhead: want_counts != 0 also keeps PreFilterState.satisfiedMap / violatedMap
  * (networkoverhead.go:283-296) for the Filter status message.  apply_own_filter (default 1): the
  * plugin's Filter verdict is ANDed into the feasible set that NormalizeScore runs over, as in the

@@ -98,10 +98,11 @@ static void load_zones(const orc_nrt_node* nd, zones_t* zs) {
 /* TopologyMatch.Filter: filter.go:176-225 with the two handlers :39-78, :162-173. */
 int orc_nrt_filter(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R) {
   if (pod->flags & ORC_NRT_POD_FILTER_BYPASS) return ORC_REASON_OK;     /* :180-183 */
-  if ((nd->flags & ORC_NRT_NODE_UNSUPPORTED) || (pod->flags & ORC_NRT_POD_UNSUPPORTED)) return ORC_REASON_UNSUPPORTED;
   if (!(nd->flags & ORC_NRT_NODE_FRESH)) return ORC_REASON_NRT_INVALID_TOPOLOGY; /* :194-197 */
   if (!(nd->flags & ORC_NRT_NODE_HAS_NRT)) return ORC_REASON_OK;         /* :198-200 */
   if (!(nd->flags & ORC_NRT_NODE_SINGLE_NUMA)) return ORC_REASON_OK;     /* :206-209, :228-230 */
+  /* the dense encoding's own escape hatch: only where the reference would start reading zones / containers (:211) */
+  if ((nd->flags & ORC_NRT_NODE_UNSUPPORTED) || (pod->flags & ORC_NRT_POD_UNSUPPORTED)) return ORC_REASON_UNSUPPORTED;
   zones_t zs;
   load_zones(nd, &zs);
   int numa_id = 0;
@@ -327,9 +328,9 @@ static void subtract_from_numas(zones_t* zs, uint8_t req_mask, const int64_t* re
 int64_t orc_nrt_score(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R, int strategy,
                       const int64_t* weights) {
   if (pod->qos != ORC_QOS_GUARANTEED) return 100;           /* :72-75 */
-  if ((nd->flags & ORC_NRT_NODE_UNSUPPORTED) || (pod->flags & ORC_NRT_POD_UNSUPPORTED)) return 0;
   if (!(nd->flags & ORC_NRT_NODE_FRESH)) return 0;           /* :79-82 */
   if (!(nd->flags & ORC_NRT_NODE_HAS_NRT)) return 0;         /* :83-86 */
+  if ((nd->flags & ORC_NRT_NODE_UNSUPPORTED) || (pod->flags & ORC_NRT_POD_UNSUPPORTED)) return 0;
   zones_t zs;
   load_zones(nd, &zs);
   const int scope_pod = (nd->flags & ORC_NRT_NODE_SCOPE_POD) != 0;

@@ -270,6 +270,7 @@ void b200s_shutdown(b200s_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
+  nrt2_destroy(c);
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
                     &c->alloc_iota,      &c->sort_tmp,         &c->tlp_util,         &c->tlp_cap,
                     &c->tlp_missing,     &c->tlp_flags,        &c->lvrb_f64,         &c->lvrb_i64,
@@ -329,6 +330,26 @@ int b200s_sync(b200s_ctx* c) {
 uint64_t b200s_launch_count(b200s_ctx* c) { return c ? c->launches : 0; }
 
 int32_t b200s_npad(b200s_ctx* c) { return c ? c->Npad : 0; }
+
+int b200s_config_nrt_path(b200s_ctx* c, int path) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  if (path < B200S_NRT_PATH_AUTO || path > B200S_NRT_PATH_BATCHED) return c->set_err(B200S_ERR_INVALID, "config_nrt_path: unknown path");
+  nrt2_set_force(c, path);
+  return B200S_OK;
+}
+
+int b200s_nrt_last_path(b200s_ctx* c) {
+  if (!c) return 0;
+  Guard g(c);
+  return nrt2_last_path(c);
+}
+
+const char* b200s_nrt_path_note(b200s_ctx* c) {
+  if (!c) return "";
+  Guard g(c);
+  return nrt2_note(c);
+}
 
 int b200s_set_profiling(b200s_ctx* c, int on) {
   if (!c) return B200S_ERR_INVALID;
@@ -536,6 +557,7 @@ int b200s_snapshot_nrt(b200s_ctx* c, const b200s_nrt_nodes* nn) {
   c->nrt_Z = Z;
   c->nrt_R = R;
   c->has_nrt = true;
+  nrt2_on_snapshot_full(c, nn);
   return B200S_OK;
 }
 
@@ -722,9 +744,13 @@ int b200s_snapshot_patch_nrt(b200s_ctx* c, int32_t count, const int32_t* node_id
                                       cnt, cnt);
     // a node that changed class must move (warps are class-pure); a node whose free capacity drifted stays where
     // it is until the next full upload -- the order within a class is only a hint
-    if (nrt_class_of(c->nrt_key_h[node_idx[i]]) != nrt_class_of(key)) c->nrt_perm_dirty = true;
+    if (nrt_class_of(c->nrt_key_h[node_idx[i]]) != nrt_class_of(key)) {
+      c->nrt_perm_dirty = true;
+      nrt2_on_class_change(c);
+    }
     c->nrt_key_h[node_idx[i]] = key;
   }
+  nrt2_on_patch_rows(c, count, nn);
   return B200S_OK;
 }
 
@@ -766,6 +792,7 @@ int b200s_snapshot_patch_nrt_deduct(b200s_ctx* c, int32_t count, const int32_t* 
   B200S_CUDA_TRY(c, cudaGetLastError());
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the staging block is re-used by the next patch call
   c->launches++;
+  nrt2_on_deduct(c, count, deduct);
   return B200S_OK;
 }
 
@@ -854,6 +881,7 @@ int b200s_config_nrt(b200s_ctx* c, int strategy, int32_t n_res, const int64_t* w
   for (int r = 0; r < B200S_NRT_MAX_RES; ++r) c->nrt_w[r] = 1;
   for (int r = 0; r < n_res; ++r) c->nrt_w[r] = (weights && weights[r] >= 1) ? weights[r] : 1;  // score.go:49-60
   c->nrt_cfg = true;
+  c->nrt_cfg_gen++;
   return B200S_OK;
 }
 
@@ -942,6 +970,9 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     up.add(&c->nrt_pod_kind, q->cont_kind, (size_t)P * C);
     up.add(&c->nrt_pod_req_mask, q->req_mask, (size_t)P * (C + 1));
     up.add(&c->nrt_pod_req, q->req, (size_t)P * (C + 1) * R * 8);
+    nrt2_on_pods(c, q, P);  // distinct request vectors of the batch (host dictionary of the batched path)
+  } else {
+    nrt2_on_pods(c, nullptr, 0);
   }
   c->has_netoh_pods = b->netoh != nullptr;
   if (b->netoh && P > 0) {
@@ -1171,7 +1202,14 @@ int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* 
   const bool score_only = plugin == B200S_PLUGIN_ALLOCATABLE || plugin == B200S_PLUGIN_TLP ||
                           plugin == B200S_PLUGIN_LVRB || plugin == B200S_PLUGIN_PEAKS;
   const size_t esz = dtype == B200S_OUT_I64 ? 8 : 1;
-  const size_t out_bytes = batch && batch->n_pods > 0 ? (size_t)batch->n_pods * c->Npad * esz : 0;
+  // The chunk decision must be the same on every rank of a sharded job (each chunk of a normalising plugin is one
+  // min/max all-reduce: ranks that disagree on chunked-or-not or on the chunk count would mismatch collectives), and
+  // shards differ in size by up to one 128-node block -- so with a communicator it is taken from rank-invariant
+  // values only: P, dtype and the nominal shard size ceil(Nglobal / world) rounded to the node alignment.
+  const int world = comm_world(c);
+  const size_t npad_nominal =
+      world > 1 ? (size_t)round_up((std::max(c->Nglobal, 1) + world - 1) / world, B200S_NODE_ALIGN) : (size_t)c->Npad;
+  const size_t out_bytes = batch && batch->n_pods > 0 ? (size_t)batch->n_pods * npad_nominal * esz : 0;
   constexpr size_t kChunkBytes = (size_t)48 << 20;
   if (score_only && batch && scores_out && !feasible_out && !reasons_out && c->snap_valid &&
       (dtype == B200S_OUT_I64 || dtype == B200S_OUT_U8) && out_bytes >= 2 * kChunkBytes && batch->n_pods >= 64) {

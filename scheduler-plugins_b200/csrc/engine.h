@@ -72,6 +72,7 @@ struct alignas(16) NormParam {
 };
 
 struct Comm;  // NCCL communicator wrapper (comm.cu)
+struct Nrt2;  // state of the batched NodeResourceTopologyMatch path (nrt2.cu)
 
 }  // namespace b200s
 
@@ -156,6 +157,8 @@ struct b200s_ctx {
   std::vector<uint64_t> nrt_key_h;
   bool nrt_perm_dirty = false;
   bool nrt_cfg = false;
+  uint64_t nrt_cfg_gen = 0;  // bumped on every config change
+  b200s::Nrt2* nrt2 = nullptr;
   int nrt_strategy = B200S_NRT_LEAST_ALLOCATED;
   int64_t nrt_w[B200S_NRT_MAX_RES] = {1, 1, 1, 1, 1, 1, 1, 1};
 
@@ -263,6 +266,20 @@ int netoh_eval(b200s_ctx* c, int dtype);
 int peaks_eval(b200s_ctx* c, int dtype);
 int lowrisk_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
+
+// nrt2.cu: batched NodeResourceTopologyMatch path (score tables per distinct request vector + coalesced expansion)
+void nrt2_destroy(b200s_ctx* c);
+void nrt2_on_snapshot_full(b200s_ctx* c, const b200s_nrt_nodes* nn);
+void nrt2_on_patch_rows(b200s_ctx* c, int count, const b200s_nrt_nodes* rows);
+void nrt2_on_deduct(b200s_ctx* c, int count, const int64_t* deduct);
+void nrt2_on_class_change(b200s_ctx* c);
+void nrt2_on_pods(b200s_ctx* c, const b200s_nrt_pods* q, int P);
+int nrt2_prepare(b200s_ctx* c);  // 1 = applicable and prepared, 0 = keep the direct kernel, < 0 = error
+int nrt2_eval(b200s_ctx* c, int dtype);
+void nrt2_set_force(b200s_ctx* c, int path);
+int nrt2_last_path(b200s_ctx* c);
+const char* nrt2_note(b200s_ctx* c);
+void nrt2_note_direct(b200s_ctx* c);
 int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint64_t* mismatches);
 
 // comm.cu

@@ -134,10 +134,12 @@ template <int Z, int R>
 __device__ int nrt_filter(const Zones<Z, R>& node_zs, uint32_t nflags, uint32_t node_res_mask, const NrtCfg& cfg,
                           const PodS<R>& pod) {
   if (pod.flags & B200S_NRT_POD_FILTER_BYPASS) return B200S_REASON_OK;
-  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return B200S_REASON_UNSUPPORTED;
   if (!(nflags & B200S_NRT_NODE_FRESH)) return B200S_REASON_NRT_INVALID_TOPOLOGY;
   if (!(nflags & B200S_NRT_NODE_HAS_NRT)) return B200S_REASON_OK;
   if (!(nflags & B200S_NRT_NODE_SINGLE_NUMA)) return B200S_REASON_OK;
+  // shapes outside the dense encoding only matter where the reference would look at the zones / containers: after
+  // its own gates (filter.go:194-209), so a stale or policy-less node answers as the reference does
+  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return B200S_REASON_UNSUPPORTED;
   // One loop for both scopes: pod scope = a single step on the pod-effective request (slot C_MAX,
   // singleNUMAPodLevelHandler :162-173); container scope = init containers without subtraction, then app
   // containers with it (:39-78).
@@ -347,8 +349,8 @@ template <int Z, int R, int SC>
 __device__ int64_t nrt_score(const Zones<Z, R>& node_zs, const int32_t (&cost)[Z][Z], uint32_t nflags, int max_numa,
                              const NrtCfg& cfg, const PodS<R>& pod) {
   if (pod.qos != B200S_QOS_GUARANTEED) return 100;
-  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return 0;
   if (!(nflags & B200S_NRT_NODE_FRESH) || !(nflags & B200S_NRT_NODE_HAS_NRT)) return 0;
+  if ((nflags & B200S_NRT_NODE_UNSUPPORTED) || (pod.flags & B200S_NRT_POD_UNSUPPORTED)) return 0;
   const bool scope_pod = nflags & B200S_NRT_NODE_SCOPE_POD;
   const int nc = pod.n_init + pod.n_app;
   const int steps = scope_pod ? 1 : nc;  // pod scope: one step on the pod-effective request (slot C_MAX)
@@ -610,7 +612,18 @@ int nrt_eval(b200s_ctx* c, int dtype) {
     cfg.w[r] = c->nrt_w[r];
     cfg.res_flags[r] = c->nrt_res_flags[r];
   }
+  // A batch goes through the batched path of nrt2.cu when it applies (score tables per distinct request vector,
+  // 32-bit scaled arithmetic, coalesced natural-order rows); single cycles, LeastNUMANodes and shapes / ranges
+  // outside it keep the direct per-(pod, node) kernel below.
+  const int batched = nrt2_prepare(c);
+  if (batched < 0) return batched;
   KernelTimer kt(c, B200S_PLUGIN_NRT);
+  if (batched == 1) {
+    B200S_TRY(nrt2_eval(c, dtype));
+    o.valid = true;
+    return B200S_OK;
+  }
+  nrt2_note_direct(c);
   int rc;
   if (c->nrt_Z <= 2 && c->nrt_R <= 4)
     rc = launch<2, 4>(c, dtype, nc, pc, cfg);

@@ -1,0 +1,924 @@
+// NodeResourceTopologyMatch, batched path: Filter + Score (Least/Most/BalancedAllocation) for P pods x N nodes.
+//
+// Reference semantics (pkg/noderesourcetopology): Filter filter.go:176-225 with the handlers :39-78 / :162-173 and
+// resourcesAvailableInAnyNUMANodes :90-160; Score score.go:62-165 with least_allocated.go:25-55,
+// most_allocated.go:25-54, balanced_allocation.go:27-54.  nrt.cu evaluates every (pod, node) pair from scratch
+// (the shape of the reference); this file exploits what a BATCH of pending pods has in common:
+//
+//  * score_each_numa (score.go:110-124) depends on ONE request vector and the node only -- container scope averages it
+//    over the pod's containers without subtraction (score.go:152-165), pod scope takes it on the pod-effective
+//    request (:142-150).  Pending pods share few distinct request vectors (c4: 10 504 container instances of the
+//    Guaranteed pods, 1 216 distinct), so a byte table T[vector][node] is built once (nrt2_table_kernel) and the
+//    P x N pass gathers from it.  The pod-scope Filter (filter.go:162-173) is a function of (effective vector, node)
+//    as well and shares the table entry (value >= 128 = rejected).
+//  * only the container-scope Filter (first-fit with subtraction, filter.go:39-78) is a per-(pod, node) state
+//    machine; it runs on the container-scope nodes only, in 32-bit arithmetic on gcd-scaled quantities.
+//  * nodes are split by control-flow class into two ORDER-PRESERVING compact lists (container-scope / pod-scope
+//    nodes that reach a handler); every other node is decided by its flags.  A CTA of the P x N kernel owns a tile of
+//    256 NATURAL node indices: the container-scope nodes of the tile are a contiguous slot range, their results are
+//    staged in shared memory, and the expansion to the [P][Npad] score / reason / feasibility outputs is written in
+//    natural order with fully coalesced rows (round 1's permuted kernel scattered them: 30.9 sectors per request).
+//
+// Exact 32-bit arithmetic: per resource slot every quantity that enters a comparison or subtraction (zone
+// Available, requests; milli-units) is divided by their common gcd gm[r]; every quantity that enters a score ratio
+// (Quantity.Value() of capacity and request) by gv[r].  Comparisons, differences and the ratios
+// (cv - rv) * 100 / cv are invariant under the common factor, so results are bit-identical to the 64-bit path as long as
+// the scaled values fit (checked on the host; otherwise nrt_eval keeps the direct 64-bit kernel of nrt.cu).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "engine.h"
+
+namespace b200s {
+
+namespace {
+
+constexpr int C_MAX = B200S_NRT_MAX_CONT;
+constexpr int TILE = 256;  // natural node indices per CTA of the P x N kernel
+constexpr int PT = 32;     // pods per CTA
+constexpr int UT = 32;     // request vectors per CTA of the table kernel
+constexpr int32_t S_MIN = INT32_MIN, S_MAX = INT32_MAX;
+constexpr int64_t LIM_MILLI = (int64_t)1 << 30;  // scaled milli quantities stay below (sentinels are +-2^31)
+constexpr int64_t LIM_VALUE = 42000000;          // scaled Value() quantities: x100 stays below 2^32
+
+// One distinct request vector of the batch, scaled (device record, 96 bytes).
+struct alignas(16) VecRec {
+  int32_t eff[4];   // Filter threshold per resource: S_MIN = does not constrain, S_MIN+1 = any LISTING zone (QoS-exempt
+                    // NUMA-affine resource, numaresources.go:137-142), else the scaled quantity
+  int32_t sub[4];   // what an app container takes from its zone (0 where exempt / zero / not requested)
+  int32_t rq[4];    // scaled request (milli domain) for the `req > cap` test of the strategies
+  int32_t rv[4];    // scaled Quantity.Value() of the request
+  int32_t w[4];     // weight of the resource if requested (the strategies iterate the requested NAMES), else 0
+  uint32_t wsum;    // sum of w
+  uint32_t wmagic;  // floor(2^32 / wsum) (2^32-1 for 1)
+  uint8_t need;     // bit r: requested with a non-zero quantity (filter.go:101-105)
+  uint8_t guar;     // Guaranteed QoS
+  uint8_t nreq;     // number of requested resource names
+  uint8_t mask;     // bit r: resource name requested
+  uint32_t pad;
+};
+static_assert(sizeof(VecRec) == 96, "VecRec layout");
+
+struct HostVec {
+  int64_t req[4];
+  uint8_t mask, guar;
+};
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+inline uint64_t hash_vec(const HostVec& v) {
+  uint64_t h = 0x9e3779b97f4a7c15ull ^ ((uint64_t)v.mask << 8 | v.guar);
+  for (int r = 0; r < 4; ++r) h = mix64(h ^ (uint64_t)v.req[r]);
+  return h;
+}
+inline bool same_vec(const HostVec& a, const HostVec& b) {
+  return a.mask == b.mask && a.guar == b.guar && a.req[0] == b.req[0] && a.req[1] == b.req[1] && a.req[2] == b.req[2] &&
+         a.req[3] == b.req[3];
+}
+inline uint64_t gcd_u64(uint64_t a, uint64_t b) { return std::gcd(a, b); }
+inline int64_t qty_value_h(int64_t milli) { return (milli + 999) / 1000; }  // Quantity.Value() of a non-negative quantity
+
+}  // namespace
+
+// Host + device state of the batched path (owned by the ctx, opaque to engine.cu).
+struct Nrt2 {
+  // ---- snapshot side
+  uint64_t gm[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};  // gcd of listed zone Available (milli / Value()); 0 = none
+  int64_t maxm[4] = {0, 0, 0, 0};
+  bool neg = false;          // a listed Available is negative: the scaled encoding does not apply
+  bool lists_valid = false;  // class lists match the flags mirror
+  int Nc = 0, Np = 0, Sc = 0, Sp = 0;  // container-scope / pod-scope handler nodes; padded to 128
+  DevBuf slot, list, tile_c0;          // [Npad] int32, [Sc + Sp] int32, [Npad / TILE + 1] int32
+  DevBuf filt, capv, magic, nzs, nrm;  // [Z][R][S] int32 x3, [S] u8 x2 (node columns of the two lists, scaled)
+  uint64_t node_prep_serial = ~0ull;
+  uint64_t node_prep_gm[4] = {0, 0, 0, 0}, node_prep_gv[4] = {0, 0, 0, 0};
+  // ---- pod side (host dictionary, built at pods_upload)
+  bool pods_ok = false;  // the batch fits the path (shape, signs, QoS consistency)
+  const char* pods_note = "no NodeResourceTopologyMatch pod columns";
+  std::vector<HostVec> vecs;
+  std::vector<int32_t> pod_vec;  // [P][C_MAX + 1] vector id or -1
+  std::vector<int32_t> tc_of, tp_of;      // [U] table row of the vector or -1
+  std::vector<int32_t> tc_list, tp_list;  // row -> vector id
+  uint64_t pgm[4] = {0, 0, 0, 0}, pgv[4] = {0, 0, 0, 0};
+  int64_t pmaxm[4] = {0, 0, 0, 0};
+  bool balanced_ok = true;  // every scored vector names >= 2 resources (else the variance is NaN, balanced_allocation.go:41)
+  uint64_t pods_serial = 0;
+  // ---- prepared batch (device), keyed
+  uint64_t prep_pods_serial = ~0ull, prep_cfg = ~0ull;
+  uint64_t prep_gm[4] = {0, 0, 0, 0}, prep_gv[4] = {0, 0, 0, 0};
+  bool prep_ok = false;
+  DevBuf vecrec, d_pod_vec, d_pod_tc, d_pod_tp, d_tc_list, d_tp_list;
+  DevBuf Tc, Tp;
+  int last_path = 0;  // 1 direct, 2 table (what the last nrt_eval ran)
+  const char* note = "";  // why the batched path was declined last time (static string)
+  int force = 0;      // 0 auto, 1 direct, 2 table when applicable
+  ~Nrt2() {
+    for (DevBuf* b : {&slot, &list, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
+                      &d_tc_list, &d_tp_list, &Tc, &Tp})
+      b->release();
+  }
+};
+
+Nrt2* nrt2_get(b200s_ctx* c) {
+  if (!c->nrt2) c->nrt2 = new Nrt2();
+  return c->nrt2;
+}
+void nrt2_destroy(b200s_ctx* c) {
+  delete c->nrt2;
+  c->nrt2 = nullptr;
+}
+void nrt2_set_force(b200s_ctx* c, int path) { nrt2_get(c)->force = path; }
+int nrt2_last_path(b200s_ctx* c) { return c->nrt2 ? c->nrt2->last_path : 0; }
+const char* nrt2_note(b200s_ctx* c) { return c->nrt2 ? c->nrt2->note : ""; }
+void nrt2_note_direct(b200s_ctx* c) { nrt2_get(c)->last_path = 1; }
+
+// ---- snapshot-side bookkeeping (called by engine.cu with the caller's host columns) -----------------------------
+namespace {
+void fold_rows(Nrt2* s, int Z, int R, int count, const uint8_t* nz, const uint8_t* zmask, const int64_t* avail) {
+  // zmask [Z][count], avail [Z][R][count]
+  for (int z = 0; z < Z; ++z)
+    for (int r = 0; r < R && r < 4; ++r) {
+      const int64_t* col = avail + ((size_t)z * R + r) * count;
+      const uint8_t* zm = zmask + (size_t)z * count;
+      uint64_t gm = s->gm[r], gv = s->gv[r];
+      int64_t mx = s->maxm[r];
+      for (int i = 0; i < count; ++i) {
+        if (z >= nz[i] || !((zm[i] >> r) & 1u)) continue;
+        const int64_t v = col[i];
+        if (v < 0) {
+          s->neg = true;
+          continue;
+        }
+        if (gm != 1) gm = gcd_u64(gm, (uint64_t)v);
+        if (gv != 1) gv = gcd_u64(gv, (uint64_t)qty_value_h(v));
+        mx = std::max(mx, v);
+      }
+      s->gm[r] = gm;
+      s->gv[r] = gv;
+      s->maxm[r] = mx;
+    }
+}
+}  // namespace
+
+void nrt2_on_snapshot_full(b200s_ctx* c, const b200s_nrt_nodes* nn) {
+  Nrt2* s = nrt2_get(c);
+  for (int r = 0; r < 4; ++r) s->gm[r] = s->gv[r] = 0, s->maxm[r] = 0;
+  s->neg = false;
+  s->lists_valid = false;
+  if (nn->n_zones <= 4 && nn->n_res <= 4 && c->N > 0)
+    fold_rows(s, nn->n_zones, nn->n_res, c->N, nn->n_zones_node, nn->zone_res_mask, nn->avail);
+}
+// patched rows: any common divisor of old and new values stays valid, so the gcds only ever shrink
+void nrt2_on_patch_rows(b200s_ctx* c, int count, const b200s_nrt_nodes* rows) {
+  Nrt2* s = nrt2_get(c);
+  if (c->nrt_Z <= 4 && c->nrt_R <= 4 && count > 0)
+    fold_rows(s, c->nrt_Z, c->nrt_R, count, rows->n_zones_node, rows->zone_res_mask, rows->avail);
+}
+// OverReserve deduction: available - q (or 0) is a multiple of g' = gcd(g, q).  Value() of a difference is not the
+// difference of the Value()s in general -- but when g' is a whole number of units (a multiple of 1000 milli) every
+// value is whole, Value(x) = x / 1000, and the Value()s are multiples of g' / 1000.
+void nrt2_on_deduct(b200s_ctx* c, int count, const int64_t* deduct /* [R][count] */) {
+  Nrt2* s = nrt2_get(c);
+  if (c->nrt_R > 4) return;
+  for (int r = 0; r < c->nrt_R; ++r) {
+    uint64_t gq = 0;
+    for (int i = 0; i < count; ++i) {
+      const int64_t q = deduct[(size_t)r * count + i];
+      if (q < 0)
+        s->neg = true;
+      else
+        gq = gcd_u64(gq, (uint64_t)q);
+    }
+    if (gq == 0) continue;  // nothing taken off this resource
+    s->gm[r] = gcd_u64(s->gm[r], gq);
+    s->gv[r] = (s->gm[r] % 1000 == 0) ? gcd_u64(s->gv[r], s->gm[r] / 1000) : 1;
+  }
+}
+void nrt2_on_class_change(b200s_ctx* c) {
+  if (c->nrt2) c->nrt2->lists_valid = false;
+}
+
+// ---- pod-side dictionary (called by pods_upload with the caller's host columns) ----------------------------------
+void nrt2_on_pods(b200s_ctx* c, const b200s_nrt_pods* q, int P) {
+  Nrt2* s = nrt2_get(c);
+  s->pods_serial++;
+  s->pods_ok = false;
+  s->vecs.clear();
+  s->tc_of.clear();
+  s->tp_of.clear();
+  s->tc_list.clear();
+  s->tp_list.clear();
+  for (int r = 0; r < 4; ++r) s->pgm[r] = s->pgv[r] = 0, s->pmaxm[r] = 0;
+  s->balanced_ok = true;
+  const int R = c->nrt_R;
+  s->pods_note = "no NodeResourceTopologyMatch pod columns / more than 4 zones or resource slots";
+  if (!q || P <= 0 || R > 4 || c->nrt_Z > 4) return;
+  s->pods_note = "";
+  s->pod_vec.assign((size_t)P * (C_MAX + 1), -1);
+  size_t cap = 64;
+  while (cap < (size_t)P * 6) cap <<= 1;
+  std::vector<int32_t> table(cap, -1);
+  const uint32_t rmask = (1u << R) - 1u;
+  bool ok = true;
+  auto intern = [&](int p, int slot, bool guar) -> int32_t {
+    HostVec v;
+    v.mask = (uint8_t)(q->req_mask[(size_t)p * (C_MAX + 1) + slot] & rmask);
+    v.guar = guar ? 1 : 0;
+    const int64_t* rq = q->req + ((size_t)p * (C_MAX + 1) + slot) * R;
+    for (int r = 0; r < 4; ++r) {
+      int64_t x = (r < R && ((v.mask >> r) & 1u)) ? rq[r] : 0;
+      if (x < 0) ok = false, s->pods_note = "negative request";
+      // a non-Guaranteed pod's NUMA-affine requests only matter as zero / non-zero (numaresources.go:137-142)
+      if (!guar && r < R && (c->nrt_res_flags[r] & B200S_NRT_RES_AFFINE)) x = x != 0 ? 1 : 0;
+      v.req[r] = x;
+    }
+    size_t h = (size_t)hash_vec(v) & (cap - 1);
+    while (table[h] >= 0) {
+      if (same_vec(s->vecs[(size_t)table[h]], v)) return table[h];
+      h = (h + 1) & (cap - 1);
+    }
+    const int32_t id = (int32_t)s->vecs.size();
+    table[h] = id;
+    s->vecs.push_back(v);
+    s->tc_of.push_back(-1);
+    s->tp_of.push_back(-1);
+    return id;
+  };
+  for (int p = 0; p < P; ++p) {
+    const uint8_t fl = q->flags[p];
+    const bool guar = q->qos[p] == B200S_QOS_GUARANTEED;
+    if (fl & B200S_NRT_POD_UNSUPPORTED) continue;  // decided by the flag alone
+    if (fl & B200S_NRT_POD_FILTER_BYPASS) {
+      if (guar) ok = false, s->pods_note = "Filter bypass on a Guaranteed pod";  // Filter bypass is BestEffort-only (filter.go:180-183); keep the direct kernel for anything else
+      continue;
+    }
+    const int nc = (int)q->n_init[p] + (int)q->n_app[p];
+    for (int cidx = 0; cidx < nc; ++cidx) {
+      const int32_t id = intern(p, cidx, guar);
+      s->pod_vec[(size_t)p * (C_MAX + 1) + cidx] = id;
+      if (guar && s->tc_of[(size_t)id] < 0) {
+        s->tc_of[(size_t)id] = (int32_t)s->tc_list.size();
+        s->tc_list.push_back(id);
+      }
+    }
+    if (guar && nc == 0) ok = false, s->pods_note = "Guaranteed pod without containers";  // mean over zero containers (score.go:162): NaN -> direct kernel
+    const int32_t id = intern(p, C_MAX, guar);
+    s->pod_vec[(size_t)p * (C_MAX + 1) + C_MAX] = id;
+    if (s->tp_of[(size_t)id] < 0) {
+      s->tp_of[(size_t)id] = (int32_t)s->tp_list.size();
+      s->tp_list.push_back(id);
+    }
+  }
+  // statistics over the distinct vectors
+  for (size_t u = 0; u < s->vecs.size(); ++u) {
+    const HostVec& v = s->vecs[u];
+    int nreq = 0;
+    for (int r = 0; r < R; ++r) {
+      if (!((v.mask >> r) & 1u)) continue;
+      ++nreq;
+      const bool exempt = !v.guar && (c->nrt_res_flags[r] & B200S_NRT_RES_AFFINE);
+      if (exempt) continue;
+      s->pgm[r] = gcd_u64(s->pgm[r], (uint64_t)v.req[r]);
+      s->pmaxm[r] = std::max(s->pmaxm[r], v.req[r]);
+      if (v.guar) s->pgv[r] = gcd_u64(s->pgv[r], (uint64_t)qty_value_h(v.req[r]));
+    }
+    if (v.guar && nreq < 2) s->balanced_ok = false;
+  }
+  s->pods_ok = ok;
+}
+
+namespace {
+
+// ---- device code ----------------------------------------------------------------------------------------------------
+
+struct NodePrepArgs {
+  const uint8_t* node_flags;
+  const uint8_t* nz;
+  const uint8_t* node_res_mask;
+  const uint8_t* zone_res_mask;  // [Zs][Npad]
+  const int64_t* avail;          // [Zs][Rs][Npad]
+  const int32_t* list;           // [S] node of slot, -1 = padding
+  int Zs, Rs, Npad, S;
+  uint64_t gm[4], gv[4];
+  uint8_t res_flags[4];
+};
+
+// One thread per slot of the two class lists: the node's zones x resources block in the scaled encodings.
+//   filt  Filter operand (see nrt.cu nrt_filter): scaled Available where the zone lists r; S_MIN where it does not but
+//         another zone does, or no zone does and r is NUMA-bound; S_MAX where no zone lists a host-level r (:139-142)
+//   capv  scaled Value() of the capacity the strategies see (0 = zone lacks the resource or has none left)
+//   magic floor(2^32 / capv) for the exact reciprocal division
+template <int Z, int R>
+__global__ void nrt2_node_prep_kernel(NodePrepArgs a, int32_t* __restrict__ filt, int32_t* __restrict__ capv,
+                                      uint32_t* __restrict__ magic, uint8_t* __restrict__ nzs, uint8_t* __restrict__ nrm) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.S) return;
+  const int n = a.list[s];
+  int nz = 0;
+  uint32_t zm[Z];
+#pragma unroll
+  for (int z = 0; z < Z; ++z) zm[z] = 0;
+  if (n >= 0) {
+    nz = min((int)a.nz[n], Z);
+#pragma unroll
+    for (int z = 0; z < Z; ++z)
+      if (z < a.Zs && z < nz) zm[z] = a.zone_res_mask[(size_t)z * a.Npad + n];
+  }
+  nzs[s] = (uint8_t)nz;
+  nrm[s] = n >= 0 ? a.node_res_mask[n] : 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) any |= (zm[z] >> r) & 1u;
+    const int32_t none = (!any && r < a.Rs && (a.res_flags[r] & B200S_NRT_RES_HOST_LEVEL)) ? S_MAX : S_MIN;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      int32_t f = none, cv = 0;
+      if (r < a.Rs && ((zm[z] >> r) & 1u)) {
+        const int64_t av = a.avail[((size_t)z * a.Rs + r) * a.Npad + n];
+        f = (int32_t)((uint64_t)av / a.gm[r]);
+        cv = (int32_t)((uint64_t)((av + 999) / 1000) / a.gv[r]);
+      }
+      const size_t o = ((size_t)z * R + r) * a.S + s;
+      filt[o] = f;
+      capv[o] = cv;
+      magic[o] = cv <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / (uint32_t)cv);
+    }
+  }
+}
+
+// floor(num / d) for num < 2^32 with m = floor(2^32 / d) (2^32 - 1 for d == 1): the estimate umulhi(num, m) is the
+// quotient or one below it (m >= 2^32/d - 1 gives num*m/2^32 > num/d - 1), so one correction step is exact.
+__device__ __forceinline__ uint32_t div_magic(uint32_t num, uint32_t d, uint32_t m) {
+  uint32_t q = __umulhi(num, m);
+  const uint32_t rem = num - q * d;
+  return rem >= d ? q + 1 : q;
+}
+__device__ __forceinline__ int64_t f2i(double x) {
+  if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
+  return (int64_t)x;
+}
+
+struct TableArgs {
+  const int32_t* filt;   // + class base already applied: [Z][R][S] with stride S, element (z, r, slot)
+  const int32_t* capv;
+  const uint32_t* magic;
+  const uint8_t* nzs;
+  const uint8_t* nrm;
+  const VecRec* vecs;
+  const int32_t* rows;  // row -> vector id
+  int nrows;
+  int S;      // stride of the node columns
+  int count;  // slots of this class (padded to 128)
+  int most;
+};
+
+// T[row][slot] for UT request vectors x 128 slots per CTA: the thread keeps its node's cells in registers, the
+// vectors come from shared memory (warp-uniform).  POD: the table of the pod-scope nodes -- entry = score (100 for a
+// non-Guaranteed vector, score.go:72-75) if resourcesAvailableInAnyNUMANodes finds a zone (filter.go:162-173), else
+// 128 + B200S_REASON_NRT_ALIGN_POD.  Otherwise the score table of the container-scope nodes.
+template <int Z, int R, int SC, bool POD>
+__global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* __restrict__ T) {
+  __shared__ VecRec sv[UT];
+  const int row0 = blockIdx.y * UT, nrow = min(UT, a.nrows - row0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.vecs);
+    uint4* dst = reinterpret_cast<uint4*>(sv);
+    for (int i = threadIdx.x; i < nrow * 6; i += 128) dst[i] = src[(size_t)a.rows[row0 + i / 6] * 6 + i % 6];
+  }
+  const int slot = blockIdx.x * 128 + threadIdx.x;
+  int32_t filt[Z][R], cv[Z][R];
+  uint32_t mg[Z][R];
+#pragma unroll
+  for (int z = 0; z < Z; ++z)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const size_t o = ((size_t)z * R + r) * a.S + slot;
+      filt[z][r] = a.filt[o];
+      cv[z][r] = a.capv[o];
+      mg[z][r] = a.magic[o];
+    }
+  const int nz = a.nzs[slot];
+  const uint32_t nrm = a.nrm[slot];
+  __syncthreads();
+  for (int j = 0; j < nrow; ++j) {
+    const VecRec& v = sv[j];
+    uint32_t entry;
+    bool pass = true;
+    if constexpr (POD) {
+      uint32_t ok = 0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        bool fits = true;
+#pragma unroll
+        for (int r = 0; r < R; ++r) fits &= filt[z][r] >= v.eff[r];
+        ok |= fits ? 1u : 0u;
+      }
+      pass = ok != 0 && !(v.need & ~nrm);  // :107-113: a non-zero request must be reported at node level
+    }
+    int32_t score = 100;
+    if (!POD || v.guar) {  // warp-uniform
+      int32_t min_score = 0;
+#pragma unroll
+      for (int z = 0; z < Z; ++z) {
+        int32_t s;
+        if constexpr (SC == 1) {
+          // balanced_allocation.go:27-54 -- same operation order as nrt.cu strategy_score (fractions of scaled
+          // Value()s: the quotient of the same rational, correctly rounded, is the same double)
+          double fr[R];
+          bool over = false;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            fr[r] = 0;
+            if (!((v.mask >> r) & 1u)) continue;
+            const int32_t c = cv[z][r];
+            const double q = (double)v.rv[r] / (double)(c == 0 ? 1 : c);
+            const double f = c == 0 ? 1.0 : q;
+            over |= f > 1;
+            fr[r] = f;
+          }
+          const int n = v.nreq;
+          double sum = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((v.mask >> r) & 1u) sum += fr[r];
+          const double mean = sum / (double)n;
+          double ss = 0, comp = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((v.mask >> r) & 1u) {
+              const double d = fr[r] - mean;
+              ss += d * d;
+              comp += d;
+            }
+          const double variance = (ss - comp * comp / (double)n) / ((double)n - 1);
+          s = over ? 0 : (int32_t)f2i((1 - variance) * 100.0);
+        } else {
+          // least_allocated.go:25-55 / most_allocated.go:25-54: sum_r w_r * s_r / sum_r w_r over the requested names
+          uint32_t acc = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int32_t c = cv[z][r];
+            const bool zero = c == 0 || v.rq[r] > filt[z][r];  // capacity 0 (or resource missing) or request > capacity
+            const uint32_t num = (uint32_t)(a.most ? v.rv[r] : c - v.rv[r]) * 100u;
+            const uint32_t q = div_magic(zero ? 0u : num, (uint32_t)(c == 0 ? 1 : c), mg[z][r]);
+            acc += q * (uint32_t)v.w[r];
+          }
+          s = v.wsum == 0 ? 0 : (int32_t)div_magic(acc, v.wsum, v.wmagic);
+        }
+        // scoreForEachNUMANode (score.go:110-124): minimum of the non-zero zone scores
+        const bool take = z < nz && (min_score == 0 || (s != 0 && s < min_score));
+        min_score = take ? s : min_score;
+      }
+      score = min_score;
+    }
+    entry = pass ? (uint32_t)score : 128u + B200S_REASON_NRT_ALIGN_POD;
+    T[(size_t)(row0 + j) * a.count + slot] = (uint8_t)entry;
+  }
+}
+
+struct ExpandArgs {
+  // node side
+  const uint8_t* node_flags;  // [Npad]
+  const int32_t* slot;        // [Npad] class-local slot
+  const int32_t* tile_c0;     // [Npad / TILE + 1]
+  const int32_t* filt;        // container-scope slots, stride S
+  const uint8_t* nrm;
+  int S;
+  int Sc, Sp;
+  // pod side
+  const uint8_t* qos;
+  const uint8_t* flags;
+  const uint8_t* n_init;
+  const uint8_t* n_app;
+  const uint8_t* kind;     // [P][C_MAX]
+  const int32_t* pod_vec;  // [P][C_MAX + 1]
+  const int32_t* pod_tc;   // [P][C_MAX] row of Tc or -1
+  const int32_t* pod_tp;   // [P] row of Tp or -1
+  const VecRec* vecs;
+  const uint8_t* Tc;  // [Uc][Sc]
+  const uint8_t* Tp;  // [Ue][Sp]
+  const uint64_t* upstream;
+  int words, N, Npad, P;
+};
+
+struct PodMeta {
+  uint8_t qos, flags, n_init, n_app;
+  uint8_t kind[C_MAX];
+  uint8_t need[C_MAX];
+  int32_t tp;
+};
+
+// The P x N pass.  Phase 1: the container-scope nodes of this tile (a contiguous slot range) run the first-fit state
+// machine of singleNUMAContainerLevelHandler (filter.go:39-78) per pod and gather the container-scope score
+// (score.go:152-165) from Tc; one byte per (pod, slot) goes to shared memory (< 128: feasible with that score,
+// >= 128: 128 + reason).  Phase 2: every thread owns one NATURAL node index and expands pod by pod -- flag-decided
+// nodes, pod-scope nodes (one byte of Tp), container-scope nodes (the staged byte) -- into coalesced rows.
+template <int Z, int R, class OutT>
+__global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* __restrict__ out,
+                                                           uint32_t* __restrict__ feas32, uint8_t* __restrict__ reasons) {
+  __shared__ int32_t s_eff[PT][C_MAX][R];
+  __shared__ int32_t s_sub[PT][C_MAX][R];
+  __shared__ int32_t s_tc[PT][C_MAX];
+  __shared__ PodMeta s_meta[PT];
+  __shared__ uint8_t s_v[PT][TILE];
+  const int tid = threadIdx.x;
+  const int p0 = blockIdx.y * PT, pend = min(PT, a.P - p0);
+  for (int i = tid; i < pend * C_MAX; i += TILE) {
+    const int pp = i / C_MAX, c = i % C_MAX;
+    const int u = a.pod_vec[(size_t)(p0 + pp) * (C_MAX + 1) + c];
+    uint8_t need = 0;
+    if (u >= 0) {
+      const VecRec& v = a.vecs[u];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        s_eff[pp][c][r] = v.eff[r];
+        s_sub[pp][c][r] = v.sub[r];
+      }
+      need = v.need;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        s_eff[pp][c][r] = S_MIN;
+        s_sub[pp][c][r] = 0;
+      }
+    }
+    s_meta[pp].need[c] = need;
+    s_meta[pp].kind[c] = a.kind[(size_t)(p0 + pp) * C_MAX + c];
+    s_tc[pp][c] = a.pod_tc[(size_t)(p0 + pp) * C_MAX + c];
+  }
+  for (int i = tid; i < pend; i += TILE) {
+    const int p = p0 + i;
+    s_meta[i].qos = a.qos[p];
+    s_meta[i].flags = a.flags[p];
+    s_meta[i].n_init = a.n_init[p];
+    s_meta[i].n_app = a.n_app[p];
+    s_meta[i].tp = a.pod_tp[p];
+  }
+  const int c0 = a.tile_c0[blockIdx.x], ncs = a.tile_c0[blockIdx.x + 1] - c0;
+  __syncthreads();
+  if (tid < ncs) {
+    const int slot = c0 + tid;
+    int32_t node[Z][R];
+#pragma unroll
+    for (int z = 0; z < Z; ++z)
+#pragma unroll
+      for (int r = 0; r < R; ++r) node[z][r] = a.filt[((size_t)z * R + r) * a.S + slot];
+    bool nolist[R];  // no zone lists the (host-level) resource: nothing to subtract from (filter.go:139-142)
+#pragma unroll
+    for (int r = 0; r < R; ++r) nolist[r] = node[0][r] == S_MAX;
+    const uint32_t nrm = a.nrm[slot];
+    for (int pp = 0; pp < pend; ++pp) {
+      const PodMeta& m = s_meta[pp];
+      if (m.flags & (B200S_NRT_POD_FILTER_BYPASS | B200S_NRT_POD_UNSUPPORTED)) continue;  // decided in phase 2
+      const int n_init = m.n_init, steps = n_init + m.n_app;
+      int32_t zs[Z][R];
+#pragma unroll
+      for (int z = 0; z < Z; ++z)
+#pragma unroll
+        for (int r = 0; r < R; ++r) zs[z][r] = node[z][r];
+      uint32_t reason = 0;
+      for (int s = 0; s < steps; ++s) {
+        int32_t e[R], sb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          e[r] = s_eff[pp][s][r];
+          sb[r] = nolist[r] ? 0 : s_sub[pp][s][r];
+        }
+        uint32_t ok = 0;
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+          bool fits = true;
+#pragma unroll
+          for (int r = 0; r < R; ++r) fits &= zs[z][r] >= e[r];
+          ok |= (fits ? 1u : 0u) << z;
+        }
+        if (m.need[s] & ~nrm) ok = 0;  // :107-113
+        const uint32_t code = s >= n_init ? B200S_REASON_NRT_ALIGN_CONTAINER
+                                          : (m.kind[s] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR
+                                                                             : B200S_REASON_NRT_ALIGN_INIT);
+        reason = (reason == 0 && ok == 0) ? code : reason;
+        if (s >= n_init) {  // subtractResourcesFromNUMANodeList (numaresources.go:145-182) on the lowest fitting id
+          const int id = __ffs(ok) - 1;
+#pragma unroll
+          for (int z = 0; z < Z; ++z)
+#pragma unroll
+            for (int r = 0; r < R; ++r) zs[z][r] -= (z == id) ? sb[r] : 0;
+        }
+      }
+      uint32_t v = 128u + reason;
+      if (reason == 0) {
+        v = 100;  // non-Guaranteed: score.go:72-75
+        if (m.qos == B200S_QOS_GUARANTEED) {
+          uint32_t sum = 0;  // containerScopeScore (score.go:152-165): mean over init + app containers, truncated
+          for (int s = 0; s < steps; ++s) sum += a.Tc[(size_t)s_tc[pp][s] * a.Sc + slot];
+          v = (sum * ((65536u + (uint32_t)steps - 1u) / (uint32_t)steps)) >> 16;  // sum <= 800: exact floor(sum / steps)
+        }
+      }
+      s_v[pp][tid] = (uint8_t)v;
+    }
+  }
+  __syncthreads();
+  const int n = blockIdx.x * TILE + tid;
+  if (n >= a.Npad) return;
+  const uint32_t nfl = n < a.N ? a.node_flags[n] : 0u;
+  const int slot = a.slot[n];
+  const bool fresh = nfl & B200S_NRT_NODE_FRESH, handler = slot >= 0;
+  const bool pod_scope = nfl & B200S_NRT_NODE_SCOPE_POD;
+  const bool trivial_ok = !(nfl & B200S_NRT_NODE_HAS_NRT) || !(nfl & B200S_NRT_NODE_SINGLE_NUMA);
+  const int word = n >> 6;
+  for (int pp = 0; pp < pend; ++pp) {
+    const int p = p0 + pp;
+    const PodMeta& m = s_meta[pp];
+    uint32_t reason = 0, score = 0;
+    bool feasible = false;
+    if (n < a.N) {
+      const bool guar = m.qos == B200S_QOS_GUARANTEED;
+      uint32_t v;
+      if (m.flags & B200S_NRT_POD_FILTER_BYPASS) v = 100;                                  // filter.go:180-183
+      else if (!fresh) v = 128u + B200S_REASON_NRT_INVALID_TOPOLOGY;                       // :194-197
+      else if (trivial_ok) v = guar ? 0u : 100u;                                           // :198-209; score.go:83-94
+      else if (!handler || (m.flags & B200S_NRT_POD_UNSUPPORTED)) v = 128u + B200S_REASON_UNSUPPORTED;
+      else if (pod_scope) v = a.Tp[(size_t)m.tp * a.Sp + slot];
+      else v = s_v[pp][slot - c0];
+      reason = v >= 128u ? v - 128u : 0u;
+      const bool up = a.upstream ? ((a.upstream[(size_t)p * a.words + word] >> (n & 63)) & 1ull) : true;
+      feasible = reason == 0 && up;
+      if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
+      score = feasible ? v : 0u;
+    }
+    const size_t o = (size_t)p * a.Npad + n;
+    out[o] = (OutT)score;
+    reasons[o] = (uint8_t)reason;
+    const uint32_t w = __ballot_sync(0xffffffffu, feasible);
+    if ((tid & 31) == 0) feas32[o >> 5] = w;
+  }
+}
+
+int build_lists(b200s_ctx* c, Nrt2* s) {
+  const int N = c->N, Npad = c->Npad, ntiles = (Npad + TILE - 1) / TILE;
+  std::vector<int32_t> slot((size_t)Npad, -1), tile_c0((size_t)ntiles + 1, 0), clist, plist;
+  clist.reserve((size_t)N);
+  plist.reserve((size_t)N);
+  constexpr uint32_t need = B200S_NRT_NODE_FRESH | B200S_NRT_NODE_HAS_NRT | B200S_NRT_NODE_SINGLE_NUMA;
+  for (int n = 0; n < N; ++n) {
+    if (n % TILE == 0) tile_c0[(size_t)(n / TILE)] = (int32_t)clist.size();
+    const uint32_t fl = (uint32_t)((c->nrt_key_h[(size_t)n] >> 48) & 0xFF);
+    if ((fl & need) != need || (fl & B200S_NRT_NODE_UNSUPPORTED)) continue;
+    if (fl & B200S_NRT_NODE_SCOPE_POD) {
+      slot[(size_t)n] = (int32_t)plist.size();
+      plist.push_back(n);
+    } else {
+      slot[(size_t)n] = (int32_t)clist.size();
+      clist.push_back(n);
+    }
+  }
+  for (int t = (N + TILE - 1) / TILE; t <= ntiles; ++t) tile_c0[(size_t)t] = (int32_t)clist.size();
+  s->Nc = (int)clist.size();
+  s->Np = (int)plist.size();
+  s->Sc = round_up(std::max(s->Nc, 1), 128);
+  s->Sp = round_up(std::max(s->Np, 1), 128);
+  std::vector<int32_t> list((size_t)(s->Sc + s->Sp), -1);
+  std::copy(clist.begin(), clist.end(), list.begin());
+  std::copy(plist.begin(), plist.end(), list.begin() + s->Sc);
+  B200S_CUDA_TRY(c, s->slot.ensure((size_t)Npad * 4));
+  B200S_CUDA_TRY(c, s->list.ensure(list.size() * 4));
+  B200S_CUDA_TRY(c, s->tile_c0.ensure(tile_c0.size() * 4));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(s->slot.p, slot.data(), (size_t)Npad * 4, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(s->list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(s->tile_c0.p, tile_c0.data(), tile_c0.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources die at return
+  s->lists_valid = true;
+  s->node_prep_serial = ~0ull;
+  return B200S_OK;
+}
+
+inline uint32_t magic_of(uint32_t d) { return d <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / d); }
+
+}  // namespace
+
+// Decides whether the batched path applies to (snapshot, pod batch, args) and prepares its device state.
+// Returns 1 = applicable and prepared, 0 = keep the direct kernel, < 0 = error.
+int nrt2_prepare(b200s_ctx* c) {
+  Nrt2* s = nrt2_get(c);
+  s->note = "";
+  auto decline = [&](const char* why) { s->note = why; return 0; };
+  if (s->force == 1) return decline("direct path forced");
+  if (c->nrt_strategy == B200S_NRT_LEAST_NUMA_NODES) return decline("LeastNUMANodes");
+  if (c->nrt_Z > 4 || c->nrt_R > 4 || c->N <= 0) return decline("more than 4 zones or 4 resource slots");
+  if (s->force != 2 && c->P < 32) return decline("fewer than 32 pods");  // a P = 1 cycle is one pass of the direct kernel
+  if (!s->pods_ok) return decline(s->pods_note);
+  if (s->neg) return decline("negative zone availability");
+  if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION && !s->balanced_ok)
+    return decline("BalancedAllocation with a Guaranteed request naming < 2 resources");
+  const int R = c->nrt_R;
+  int64_t wtot = 0;
+  for (int r = 0; r < R; ++r) {
+    if (c->nrt_w[r] < 1 || c->nrt_w[r] > (1 << 20)) return decline("resource weight above 2^20");
+    wtot += c->nrt_w[r];
+  }
+  if (wtot * 100 >= ((int64_t)1 << 31)) return decline("resource weights too large");
+  uint64_t gm[4] = {1, 1, 1, 1}, gv[4] = {1, 1, 1, 1};
+  for (int r = 0; r < R; ++r) {
+    gm[r] = gcd_u64(s->gm[r], s->pgm[r]);
+    gv[r] = gcd_u64(s->gv[r], s->pgv[r]);
+    if (gm[r] == 0) gm[r] = 1;
+    if (gv[r] == 0) gv[r] = 1;
+    const int64_t mx = std::max(s->maxm[r], s->pmaxm[r]);
+    if (mx / (int64_t)gm[r] >= LIM_MILLI) return decline("a quantity does not fit 30 bits after gcd scaling");
+    if (qty_value_h(mx) / (int64_t)gv[r] >= LIM_VALUE) return decline("a Value() does not fit after gcd scaling");
+  }
+  if (!s->lists_valid) B200S_TRY(build_lists(c, s));
+  const size_t S = (size_t)s->Sc + s->Sp;
+  const size_t tc_bytes = (size_t)std::max<size_t>(s->tc_list.size(), 1) * s->Sc;
+  const size_t tp_bytes = (size_t)std::max<size_t>(s->tp_list.size(), 1) * s->Sp;
+  if (tc_bytes + tp_bytes > ((size_t)16 << 30)) return decline("score tables above 16 GiB");
+  // node columns of the two lists in the scaled encodings (per snapshot and scale)
+  if (s->node_prep_serial != c->snap_serial || memcmp(s->node_prep_gm, gm, sizeof(gm)) != 0 ||
+      memcmp(s->node_prep_gv, gv, sizeof(gv)) != 0) {
+    B200S_CUDA_TRY(c, s->filt.ensure(16 * S * 4));
+    B200S_CUDA_TRY(c, s->capv.ensure(16 * S * 4));
+    B200S_CUDA_TRY(c, s->magic.ensure(16 * S * 4));
+    B200S_CUDA_TRY(c, s->nzs.ensure(S));
+    B200S_CUDA_TRY(c, s->nrm.ensure(S));
+    NodePrepArgs a;
+    a.node_flags = c->nrt_node_flags.as<uint8_t>();
+    a.nz = c->nrt_nz.as<uint8_t>();
+    a.node_res_mask = c->nrt_node_res_mask.as<uint8_t>();
+    a.zone_res_mask = c->nrt_zone_res_mask.as<uint8_t>();
+    a.avail = c->nrt_avail.as<int64_t>();
+    a.list = s->list.as<int32_t>();
+    a.Zs = c->nrt_Z;
+    a.Rs = R;
+    a.Npad = c->Npad;
+    a.S = (int)S;
+    for (int r = 0; r < 4; ++r) {
+      a.gm[r] = gm[r];
+      a.gv[r] = gv[r];
+      a.res_flags[r] = r < R ? c->nrt_res_flags[r] : 0;
+    }
+    nrt2_node_prep_kernel<4, 4><<<(unsigned)((S + 127) / 128), 128, 0, c->stream>>>(
+        a, s->filt.as<int32_t>(), s->capv.as<int32_t>(), s->magic.as<uint32_t>(), s->nzs.as<uint8_t>(),
+        s->nrm.as<uint8_t>());
+    c->launches += 1;
+    B200S_CUDA_TRY(c, cudaGetLastError());
+    s->node_prep_serial = c->snap_serial;
+    memcpy(s->node_prep_gm, gm, sizeof(gm));
+    memcpy(s->node_prep_gv, gv, sizeof(gv));
+  }
+  // the batch's vectors in the scaled encoding (per pod batch, scale and plugin args)
+  const uint64_t cfg = c->nrt_cfg_gen;
+  if (!s->prep_ok || s->prep_pods_serial != s->pods_serial || s->prep_cfg != cfg || memcmp(s->prep_gm, gm, sizeof(gm)) != 0 ||
+      memcmp(s->prep_gv, gv, sizeof(gv)) != 0) {
+    s->prep_ok = false;
+    const size_t U = s->vecs.size(), P = (size_t)c->P;
+    std::vector<VecRec> recs(std::max<size_t>(U, 1));
+    memset(recs.data(), 0, recs.size() * sizeof(VecRec));
+    for (size_t u = 0; u < U; ++u) {
+      const HostVec& v = s->vecs[u];
+      VecRec& o = recs[u];
+      uint32_t wsum = 0;
+      for (int r = 0; r < 4; ++r) {
+        const bool named = r < R && ((v.mask >> r) & 1u);
+        const bool needed = named && v.req[r] != 0;
+        const bool exempt = !v.guar && r < R && (c->nrt_res_flags[r] & B200S_NRT_RES_AFFINE);
+        const int32_t q = (needed && !exempt) ? (int32_t)((uint64_t)v.req[r] / gm[r]) : 0;
+        o.eff[r] = needed ? (exempt ? S_MIN + 1 : q) : S_MIN;
+        o.sub[r] = q;
+        o.rq[r] = (named && v.guar) ? (int32_t)((uint64_t)v.req[r] / gm[r]) : 0;
+        o.rv[r] = (named && v.guar) ? (int32_t)((uint64_t)qty_value_h(v.req[r]) / gv[r]) : 0;
+        o.w[r] = named ? (int32_t)c->nrt_w[r] : 0;
+        wsum += (uint32_t)o.w[r];
+        if (needed) o.need |= (uint8_t)(1u << r);
+        if (named) o.nreq++;
+      }
+      o.wsum = wsum;
+      o.wmagic = magic_of(wsum);
+      o.guar = v.guar;
+      o.mask = v.mask;
+    }
+    std::vector<int32_t> pod_tc(std::max<size_t>(P * C_MAX, 1), -1), pod_tp(std::max<size_t>(P, 1), -1);
+    for (size_t p = 0; p < P; ++p) {
+      for (int cidx = 0; cidx < C_MAX; ++cidx) {
+        const int32_t u = s->pod_vec[p * (C_MAX + 1) + cidx];
+        if (u >= 0) pod_tc[p * C_MAX + cidx] = s->tc_of[(size_t)u];
+      }
+      const int32_t u = s->pod_vec[p * (C_MAX + 1) + C_MAX];
+      if (u >= 0) pod_tp[p] = s->tp_of[(size_t)u];
+    }
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> int {
+      B200S_CUDA_TRY(c, d.ensure(std::max<size_t>(bytes, 16)));
+      if (bytes) B200S_CUDA_TRY(c, cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+      return B200S_OK;
+    };
+    B200S_TRY(up(s->vecrec, recs.data(), recs.size() * sizeof(VecRec)));
+    B200S_TRY(up(s->d_pod_vec, s->pod_vec.data(), s->pod_vec.size() * 4));
+    B200S_TRY(up(s->d_pod_tc, pod_tc.data(), pod_tc.size() * 4));
+    B200S_TRY(up(s->d_pod_tp, pod_tp.data(), pod_tp.size() * 4));
+    B200S_TRY(up(s->d_tc_list, s->tc_list.data(), s->tc_list.size() * 4));
+    B200S_TRY(up(s->d_tp_list, s->tp_list.data(), s->tp_list.size() * 4));
+    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources die at return
+    s->prep_pods_serial = s->pods_serial;
+    s->prep_cfg = cfg;
+    memcpy(s->prep_gm, gm, sizeof(gm));
+    memcpy(s->prep_gv, gv, sizeof(gv));
+    s->prep_ok = true;
+  }
+  B200S_CUDA_TRY(c, s->Tc.ensure(tc_bytes));
+  B200S_CUDA_TRY(c, s->Tp.ensure(tp_bytes));
+  return 1;
+}
+
+namespace {
+template <int SC>
+void launch_tables(b200s_ctx* c, Nrt2* s) {
+  const int S = s->Sc + s->Sp;
+  TableArgs a;
+  a.vecs = s->vecrec.as<VecRec>();
+  a.S = S;
+  a.most = c->nrt_strategy == B200S_NRT_MOST_ALLOCATED;
+  if (!s->tc_list.empty() && s->Nc > 0) {
+    a.filt = s->filt.as<int32_t>();
+    a.capv = s->capv.as<int32_t>();
+    a.magic = s->magic.as<uint32_t>();
+    a.nzs = s->nzs.as<uint8_t>();
+    a.nrm = s->nrm.as<uint8_t>();
+    a.rows = s->d_tc_list.as<int32_t>();
+    a.nrows = (int)s->tc_list.size();
+    a.count = s->Sc;
+    dim3 grid((unsigned)(s->Sc / 128), (unsigned)((a.nrows + UT - 1) / UT));
+    nrt2_table_kernel<4, 4, SC, false><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint8_t>());
+    c->launches += 1;
+  }
+  if (!s->tp_list.empty() && s->Np > 0) {
+    a.filt = s->filt.as<int32_t>() + s->Sc;
+    a.capv = s->capv.as<int32_t>() + s->Sc;
+    a.magic = s->magic.as<uint32_t>() + s->Sc;
+    a.nzs = s->nzs.as<uint8_t>() + s->Sc;
+    a.nrm = s->nrm.as<uint8_t>() + s->Sc;
+    a.rows = s->d_tp_list.as<int32_t>();
+    a.nrows = (int)s->tp_list.size();
+    a.count = s->Sp;
+    dim3 grid((unsigned)(s->Sp / 128), (unsigned)((a.nrows + UT - 1) / UT));
+    nrt2_table_kernel<4, 4, SC, true><<<grid, 128, 0, c->stream>>>(a, s->Tp.as<uint8_t>());
+    c->launches += 1;
+  }
+}
+}  // namespace
+
+// Runs the batched path (nrt2_prepare returned 1; outputs ensured by the caller).
+int nrt2_eval(b200s_ctx* c, int dtype) {
+  Nrt2* s = nrt2_get(c);
+  PluginOut& o = c->out[B200S_PLUGIN_NRT];
+  if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION)
+    launch_tables<1>(c, s);
+  else
+    launch_tables<0>(c, s);
+  ExpandArgs a;
+  a.node_flags = c->nrt_node_flags.as<uint8_t>();
+  a.slot = s->slot.as<int32_t>();
+  a.tile_c0 = s->tile_c0.as<int32_t>();
+  a.filt = s->filt.as<int32_t>();
+  a.nrm = s->nrm.as<uint8_t>();
+  a.S = s->Sc + s->Sp;
+  a.Sc = s->Sc;
+  a.Sp = s->Sp;
+  a.qos = c->nrt_pod_qos.as<uint8_t>();
+  a.flags = c->nrt_pod_flags.as<uint8_t>();
+  a.n_init = c->nrt_pod_ninit.as<uint8_t>();
+  a.n_app = c->nrt_pod_napp.as<uint8_t>();
+  a.kind = c->nrt_pod_kind.as<uint8_t>();
+  a.pod_vec = s->d_pod_vec.as<int32_t>();
+  a.pod_tc = s->d_pod_tc.as<int32_t>();
+  a.pod_tp = s->d_pod_tp.as<int32_t>();
+  a.vecs = s->vecrec.as<VecRec>();
+  a.Tc = s->Tc.as<uint8_t>();
+  a.Tp = s->Tp.as<uint8_t>();
+  a.upstream = c->upstream_mask();
+  a.words = c->Npad / 64;
+  a.N = c->N;
+  a.Npad = c->Npad;
+  a.P = c->P;
+  dim3 grid((unsigned)((c->Npad + TILE - 1) / TILE), (unsigned)((c->P + PT - 1) / PT));
+  if (dtype == B200S_OUT_I64)
+    nrt2_expand_kernel<4, 4, int64_t><<<grid, TILE, 0, c->stream>>>(a, o.scores.as<int64_t>(), o.feas.as<uint32_t>(),
+                                                                    o.reasons.as<uint8_t>());
+  else
+    nrt2_expand_kernel<4, 4, uint8_t><<<grid, TILE, 0, c->stream>>>(a, o.scores.as<uint8_t>(), o.feas.as<uint32_t>(),
+                                                                    o.reasons.as<uint8_t>());
+  c->launches += 1;
+  B200S_CUDA_TRY(c, cudaGetLastError());
+  s->last_path = 2;
+  return B200S_OK;
+}
+
+}  // namespace b200s

@@ -58,14 +58,33 @@ __device__ double go_pow(double x, double y) {
 }
 
 // x / d for a divisor whose correctly rounded reciprocal r = RN(1/d) is hoisted out of the pod loop:
-// q0 = RN(x*r); rem = x - q0*d exactly (FMA); q1 = RN(q0 + rem*r) is the correctly rounded quotient
-// (Markstein's division-by-invariant; normal range, d finite and non-zero).  Replaces the ~35-instruction
-// IEEE division sequence by 3 fp64 ops and stays bit-identical to Go's x/d — checked exhaustively against
-// the hardware division by b200s_debug_div_check (tests/test_gpu_parity.py).
+//   q0 = RN(x*r);  rem = x - q0*d (exact in one FMA);  q1 = RN(q0 + rem*r).
+// When is q1 the correctly rounded quotient?  Markstein's theorem needs q0 FAITHFUL (one of the two neighbours of
+// x/d), and RN(x * RN(1/d)) can be 1.5 ulp off, so it does not hold for every divisor.  Brisebarre, Muller & Raina
+// ("Accelerating correctly rounded floating-point division when the divisor is known in advance", IEEE TC 53(8),
+// 2004, Theorem 4 on exactly this 1 multiplication + 2 FMA sequence) give sufficient conditions on the DIVISOR alone;
+// the first is: the last bit of d's significand is 0.  Every divisor on this path is an integer below 2^52 converted
+// to float64 (capacity in milli-cores, targetloadpacking.go:146; the target utilisation and its complement, :174-184;
+// allocatable milli-cores, resourcestats.go:55) or such an integer times 2^-20 (memory in MiB, resourcestats.go:60-64)
+// -- all have a zero last significand bit.  inv_for_div() checks that bit (and a moderate exponent) per divisor,
+// hoisted; a divisor that fails gets a NaN "reciprocal", which sends every division by it to the IEEE sequence.
+// The theorem also assumes no overflow / underflow: quotients outside [2^-800, 2^800] (and NaN, Inf, 0 -- e.g. an
+// infinite utilisation metric, where x*r - based steps would produce NaN but Go's x/d is +Inf) are recomputed with
+// the IEEE division as well.  b200s_debug_div_check compares against the hardware division on the device, on
+// random operands and on operands constructed at rounding boundaries (tests/test_gpu_divcheck.py).
+__device__ __forceinline__ double inv_for_div(double d) {
+  const long long b = __double_as_longlong(d);
+  const unsigned e = (unsigned)(b >> 52) & 0x7ffu;
+  const bool ok = !(b & 1) && e - 923u <= 200u;  // last significand bit 0, 2^-100 <= |d| < 2^101
+  return ok ? 1.0 / d : CUDART_NAN;
+}
 __device__ __forceinline__ double div_inv(double x, double d, double r) {
   const double q0 = x * r;
   const double rem = __fma_rn(-q0, d, x);
-  return __fma_rn(rem, r, q0);
+  double q1 = __fma_rn(rem, r, q0);
+  const unsigned e = ((unsigned)__double2hiint(q1) >> 20) & 0x7ffu;  // integer pipe, not fp64
+  if (e - 223u > 1600u) q1 = x / d;  // NaN / Inf / 0 / out of the theorem's range / ineligible divisor
+  return q1;
 }
 
 __global__ void div_check_kernel(const double* __restrict__ x, const double* __restrict__ d, int n,
@@ -73,7 +92,7 @@ __global__ void div_check_kernel(const double* __restrict__ x, const double* __r
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double want = x[i] / d[i];
-  const double got = div_inv(x[i], d[i], 1.0 / d[i]);
+  const double got = div_inv(x[i], d[i], inv_for_div(d[i]));
   if (__double_as_longlong(want) != __double_as_longlong(got) && !(want != want && got != got)) atomicAdd(mismatches, 1ull);
 }
 
@@ -95,7 +114,7 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
     for (int j = 0; j < NPT; ++j) {
       int n = nb + j;
       ncap[j] = (double)cap[n];
-      rcap[j] = 1.0 / ncap[j];
+      rcap[j] = inv_for_div(ncap[j]);
       base[j] = (util[n] / 100) * ncap[j];  // nodeCPUUtilMillis, :147
       miss[j] = (double)missing[n];
       uint8_t f = flags[n];
@@ -106,9 +125,8 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
   if (nb >= Npad) return;
   const double t = (double)target;
   const double hundred_minus_t = 100 - t;
-  const double r_t = 1.0 / t, r_hmt = 1.0 / hundred_minus_t;
-  // the reciprocal trick needs finite non-zero divisors; target 0 or 100 keeps the plain IEEE division
-  const bool fast_t = t >= 1 && t <= 99;
+  // target 0 or 100 (a zero divisor) gets a NaN reciprocal: div_inv then takes the IEEE division
+  const double r_t = inv_for_div(t), r_hmt = inv_for_div(hundred_minus_t);
   const int pend = min(PT, P - p0);
   OutT* orow = out + (size_t)p0 * Npad + nb;
   for (int pp = 0; pp < pend; ++pp, orow += Npad) {
@@ -123,7 +141,7 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
       const bool over = predicted > t;
       const double num = over ? t * (100 - predicted) : hundred_minus_t * predicted;
       const double d = over ? hundred_minus_t : t, r = over ? r_hmt : r_t;
-      double quo = fast_t ? div_inv(num, d, r) : num / d;
+      double quo = div_inv(num, d, r);
       quo = over ? quo : quo + t;                       // :183
       double s = go_round(quo);
       s = (over && predicted > 100) ? 0.0 : s;          // :175-177
@@ -142,7 +160,7 @@ __device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, 
                                               double sens) {
   LvrbNode r;
   r.cap = cap;
-  r.rcap = 1.0 / cap;
+  r.rcap = inv_for_div(cap);
   double used_avg = util_avg * cap / 100;  // resourcestats.go:68
   double used_std = util_std * cap / 100;  // :69
   r.avg = go_max(go_min(used_avg, cap), 0);

@@ -24,6 +24,7 @@ NRT_MOST_ALLOCATED, NRT_BALANCED_ALLOCATION, NRT_LEAST_ALLOCATED, NRT_LEAST_NUMA
 NODE_ALIGN = 128
 NRT_MAX_ZONES = NRT_MAX_RES = NRT_MAX_CONT = 8
 NETOH_MISSING = -(2**63)
+NRT_PATH_AUTO, NRT_PATH_DIRECT, NRT_PATH_BATCHED = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NCCL, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = [
@@ -41,6 +42,7 @@ EXPORTS = [
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
+    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note",
 ]
 
 
@@ -84,6 +86,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                           "(the engine has no CPU fallback)")
     lib = C.CDLL(path)
     lib.b200s_last_error.restype = C.c_char_p
+    lib.b200s_nrt_path_note.restype = C.c_char_p
     lib.b200s_stream.restype = C.c_void_p
     lib.b200s_launch_count.restype = C.c_uint64
     lib.b200s_device_scores.restype = C.c_void_p
@@ -373,6 +376,16 @@ class Engine:
         w = _arr(weights if weights is not None else [], np.int64)
         self._chk(self.lib.b200s_config_nrt(self.ctx, C.c_int(strategy), C.c_int32(len(w)),
                                             _ptr(w) if len(w) else None))
+
+    def config_nrt_path(self, path):
+        """NRT_PATH_AUTO / NRT_PATH_DIRECT / NRT_PATH_BATCHED (include/b200sched.h)."""
+        self._chk(self.lib.b200s_config_nrt_path(self.ctx, C.c_int(path)))
+
+    def nrt_last_path(self):
+        return int(self.lib.b200s_nrt_last_path(self.ctx))
+
+    def nrt_path_note(self):
+        return (self.lib.b200s_nrt_path_note(self.ctx) or b"").decode()
 
     # -- pods -----------------------------------------------------------------------------
     def make_batch(self, n_pods, feasible=None, tlp_pod_cpu_milli=None, lvrb_req_cpu_milli=None,

@@ -166,6 +166,7 @@ PYBIND11_MODULE(_b200host, m) {
       .def("pre_score", &Allocatable::PreScore)
       .def("score", &Allocatable::Score)
       .def("patched_rows", &Allocatable::PatchedRows)
+      .def("debug_leave_patch_open", &Allocatable::DebugLeavePatchOpen)
       .def("normalize_score", [](Allocatable& a, CycleState& s, const Pod& p, std::vector<NodeScore> l) {
         Status st = a.NormalizeScore(s, p, l);
         return std::make_pair(st, l);

@@ -142,10 +142,17 @@ bool Allocatable::PatchSnapshot() {
       for (size_t r = 0; r < res_.size(); ++r) cols[r][j] = AllocatableColumn(*nd, res_[r].name);
   std::vector<const int64_t*> ptrs;
   for (auto& c : cols) ptrs.push_back(c.data());
-  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
-  eng_->Check(b200s_snapshot_patch_allocatable(eng_->ctx(), (int32_t)idx.size(), idx.data(), (int32_t)ptrs.size(), ptrs.data()),
-              "snapshot_patch_allocatable");
-  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  // A failed patch (allocation, CUDA error, size check) leaves the engine's snapshot open and half rewritten:
+  // report "not patched" so that EnsureSnapshot does the full b200s_snapshot_begin upload, which resets it.
+  try {
+    eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+    eng_->Check(b200s_snapshot_patch_allocatable(eng_->ctx(), (int32_t)idx.size(), idx.data(), (int32_t)ptrs.size(), ptrs.data()),
+                "snapshot_patch_allocatable");
+    eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  } catch (const std::exception&) {
+    snap_gen_ = 0;
+    return false;
+  }
   snap_gen_ = h_->generation;
   patched_rows_ += (int64_t)idx.size();
   return true;
@@ -276,11 +283,18 @@ bool TargetLoadPacking::PatchSnapshot() {
     const Row row = FlattenRow(ni);
     util[j] = row.util, cap[j] = row.cap, missing[j] = row.missing, flags[j] = row.flags;
   }
-  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
-  eng_->Check(b200s_snapshot_patch_tlp(eng_->ctx(), (int32_t)idx.size(), idx.data(), util.data(), cap.data(), missing.data(),
-                                       flags.data()),
-              "snapshot_patch_tlp");
-  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  // A failed patch (allocation, CUDA error, size check) leaves the engine's snapshot open and half rewritten:
+  // report "not patched" so that EnsureSnapshot does the full b200s_snapshot_begin upload, which resets it.
+  try {
+    eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+    eng_->Check(b200s_snapshot_patch_tlp(eng_->ctx(), (int32_t)idx.size(), idx.data(), util.data(), cap.data(), missing.data(),
+                                         flags.data()),
+                "snapshot_patch_tlp");
+    eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  } catch (const std::exception&) {
+    snap_gen_ = 0;
+    return false;
+  }
   snap_gen_ = h_->generation;
   patched_rows_ += (int64_t)idx.size();
   return true;
@@ -388,11 +402,18 @@ bool LoadVariationRiskBalancing::PatchSnapshot() {
     const Row row = FlattenRow(ni);
     ca[j] = row.ca, cs[j] = row.cs, ma[j] = row.ma, ms[j] = row.ms, acpu[j] = row.acpu, amem[j] = row.amem, flags[j] = row.flags;
   }
-  eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
-  eng_->Check(b200s_snapshot_patch_lvrb(eng_->ctx(), (int32_t)idx.size(), idx.data(), ca.data(), cs.data(), ma.data(), ms.data(),
-                                        acpu.data(), amem.data(), flags.data()),
-              "snapshot_patch_lvrb");
-  eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  // A failed patch (allocation, CUDA error, size check) leaves the engine's snapshot open and half rewritten:
+  // report "not patched" so that EnsureSnapshot does the full b200s_snapshot_begin upload, which resets it.
+  try {
+    eng_->Check(b200s_snapshot_patch_begin(eng_->ctx(), h_->generation), "snapshot_patch_begin");
+    eng_->Check(b200s_snapshot_patch_lvrb(eng_->ctx(), (int32_t)idx.size(), idx.data(), ca.data(), cs.data(), ma.data(), ms.data(),
+                                          acpu.data(), amem.data(), flags.data()),
+                "snapshot_patch_lvrb");
+    eng_->Check(b200s_snapshot_commit(eng_->ctx()), "snapshot_commit");
+  } catch (const std::exception&) {
+    snap_gen_ = 0;
+    return false;
+  }
   snap_gen_ = h_->generation;
   patched_rows_ += (int64_t)idx.size();
   return true;

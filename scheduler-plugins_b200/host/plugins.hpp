@@ -124,6 +124,8 @@ class Allocatable {
 
  public:
   int64_t PatchedRows() const { return patched_rows_; }  // rows rewritten through b200s_snapshot_patch_* so far
+  // test hook (fault injection): leaves a patch open on the engine, as a patch that failed half-way would
+  int DebugLeavePatchOpen() { return b200s_snapshot_patch_begin(eng_->ctx(), 0); }
 
  private:
   std::shared_ptr<CycleResult> Run(const Pod& pod, const std::vector<NodeInfo>* feasible);

@@ -379,6 +379,25 @@ def test_incremental_snapshot_allocatable(H):
     assert _scores(p, H, pod, fh) == after and p.patched_rows() == 2
 
 
+def test_incremental_snapshot_survives_a_failed_patch(H):
+    """A patch that fails half-way leaves the engine's snapshot open; the plugin must fall back to the full upload
+    (which resets it) instead of returning an Error status for every later cycle."""
+    nodes = [make_node(H, f"machine{i}", {"cpu": f"{1000 * (i % 7 + 1)}m", "memory": str((i % 5 + 1) << 30)}) for i in range(40)]
+    fh = handle_with(H, nodes)
+    p = H.Allocatable.new(None, fh)
+    pod = make_pod(H, {})
+    _scores(p, H, pod, fh)
+    nodes[5].allocatable = H.resource_list({"cpu": "64000m", "memory": str(1 << 30)})
+    fh.touch_node(5)
+    assert p.debug_leave_patch_open() == 0            # the engine now refuses b200s_snapshot_patch_begin
+    after = _scores(p, H, pod, fh)                    # ... and the plugin recovers through the bulk path
+    assert p.patched_rows() == 0
+    assert after == _scores(H.Allocatable.new(None, fh), H, pod, fh)
+    nodes[6].allocatable = H.resource_list({"cpu": "100m", "memory": str(1 << 30)})
+    fh.touch_node(6)
+    assert _scores(p, H, pod, fh) == _scores(H.Allocatable.new(None, fh), H, pod, fh) and p.patched_rows() == 1
+
+
 def test_incremental_snapshot_trimaran_bind(H):
     """handler.go:131-167: a bind adds the pod to ScheduledPodsCache[node]; only that node's missing-utilisation
     changes, so TargetLoadPacking patches one row.  LoadVariationRiskBalancing follows node allocatable changes."""

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Condenses `ncu --page raw --csv` exports (one row per captured launch) into the handful of numbers DESIGN.md and
+the judge quote: duration, DRAM bytes, issue-slot use, pipe use, occupancy, lanes per instruction, sectors per global
+store request, registers and the leading stall reason.  Usage: ncu_summary.py out.json a_raw.csv [b_raw.csv ...]"""
+import csv
+import json
+import sys
+
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3,
+        "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}
+
+
+def num(v):
+    try:
+        return float(v.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def summarize(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in data:
+        def g(name, scale=True):
+            i = col.get(name)
+            if i is None or i >= len(r):
+                return None
+            v = num(r[i])
+            if v is None:
+                return None
+            return v * UNIT.get(units[i], 1) if scale else v
+        stalls = {h.split("issue_stalled_")[1].split("_per_issue")[0]: num(r[i]) for h, i in col.items()
+                  if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")
+                  and "selected" not in h and num(r[i]) is not None}
+        top = sorted(stalls.items(), key=lambda kv: -kv[1])[:3]
+        out.append(dict(
+            kernel=r[col["Kernel Name"]].replace("void unnamed>::", ""),
+            grid=[int(g("launch__grid_dim_x", False) or 0), int(g("launch__grid_dim_y", False) or 0)],
+            block=int(g("launch__block_size", False) or 0),
+            registers=int(g("launch__registers_per_thread", False) or 0),
+            duration_ms=g("gpu__time_duration.sum"),
+            dram_read_bytes=g("dram__bytes_read.sum"), dram_write_bytes=g("dram__bytes_write.sum"),
+            dram_pct_of_peak=g("dram__throughput.avg.pct_of_peak_sustained_elapsed", False),
+            issue_active_pct=g("sm__issue_active.avg.pct_of_peak_sustained_elapsed", False),
+            warp_instructions=g("smsp__inst_executed.sum", False),
+            lanes_per_instruction=g("smsp__thread_inst_executed_per_inst_executed.ratio", False),
+            occupancy_pct=g("sm__warps_active.avg.pct_of_peak_sustained_active", False),
+            pipe_fp64_pct=g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", False),
+            pipe_alu_pct=g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", False),
+            pipe_fma_pct=g("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", False),
+            pipe_lsu_pct=g("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", False),
+            st_sectors_per_request=g("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio", False),
+            ld_sectors_per_request=g("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio", False),
+            l2_hit_pct=g("lts__t_sector_hit_rate.pct", False),
+            top_stalls=[[k, round(v, 3)] for k, v in top], source=path.split("/")[-1]))
+    return out
+
+
+if __name__ == "__main__":
+    res = []
+    for p in sys.argv[2:]:
+        res += summarize(p)
+    json.dump(res, open(sys.argv[1], "w"), indent=1)
+    for k in res:
+        print(json.dumps({a: (round(b, 4) if isinstance(b, float) else b) for a, b in k.items()}))
