@@ -279,7 +279,8 @@ int b200s_config_nrt(b200s_ctx* ctx, int strategy, int32_t n_res, const int64_t*
 #define B200S_NRT_PATH_BATCHED 2 /* also for P < 32; still falls back to DIRECT where the path does not apply */
 int b200s_config_nrt_path(b200s_ctx* ctx, int path);
 int b200s_nrt_last_path(b200s_ctx* ctx); /* 0 = none yet, else B200S_NRT_PATH_DIRECT / _BATCHED */
-/* why the last eval declined the batched path ("" if it ran); a static string, valid for the life of the library */
+/* why the last eval declined the batched path ("" if it ran, or a remark on the variant that ran); a static string,
+ * valid for the life of the library */
 const char* b200s_nrt_path_note(b200s_ctx* ctx);
 /* NetworkOverhead: want_counts != 0 also keeps PreFilterState.satisfiedMap / violatedMap
  * (networkoverhead.go:283-296) for the Filter status message.  apply_own_filter (default 1): the

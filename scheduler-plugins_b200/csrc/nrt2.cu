@@ -15,7 +15,8 @@
 //    machine; it runs on the container-scope nodes only, in 32-bit arithmetic on gcd-scaled quantities.
 //  * nodes are split by control-flow class into two ORDER-PRESERVING compact lists (container-scope / pod-scope
 //    nodes that reach a handler); every other node is decided by its flags.  A CTA of the P x N kernel owns a tile of
-//    256 NATURAL node indices: the container-scope nodes of the tile are a contiguous slot range, their results are
+//    consecutive NATURAL node indices cut (on the host, at 32-node boundaries) so that it holds at most 256
+//    container-scope nodes -- one per thread for the state machine, a contiguous slot range; their results are
 //    staged in shared memory, and the expansion to the [P][Npad] score / reason / feasibility outputs is written in
 //    natural order with fully coalesced rows (round 1's permuted kernel scattered them: 30.9 sectors per request).
 //
@@ -36,12 +37,14 @@ namespace b200s {
 namespace {
 
 constexpr int C_MAX = B200S_NRT_MAX_CONT;
-constexpr int TILE = 256;  // natural node indices per CTA of the P x N kernel
+constexpr int TILE = 256;      // threads per CTA of the P x N kernel = most container-scope slots of one tile
+constexpr int TILE_SPAN = 1024;  // most natural node indices of one tile
 constexpr int PT = 32;     // pods per CTA
 constexpr int UT = 32;     // request vectors per CTA of the table kernel
 constexpr int32_t S_MIN = INT32_MIN, S_MAX = INT32_MAX;
 constexpr int64_t LIM_MILLI = (int64_t)1 << 30;  // scaled milli quantities stay below (sentinels are +-2^31)
-constexpr int64_t LIM_VALUE = 42000000;          // scaled Value() quantities: x100 stays below 2^32
+constexpr int64_t LIM_VALUE = 42000000;          // scaled Value() quantities: x100 stays below 2^32 (32-bit ratio path)
+constexpr int64_t LIM_VALUE_WIDE = (int64_t)1 << 31;  // beyond that, up to here: 64-bit numerator (WIDE table kernel)
 
 // One distinct request vector of the batch, scaled (device record, 96 bytes).
 struct alignas(16) VecRec {
@@ -96,10 +99,12 @@ struct Nrt2 {
   bool neg = false;          // a listed Available is negative: the scaled encoding does not apply
   bool lists_valid = false;  // class lists match the flags mirror
   int Nc = 0, Np = 0, Sc = 0, Sp = 0;  // container-scope / pod-scope handler nodes; padded to 128
-  DevBuf slot, list, tile_c0;          // [Npad] int32, [Sc + Sp] int32, [Npad / TILE + 1] int32
+  DevBuf slot, list, tile_n0, tile_c0;  // [Npad] int32, [Sc + Sp] int32, [tiles + 1] first node / first container slot
+  int n_tiles = 0;
   DevBuf filt, capv, magic, nzs, nrm;  // [Z][R][S] int32 x3, [S] u8 x2 (node columns of the two lists, scaled)
   uint64_t node_prep_serial = ~0ull;
   uint64_t node_prep_gm[4] = {0, 0, 0, 0}, node_prep_gv[4] = {0, 0, 0, 0};
+  bool wide = false, node_prep_wide = false;  // a scaled Value() needs the 64-bit numerator form of the ratio
   // ---- pod side (host dictionary, built at pods_upload)
   bool pods_ok = false;  // the batch fits the path (shape, signs, QoS consistency)
   const char* pods_note = "no NodeResourceTopologyMatch pod columns";
@@ -121,7 +126,7 @@ struct Nrt2 {
   const char* note = "";  // why the batched path was declined last time (static string)
   int force = 0;      // 0 auto, 1 direct, 2 table when applicable
   ~Nrt2() {
-    for (DevBuf* b : {&slot, &list, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
+    for (DevBuf* b : {&slot, &list, &tile_n0, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
                       &d_tc_list, &d_tp_list, &Tc, &Tp})
       b->release();
   }
@@ -309,6 +314,7 @@ struct NodePrepArgs {
   int Zs, Rs, Npad, S;
   uint64_t gm[4], gv[4];
   uint8_t res_flags[4];
+  int wide;  // magic column holds the fp32 reciprocal bits instead of floor(2^32 / capv)
 };
 
 // One thread per slot of the two class lists: the node's zones x resources block in the scaled encodings.
@@ -351,7 +357,8 @@ __global__ void nrt2_node_prep_kernel(NodePrepArgs a, int32_t* __restrict__ filt
       const size_t o = ((size_t)z * R + r) * a.S + s;
       filt[o] = f;
       capv[o] = cv;
-      magic[o] = cv <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / (uint32_t)cv);
+      magic[o] = a.wide ? __float_as_uint(1.0f / (float)(cv == 0 ? 1 : cv))
+                        : (cv <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / (uint32_t)cv));
     }
   }
 }
@@ -362,6 +369,16 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t num, uint32_t d, uint32_t
   uint32_t q = __umulhi(num, m);
   const uint32_t rem = num - q * d;
   return rem >= d ? q + 1 : q;
+}
+// floor(a * 100 / cv) for 0 <= a <= cv < 2^31 with rcv ~ 1/cv in fp32: the fp32 estimate of a quotient <= 100 is
+// off by far less than 1 (relative error < 2^-20), so after truncation it is the quotient or a neighbour; the exact
+// 64-bit residual decides.
+__device__ __forceinline__ uint32_t div100_wide(uint32_t a, uint32_t cv, float rcv) {
+  const uint64_t num = (uint64_t)a * 100u;
+  uint32_t q = (uint32_t)((float)a * 100.0f * rcv);
+  const int64_t rem = (int64_t)num - (int64_t)((uint64_t)q * cv);
+  q = rem < 0 ? q - 1 : (rem >= (int64_t)cv ? q + 1 : q);
+  return q;
 }
 __device__ __forceinline__ int64_t f2i(double x) {
   if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
@@ -386,7 +403,7 @@ struct TableArgs {
 // vectors come from shared memory (warp-uniform).  POD: the table of the pod-scope nodes -- entry = score (100 for a
 // non-Guaranteed vector, score.go:72-75) if resourcesAvailableInAnyNUMANodes finds a zone (filter.go:162-173), else
 // 128 + B200S_REASON_NRT_ALIGN_POD.  Otherwise the score table of the container-scope nodes.
-template <int Z, int R, int SC, bool POD>
+template <int Z, int R, int SC, bool POD, bool WIDE>
 __global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* __restrict__ T) {
   __shared__ VecRec sv[UT];
   const int row0 = blockIdx.y * UT, nrow = min(UT, a.nrows - row0);
@@ -469,8 +486,9 @@ __global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* _
           for (int r = 0; r < R; ++r) {
             const int32_t c = cv[z][r];
             const bool zero = c == 0 || v.rq[r] > filt[z][r];  // capacity 0 (or resource missing) or request > capacity
-            const uint32_t num = (uint32_t)(a.most ? v.rv[r] : c - v.rv[r]) * 100u;
-            const uint32_t q = div_magic(zero ? 0u : num, (uint32_t)(c == 0 ? 1 : c), mg[z][r]);
+            const uint32_t av = zero ? 0u : (uint32_t)(a.most ? v.rv[r] : c - v.rv[r]);
+            const uint32_t q = WIDE ? div100_wide(av, (uint32_t)(c == 0 ? 1 : c), __uint_as_float(mg[z][r]))
+                                    : div_magic(av * 100u, (uint32_t)(c == 0 ? 1 : c), mg[z][r]);
             acc += q * (uint32_t)v.w[r];
           }
           s = v.wsum == 0 ? 0 : (int32_t)div_magic(acc, v.wsum, v.wmagic);
@@ -490,7 +508,8 @@ struct ExpandArgs {
   // node side
   const uint8_t* node_flags;  // [Npad]
   const int32_t* slot;        // [Npad] class-local slot
-  const int32_t* tile_c0;     // [Npad / TILE + 1]
+  const int32_t* tile_n0;     // [tiles + 1] first natural node index of the tile (multiple of 32)
+  const int32_t* tile_c0;     // [tiles + 1] first container-scope slot of the tile
   const int32_t* filt;        // container-scope slots, stride S
   const uint8_t* nrm;
   int S;
@@ -518,11 +537,13 @@ struct PodMeta {
   int32_t tp;
 };
 
-// The P x N pass.  Phase 1: the container-scope nodes of this tile (a contiguous slot range) run the first-fit state
-// machine of singleNUMAContainerLevelHandler (filter.go:39-78) per pod and gather the container-scope score
-// (score.go:152-165) from Tc; one byte per (pod, slot) goes to shared memory (< 128: feasible with that score,
-// >= 128: 128 + reason).  Phase 2: every thread owns one NATURAL node index and expands pod by pod -- flag-decided
-// nodes, pod-scope nodes (one byte of Tp), container-scope nodes (the staged byte) -- into coalesced rows.
+// The P x N pass.  Phase 1: the container-scope nodes of this tile (a contiguous slot range, one per thread) run the
+// first-fit state machine of singleNUMAContainerLevelHandler (filter.go:39-78) per pod and gather the
+// container-scope score (score.go:152-165) from Tc; one byte per (pod, slot) goes to shared memory (< 128: feasible
+// with that score, >= 128: 128 + reason).  Phase 2: the threads sweep the tile's NATURAL node indices and expand pod
+// by pod -- flag-decided nodes, pod-scope nodes (one byte of Tp), container-scope nodes (the staged byte) -- into
+// coalesced rows.  All pod data is warp-uniform (shared-memory broadcasts, uniform branches): resources a container
+// does not request are skipped for the whole warp.
 template <int Z, int R, class OutT>
 __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* __restrict__ out,
                                                            uint32_t* __restrict__ feas32, uint8_t* __restrict__ reasons) {
@@ -564,6 +585,7 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
     s_meta[i].n_app = a.n_app[p];
     s_meta[i].tp = a.pod_tp[p];
   }
+  const int n0 = a.tile_n0[blockIdx.x], n1 = a.tile_n0[blockIdx.x + 1];
   const int c0 = a.tile_c0[blockIdx.x], ncs = a.tile_c0[blockIdx.x + 1] - c0;
   __syncthreads();
   if (tid < ncs) {
@@ -588,20 +610,19 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
         for (int r = 0; r < R; ++r) zs[z][r] = node[z][r];
       uint32_t reason = 0;
       for (int s = 0; s < steps; ++s) {
-        int32_t e[R], sb[R];
+        bool fit[Z];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) fit[z] = true;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          e[r] = s_eff[pp][s][r];
-          sb[r] = nolist[r] ? 0 : s_sub[pp][s][r];
+          const int32_t e = s_eff[pp][s][r];
+          if (e == S_MIN) continue;  // not requested / zero: constrains nothing (warp-uniform)
+#pragma unroll
+          for (int z = 0; z < Z; ++z) fit[z] &= zs[z][r] >= e;
         }
         uint32_t ok = 0;
 #pragma unroll
-        for (int z = 0; z < Z; ++z) {
-          bool fits = true;
-#pragma unroll
-          for (int r = 0; r < R; ++r) fits &= zs[z][r] >= e[r];
-          ok |= (fits ? 1u : 0u) << z;
-        }
+        for (int z = 0; z < Z; ++z) ok |= (fit[z] ? 1u : 0u) << z;
         if (m.need[s] & ~nrm) ok = 0;  // :107-113
         const uint32_t code = s >= n_init ? B200S_REASON_NRT_ALIGN_CONTAINER
                                           : (m.kind[s] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR
@@ -610,9 +631,13 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
         if (s >= n_init) {  // subtractResourcesFromNUMANodeList (numaresources.go:145-182) on the lowest fitting id
           const int id = __ffs(ok) - 1;
 #pragma unroll
-          for (int z = 0; z < Z; ++z)
+          for (int r = 0; r < R; ++r) {
+            const int32_t q = s_sub[pp][s][r];
+            if (q == 0) continue;  // warp-uniform
+            const int32_t qq = nolist[r] ? 0 : q;
 #pragma unroll
-            for (int r = 0; r < R; ++r) zs[z][r] -= (z == id) ? sb[r] : 0;
+            for (int z = 0; z < Z; ++z) zs[z][r] -= (z == id) ? qq : 0;
+          }
         }
       }
       uint32_t v = 128u + reason;
@@ -628,50 +653,51 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
     }
   }
   __syncthreads();
-  const int n = blockIdx.x * TILE + tid;
-  if (n >= a.Npad) return;
-  const uint32_t nfl = n < a.N ? a.node_flags[n] : 0u;
-  const int slot = a.slot[n];
-  const bool fresh = nfl & B200S_NRT_NODE_FRESH, handler = slot >= 0;
-  const bool pod_scope = nfl & B200S_NRT_NODE_SCOPE_POD;
-  const bool trivial_ok = !(nfl & B200S_NRT_NODE_HAS_NRT) || !(nfl & B200S_NRT_NODE_SINGLE_NUMA);
-  const int word = n >> 6;
-  for (int pp = 0; pp < pend; ++pp) {
-    const int p = p0 + pp;
-    const PodMeta& m = s_meta[pp];
-    uint32_t reason = 0, score = 0;
-    bool feasible = false;
-    if (n < a.N) {
-      const bool guar = m.qos == B200S_QOS_GUARANTEED;
-      uint32_t v;
-      if (m.flags & B200S_NRT_POD_FILTER_BYPASS) v = 100;                                  // filter.go:180-183
-      else if (!fresh) v = 128u + B200S_REASON_NRT_INVALID_TOPOLOGY;                       // :194-197
-      else if (trivial_ok) v = guar ? 0u : 100u;                                           // :198-209; score.go:83-94
-      else if (!handler || (m.flags & B200S_NRT_POD_UNSUPPORTED)) v = 128u + B200S_REASON_UNSUPPORTED;
-      else if (pod_scope) v = a.Tp[(size_t)m.tp * a.Sp + slot];
-      else v = s_v[pp][slot - c0];
-      reason = v >= 128u ? v - 128u : 0u;
-      const bool up = a.upstream ? ((a.upstream[(size_t)p * a.words + word] >> (n & 63)) & 1ull) : true;
-      feasible = reason == 0 && up;
-      if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
-      score = feasible ? v : 0u;
+  // n0 and n1 are multiples of 32: a warp is entirely inside or outside the tile (the ballot below needs full warps)
+  for (int n = n0 + tid; n < n1; n += TILE) {
+    const uint32_t nfl = n < a.N ? a.node_flags[n] : 0u;
+    const int slot = a.slot[n];
+    const bool fresh = nfl & B200S_NRT_NODE_FRESH, handler = slot >= 0;
+    const bool pod_scope = nfl & B200S_NRT_NODE_SCOPE_POD;
+    const bool trivial_ok = !(nfl & B200S_NRT_NODE_HAS_NRT) || !(nfl & B200S_NRT_NODE_SINGLE_NUMA);
+    const int word = n >> 6;
+    for (int pp = 0; pp < pend; ++pp) {
+      const int p = p0 + pp;
+      const PodMeta& m = s_meta[pp];
+      uint32_t reason = 0, score = 0;
+      bool feasible = false;
+      if (n < a.N) {
+        const bool guar = m.qos == B200S_QOS_GUARANTEED;
+        uint32_t v;
+        if (m.flags & B200S_NRT_POD_FILTER_BYPASS) v = 100;                                  // filter.go:180-183
+        else if (!fresh) v = 128u + B200S_REASON_NRT_INVALID_TOPOLOGY;                       // :194-197
+        else if (trivial_ok) v = guar ? 0u : 100u;                                           // :198-209; score.go:83-94
+        else if (!handler || (m.flags & B200S_NRT_POD_UNSUPPORTED)) v = 128u + B200S_REASON_UNSUPPORTED;
+        else if (pod_scope) v = a.Tp[(size_t)m.tp * a.Sp + slot];
+        else v = s_v[pp][slot - c0];
+        reason = v >= 128u ? v - 128u : 0u;
+        const bool up = a.upstream ? ((a.upstream[(size_t)p * a.words + word] >> (n & 63)) & 1ull) : true;
+        feasible = reason == 0 && up;
+        if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
+        score = feasible ? v : 0u;
+      }
+      const size_t o = (size_t)p * a.Npad + n;
+      out[o] = (OutT)score;
+      reasons[o] = (uint8_t)reason;
+      const uint32_t w = __ballot_sync(0xffffffffu, feasible);
+      if ((tid & 31) == 0) feas32[o >> 5] = w;
     }
-    const size_t o = (size_t)p * a.Npad + n;
-    out[o] = (OutT)score;
-    reasons[o] = (uint8_t)reason;
-    const uint32_t w = __ballot_sync(0xffffffffu, feasible);
-    if ((tid & 31) == 0) feas32[o >> 5] = w;
   }
 }
 
 int build_lists(b200s_ctx* c, Nrt2* s) {
-  const int N = c->N, Npad = c->Npad, ntiles = (Npad + TILE - 1) / TILE;
-  std::vector<int32_t> slot((size_t)Npad, -1), tile_c0((size_t)ntiles + 1, 0), clist, plist;
+  const int N = c->N, Npad = c->Npad;
+  std::vector<int32_t> slot((size_t)Npad, -1), clist, plist;
+  std::vector<uint8_t> is_c((size_t)Npad, 0);
   clist.reserve((size_t)N);
   plist.reserve((size_t)N);
   constexpr uint32_t need = B200S_NRT_NODE_FRESH | B200S_NRT_NODE_HAS_NRT | B200S_NRT_NODE_SINGLE_NUMA;
   for (int n = 0; n < N; ++n) {
-    if (n % TILE == 0) tile_c0[(size_t)(n / TILE)] = (int32_t)clist.size();
     const uint32_t fl = (uint32_t)((c->nrt_key_h[(size_t)n] >> 48) & 0xFF);
     if ((fl & need) != need || (fl & B200S_NRT_NODE_UNSUPPORTED)) continue;
     if (fl & B200S_NRT_NODE_SCOPE_POD) {
@@ -680,9 +706,30 @@ int build_lists(b200s_ctx* c, Nrt2* s) {
     } else {
       slot[(size_t)n] = (int32_t)clist.size();
       clist.push_back(n);
+      is_c[(size_t)n] = 1;
     }
   }
-  for (int t = (N + TILE - 1) / TILE; t <= ntiles; ++t) tile_c0[(size_t)t] = (int32_t)clist.size();
+  // tiles of the P x N kernel: consecutive 32-node groups, at most TILE container-scope nodes (one state machine per
+  // thread) and at most TILE_SPAN nodes each
+  std::vector<int32_t> tile_n0, tile_c0;
+  int32_t cs = 0;
+  for (int n = 0; n < Npad;) {
+    tile_n0.push_back(n);
+    tile_c0.push_back(cs);
+    int in_tile = 0;
+    const int start = n;
+    while (n < Npad && n - start < TILE_SPAN) {
+      int cnt = 0;
+      for (int j = n; j < n + 32; ++j) cnt += is_c[(size_t)j];
+      if (in_tile + cnt > TILE) break;
+      in_tile += cnt;
+      n += 32;
+    }
+    cs += in_tile;
+  }
+  tile_n0.push_back(Npad);
+  tile_c0.push_back(cs);
+  s->n_tiles = (int)tile_n0.size() - 1;
   s->Nc = (int)clist.size();
   s->Np = (int)plist.size();
   s->Sc = round_up(std::max(s->Nc, 1), 128);
@@ -692,9 +739,11 @@ int build_lists(b200s_ctx* c, Nrt2* s) {
   std::copy(plist.begin(), plist.end(), list.begin() + s->Sc);
   B200S_CUDA_TRY(c, s->slot.ensure((size_t)Npad * 4));
   B200S_CUDA_TRY(c, s->list.ensure(list.size() * 4));
+  B200S_CUDA_TRY(c, s->tile_n0.ensure(tile_n0.size() * 4));
   B200S_CUDA_TRY(c, s->tile_c0.ensure(tile_c0.size() * 4));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(s->slot.p, slot.data(), (size_t)Npad * 4, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(s->list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(s->tile_n0.p, tile_n0.data(), tile_n0.size() * 4, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaMemcpyAsync(s->tile_c0.p, tile_c0.data(), tile_c0.size() * 4, cudaMemcpyHostToDevice, c->stream));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources die at return
   s->lists_valid = true;
@@ -728,6 +777,7 @@ int nrt2_prepare(b200s_ctx* c) {
   }
   if (wtot * 100 >= ((int64_t)1 << 31)) return decline("resource weights too large");
   uint64_t gm[4] = {1, 1, 1, 1}, gv[4] = {1, 1, 1, 1};
+  bool wide = false;
   for (int r = 0; r < R; ++r) {
     gm[r] = gcd_u64(s->gm[r], s->pgm[r]);
     gv[r] = gcd_u64(s->gv[r], s->pgv[r]);
@@ -735,15 +785,18 @@ int nrt2_prepare(b200s_ctx* c) {
     if (gv[r] == 0) gv[r] = 1;
     const int64_t mx = std::max(s->maxm[r], s->pmaxm[r]);
     if (mx / (int64_t)gm[r] >= LIM_MILLI) return decline("a quantity does not fit 30 bits after gcd scaling");
-    if (qty_value_h(mx) / (int64_t)gv[r] >= LIM_VALUE) return decline("a Value() does not fit after gcd scaling");
+    if (qty_value_h(mx) / (int64_t)gv[r] >= LIM_VALUE_WIDE) return decline("a Value() does not fit 31 bits after gcd scaling");
+    if (qty_value_h(mx) / (int64_t)gv[r] >= LIM_VALUE) wide = true;
   }
+  s->wide = wide;
+  if (wide) s->note = "batched, 64-bit Value() ratios";
   if (!s->lists_valid) B200S_TRY(build_lists(c, s));
   const size_t S = (size_t)s->Sc + s->Sp;
   const size_t tc_bytes = (size_t)std::max<size_t>(s->tc_list.size(), 1) * s->Sc;
   const size_t tp_bytes = (size_t)std::max<size_t>(s->tp_list.size(), 1) * s->Sp;
   if (tc_bytes + tp_bytes > ((size_t)16 << 30)) return decline("score tables above 16 GiB");
   // node columns of the two lists in the scaled encodings (per snapshot and scale)
-  if (s->node_prep_serial != c->snap_serial || memcmp(s->node_prep_gm, gm, sizeof(gm)) != 0 ||
+  if (s->node_prep_serial != c->snap_serial || s->node_prep_wide != wide || memcmp(s->node_prep_gm, gm, sizeof(gm)) != 0 ||
       memcmp(s->node_prep_gv, gv, sizeof(gv)) != 0) {
     B200S_CUDA_TRY(c, s->filt.ensure(16 * S * 4));
     B200S_CUDA_TRY(c, s->capv.ensure(16 * S * 4));
@@ -761,6 +814,7 @@ int nrt2_prepare(b200s_ctx* c) {
     a.Rs = R;
     a.Npad = c->Npad;
     a.S = (int)S;
+    a.wide = wide ? 1 : 0;
     for (int r = 0; r < 4; ++r) {
       a.gm[r] = gm[r];
       a.gv[r] = gv[r];
@@ -772,6 +826,7 @@ int nrt2_prepare(b200s_ctx* c) {
     c->launches += 1;
     B200S_CUDA_TRY(c, cudaGetLastError());
     s->node_prep_serial = c->snap_serial;
+    s->node_prep_wide = wide;
     memcpy(s->node_prep_gm, gm, sizeof(gm));
     memcpy(s->node_prep_gv, gv, sizeof(gv));
   }
@@ -839,7 +894,7 @@ int nrt2_prepare(b200s_ctx* c) {
 }
 
 namespace {
-template <int SC>
+template <int SC, bool WIDE>
 void launch_tables(b200s_ctx* c, Nrt2* s) {
   const int S = s->Sc + s->Sp;
   TableArgs a;
@@ -856,7 +911,7 @@ void launch_tables(b200s_ctx* c, Nrt2* s) {
     a.nrows = (int)s->tc_list.size();
     a.count = s->Sc;
     dim3 grid((unsigned)(s->Sc / 128), (unsigned)((a.nrows + UT - 1) / UT));
-    nrt2_table_kernel<4, 4, SC, false><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint8_t>());
+    nrt2_table_kernel<4, 4, SC, false, WIDE><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint8_t>());
     c->launches += 1;
   }
   if (!s->tp_list.empty() && s->Np > 0) {
@@ -869,7 +924,7 @@ void launch_tables(b200s_ctx* c, Nrt2* s) {
     a.nrows = (int)s->tp_list.size();
     a.count = s->Sp;
     dim3 grid((unsigned)(s->Sp / 128), (unsigned)((a.nrows + UT - 1) / UT));
-    nrt2_table_kernel<4, 4, SC, true><<<grid, 128, 0, c->stream>>>(a, s->Tp.as<uint8_t>());
+    nrt2_table_kernel<4, 4, SC, true, WIDE><<<grid, 128, 0, c->stream>>>(a, s->Tp.as<uint8_t>());
     c->launches += 1;
   }
 }
@@ -880,12 +935,15 @@ int nrt2_eval(b200s_ctx* c, int dtype) {
   Nrt2* s = nrt2_get(c);
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
   if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION)
-    launch_tables<1>(c, s);
+    launch_tables<1, false>(c, s);  // fractions in float64: no 32-bit ratio to widen
+  else if (s->wide)
+    launch_tables<0, true>(c, s);
   else
-    launch_tables<0>(c, s);
+    launch_tables<0, false>(c, s);
   ExpandArgs a;
   a.node_flags = c->nrt_node_flags.as<uint8_t>();
   a.slot = s->slot.as<int32_t>();
+  a.tile_n0 = s->tile_n0.as<int32_t>();
   a.tile_c0 = s->tile_c0.as<int32_t>();
   a.filt = s->filt.as<int32_t>();
   a.nrm = s->nrm.as<uint8_t>();
@@ -908,7 +966,7 @@ int nrt2_eval(b200s_ctx* c, int dtype) {
   a.N = c->N;
   a.Npad = c->Npad;
   a.P = c->P;
-  dim3 grid((unsigned)((c->Npad + TILE - 1) / TILE), (unsigned)((c->P + PT - 1) / PT));
+  dim3 grid((unsigned)s->n_tiles, (unsigned)((c->P + PT - 1) / PT));
   if (dtype == B200S_OUT_I64)
     nrt2_expand_kernel<4, 4, int64_t><<<grid, TILE, 0, c->stream>>>(a, o.scores.as<int64_t>(), o.feas.as<uint32_t>(),
                                                                     o.reasons.as<uint8_t>());

@@ -62,29 +62,33 @@ __device__ double go_pow(double x, double y) {
 // When is q1 the correctly rounded quotient?  Markstein's theorem needs q0 FAITHFUL (one of the two neighbours of
 // x/d), and RN(x * RN(1/d)) can be 1.5 ulp off, so it does not hold for every divisor.  Brisebarre, Muller & Raina
 // ("Accelerating correctly rounded floating-point division when the divisor is known in advance", IEEE TC 53(8),
-// 2004, Theorem 4 on exactly this 1 multiplication + 2 FMA sequence) give sufficient conditions on the DIVISOR alone;
-// the first is: the last bit of d's significand is 0.  Every divisor on this path is an integer below 2^52 converted
-// to float64 (capacity in milli-cores, targetloadpacking.go:146; the target utilisation and its complement, :174-184;
-// allocatable milli-cores, resourcestats.go:55) or such an integer times 2^-20 (memory in MiB, resourcestats.go:60-64)
-// -- all have a zero last significand bit.  inv_for_div() checks that bit (and a moderate exponent) per divisor,
-// hoisted; a divisor that fails gets a NaN "reciprocal", which sends every division by it to the IEEE sequence.
-// The theorem also assumes no overflow / underflow: quotients outside [2^-800, 2^800] (and NaN, Inf, 0 -- e.g. an
-// infinite utilisation metric, where x*r - based steps would produce NaN but Go's x/d is +Inf) are recomputed with
-// the IEEE division as well.  b200s_debug_div_check compares against the hardware division on the device, on
-// random operands and on operands constructed at rounding boundaries (tests/test_gpu_divcheck.py).
-__device__ __forceinline__ double inv_for_div(double d) {
+// 2004, Theorem 4, on exactly this 1 multiplication + 2 FMA sequence) give sufficient conditions on the DIVISOR alone;
+// the first: the last bit of d's significand is 0.  Every divisor on this path is an integer below 2^52 converted to
+// float64 (capacity in milli-cores, targetloadpacking.go:146; the target utilisation and its complement, :174-184;
+// allocatable milli-cores, resourcestats.go:55) or such an integer times 2^-20 (memory in MiB, resourcestats.go:60-64):
+// all have a zero last significand bit.  The theorem also assumes that nothing overflows or underflows.  Both
+// conditions are checked ONCE per divisor / per node, hoisted out of the pod loop (div_eligible, num_in_range): a
+// thread whose nodes pass runs the straight-line div_inv form, any other thread runs the same formulas with the
+// IEEE division -- so an infinite or denormal metric, a capacity with 53 significant bits, or a target of 0 or 100
+// behave exactly as Go's x/d.  b200s_debug_div_check compares the two on the device (eligible divisors through
+// div_inv, the rest through the division itself), on random operands and on operands constructed at rounding
+// boundaries of the quotient (tests/test_gpu_divcheck.py).
+__device__ __forceinline__ bool div_eligible(double d) {
   const long long b = __double_as_longlong(d);
   const unsigned e = (unsigned)(b >> 52) & 0x7ffu;
-  const bool ok = !(b & 1) && e - 923u <= 200u;  // last significand bit 0, 2^-100 <= |d| < 2^101
-  return ok ? 1.0 / d : CUDART_NAN;
+  return !(b & 1) && e - 923u <= 200u;  // last significand bit 0, 2^-100 <= |d| < 2^101
+}
+// a numerator term that is 0 or of moderate magnitude: sums / products with the int64-derived pod terms then stay
+// either exactly 0 or inside [2^-300, 2^300], where neither the quotient nor the residual can underflow or overflow
+__device__ __forceinline__ bool num_in_range(double x) {
+  const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+  // +0 (the FMA steps would turn -0 / d into +0), or 2^-200 <= |x| < 2^201 (excludes NaN, Inf, denormals)
+  return __double_as_longlong(x) == 0 || e - 823u <= 400u;
 }
 __device__ __forceinline__ double div_inv(double x, double d, double r) {
   const double q0 = x * r;
   const double rem = __fma_rn(-q0, d, x);
-  double q1 = __fma_rn(rem, r, q0);
-  const unsigned e = ((unsigned)__double2hiint(q1) >> 20) & 0x7ffu;  // integer pipe, not fp64
-  if (e - 223u > 1600u) q1 = x / d;  // NaN / Inf / 0 / out of the theorem's range / ineligible divisor
-  return q1;
+  return __fma_rn(rem, r, q0);
 }
 
 __global__ void div_check_kernel(const double* __restrict__ x, const double* __restrict__ d, int n,
@@ -92,7 +96,7 @@ __global__ void div_check_kernel(const double* __restrict__ x, const double* __r
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double want = x[i] / d[i];
-  const double got = div_inv(x[i], d[i], inv_for_div(d[i]));
+  const double got = (div_eligible(d[i]) && num_in_range(x[i])) ? div_inv(x[i], d[i], 1.0 / d[i]) : x[i] / d[i];
   if (__double_as_longlong(want) != __double_as_longlong(got) && !(want != want && got != got)) atomicAdd(mismatches, 1ull);
 }
 
@@ -109,42 +113,65 @@ tlp_kernel(const double* __restrict__ util, const int64_t* __restrict__ cap, con
     if (p0 + i < P) s_pod[i] = (double)pod_cpu[p0 + i];
   double ncap[NPT], rcap[NPT], base[NPT], miss[NPT];
   uint32_t ok = 0;
+  bool fast = true;  // every division this thread does satisfies the div_inv conditions (see above)
   if (nb < Npad) {
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
       int n = nb + j;
       ncap[j] = (double)cap[n];
-      rcap[j] = inv_for_div(ncap[j]);
+      rcap[j] = 1.0 / ncap[j];
       base[j] = (util[n] / 100) * ncap[j];  // nodeCPUUtilMillis, :147
       miss[j] = (double)missing[n];
       uint8_t f = flags[n];
       if (n < N && (f & B200S_TLP_HAS_METRICS) && (f & B200S_TLP_CPU_FOUND)) ok |= 1u << j;
+      if (ncap[j] != 0 && !(div_eligible(ncap[j]) && num_in_range(base[j]))) fast = false;
     }
   }
   __syncthreads();
   if (nb >= Npad) return;
   const double t = (double)target;
   const double hundred_minus_t = 100 - t;
-  // target 0 or 100 (a zero divisor) gets a NaN reciprocal: div_inv then takes the IEEE division
-  const double r_t = inv_for_div(t), r_hmt = inv_for_div(hundred_minus_t);
+  const double r_t = 1.0 / t, r_hmt = 1.0 / hundred_minus_t;
+  // target 0 or 100 divides by zero in one branch: the IEEE form handles it as Go does
+  if (!(div_eligible(t) && div_eligible(hundred_minus_t))) fast = false;
   const int pend = min(PT, P - p0);
   OutT* orow = out + (size_t)p0 * Npad + nb;
-  for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+  if (fast) {
+    for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+      const double pc = s_pod[pp];
+      int64_t q[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) {
+        double predicted = 0;
+        if (ncap[j] != 0) predicted = div_inv(100 * (base[j] + pc + miss[j]), ncap[j], rcap[j]);  // :170-173
+        // both branches of :174-184 are a division by a launch invariant followed by math.Round: evaluate them as ONE
+        // straight-line chain with the operands selected (same operations on the same values, no divergent paths)
+        const bool over = predicted > t;
+        const double num = over ? t * (100 - predicted) : hundred_minus_t * predicted;
+        const double d = over ? hundred_minus_t : t, r = over ? r_hmt : r_t;
+        double quo = div_inv(num, d, r);
+        quo = over ? quo : quo + t;                       // :183
+        double s = go_round(quo);
+        s = (over && predicted > 100) ? 0.0 : s;          // :175-177
+        q[j] = ((ok >> j) & 1u) ? go_f2i(s) : 0;
+      }
+      Store<OutT, NPT>::put64(orow, q);
+    }
+    return;
+  }
+  for (int pp = 0; pp < pend; ++pp, orow += Npad) {  // the same formulas with the IEEE division
     const double pc = s_pod[pp];
     int64_t q[NPT];
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
       double predicted = 0;
-      if (ncap[j] != 0) predicted = div_inv(100 * (base[j] + pc + miss[j]), ncap[j], rcap[j]);  // :170-173
-      // both branches of :174-184 are a division by a launch invariant followed by math.Round: evaluate them as ONE
-      // straight-line chain with the operands selected (same operations on the same values, no divergent paths)
+      if (ncap[j] != 0) predicted = 100 * (base[j] + pc + miss[j]) / ncap[j];
       const bool over = predicted > t;
       const double num = over ? t * (100 - predicted) : hundred_minus_t * predicted;
-      const double d = over ? hundred_minus_t : t, r = over ? r_hmt : r_t;
-      double quo = div_inv(num, d, r);
-      quo = over ? quo : quo + t;                       // :183
+      double quo = num / (over ? hundred_minus_t : t);
+      quo = over ? quo : quo + t;
       double s = go_round(quo);
-      s = (over && predicted > 100) ? 0.0 : s;          // :175-177
+      s = (over && predicted > 100) ? 0.0 : s;
       q[j] = ((ok >> j) & 1u) ? go_f2i(s) : 0;
     }
     Store<OutT, NPT>::put64(orow, q);
@@ -160,7 +187,7 @@ __device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, 
                                               double sens) {
   LvrbNode r;
   r.cap = cap;
-  r.rcap = inv_for_div(cap);
+  r.rcap = 1.0 / cap;
   double used_avg = util_avg * cap / 100;  // resourcestats.go:68
   double used_std = util_std * cap / 100;  // :69
   r.avg = go_max(go_min(used_avg, cap), 0);
@@ -179,19 +206,19 @@ __device__ __forceinline__ LvrbNode lvrb_node(double util_avg, double util_std, 
 
 __device__ __forceinline__ double lvrb_res_score(const LvrbNode& nd, double req) {
   if (nd.cap <= 0) return 0;  // analysis.go:35-38
-  double mu = div_inv(nd.avg + req, nd.cap, nd.rcap);
+  double mu = (nd.avg + req) / nd.cap;
   mu = go_max(go_min(mu, 1), 0);
   double risk = (mu + nd.sigma) / 2;
   return (1. - risk) * 100.0;
 }
-// Same, for a node whose avg / sigma / capacity are finite (checked once per node): mu cannot be NaN, so the
-// NaN-propagating clamps of Go's builtin min/max reduce to the hardware min/max.
+// Same, for a node whose avg / sigma / capacity are finite and satisfy the div_inv conditions (checked once per
+// node): mu cannot be NaN, so the NaN-propagating clamps of Go's builtin min/max reduce to the hardware min/max.
 __device__ __forceinline__ double lvrb_res_score_finite(const LvrbNode& nd, double req) {
   const double mu = fmax(fmin(div_inv(nd.avg + req, nd.cap, nd.rcap), 1.0), 0.0);
   return (1. - (mu + nd.sigma) / 2) * 100.0;
 }
 __device__ __forceinline__ bool lvrb_finite(const LvrbNode& nd) {
-  return nd.cap > 0 && nd.cap < CUDART_INF && nd.avg == nd.avg && nd.sigma == nd.sigma;
+  return nd.cap > 0 && div_eligible(nd.cap) && num_in_range(nd.avg) && nd.sigma == nd.sigma;
 }
 
 template <class OutT, int NPT, int PT>

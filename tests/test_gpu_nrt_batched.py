@@ -40,6 +40,26 @@ def test_batched_equals_oracle_many_shapes(eng, engine_mod, strategy):
         assert np.array_equal(gs, ws), (seed, np.argwhere(gs != ws)[:5])
 
 
+@pytest.mark.parametrize("strategy", [0, 2])
+def test_batched_wide_value_ratios(eng, engine_mod, strategy):
+    """page-granular (4 KiB) memory: zone capacities in pages exceed 2^32 / 100, the table kernel switches to the
+    64-bit numerator form of (cv - rv) * 100 / cv -- same scores."""
+    from oracle import pyoracle_nrt
+
+    E = engine_mod
+    P, N = 80, 1100
+    nodes, pods = synth.gen_nrt(23, N, P, Z=4)
+    nodes = dict(nodes, avail=nodes["avail"].copy())
+    listed = ((nodes["zone_res_mask"] >> 1) & 1).astype(np.int64)
+    rng = np.random.default_rng(5)
+    nodes["avail"][:, 1] = (nodes["avail"][:, 1] * 8 + rng.integers(0, 256, listed.shape) * 4096 * 1000) * listed
+    w = [1, 3, 1, 2]
+    gs, gf, gr = run_nrt(eng, E, nodes, pods, strategy, w, None, path=E.NRT_PATH_BATCHED)
+    assert eng.nrt_last_path() == E.NRT_PATH_BATCHED and "64-bit" in eng.nrt_path_note(), eng.nrt_path_note()
+    ws, wf, wr = pyoracle_nrt.nrt_batch(nodes, pods, strategy, w, None, pitch=eng.Npad)
+    assert np.array_equal(gr, wr) and np.array_equal(gf, wf) and np.array_equal(gs, ws)
+
+
 def test_batched_declines_what_it_cannot_encode(eng, engine_mod):
     """Quantities that do not fit the scaled 32-bit encoding, absurd weights, a Guaranteed pod that names a single
     resource under BalancedAllocation (NaN variance) and LeastNUMANodes all keep the direct kernel -- with the
