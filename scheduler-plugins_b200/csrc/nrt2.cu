@@ -37,9 +37,19 @@ namespace b200s {
 namespace {
 
 constexpr int C_MAX = B200S_NRT_MAX_CONT;
-constexpr int TILE = 256;      // threads per CTA of the P x N kernel = most container-scope slots of one tile
-constexpr int TILE_SPAN = 1024;  // most natural node indices of one tile
-constexpr int PT = 32;     // pods per CTA
+// tuning knobs (defaults = the measured best; -D overrides for A/B builds, tools/ab_build.sh)
+#ifndef B200S_NRT2_SPAN
+#define B200S_NRT2_SPAN 1024
+#endif
+#ifndef B200S_NRT2_PT
+#define B200S_NRT2_PT 32
+#endif
+#ifndef B200S_NRT2_SKIP
+#define B200S_NRT2_SKIP 1
+#endif
+constexpr int TILE = 256;                   // threads per CTA of the P x N kernel = most container-scope slots of one tile
+constexpr int TILE_SPAN = B200S_NRT2_SPAN;  // most natural node indices of one tile
+constexpr int PT = B200S_NRT2_PT;           // pods per CTA
 constexpr int UT = 32;     // request vectors per CTA of the table kernel
 constexpr int32_t S_MIN = INT32_MIN, S_MAX = INT32_MAX;
 constexpr int64_t LIM_MILLI = (int64_t)1 << 30;  // scaled milli quantities stay below (sentinels are +-2^31)
@@ -269,7 +279,7 @@ void nrt2_on_pods(b200s_ctx* c, const b200s_nrt_pods* q, int P) {
     for (int cidx = 0; cidx < nc; ++cidx) {
       const int32_t id = intern(p, cidx, guar);
       s->pod_vec[(size_t)p * (C_MAX + 1) + cidx] = id;
-      if (guar && s->tc_of[(size_t)id] < 0) {
+      if (s->tc_of[(size_t)id] < 0) {  // one row of the container table per distinct container vector
         s->tc_of[(size_t)id] = (int32_t)s->tc_list.size();
         s->tc_list.push_back(id);
       }
@@ -400,11 +410,13 @@ struct TableArgs {
 };
 
 // T[row][slot] for UT request vectors x 128 slots per CTA: the thread keeps its node's cells in registers, the
-// vectors come from shared memory (warp-uniform).  POD: the table of the pod-scope nodes -- entry = score (100 for a
-// non-Guaranteed vector, score.go:72-75) if resourcesAvailableInAnyNUMANodes finds a zone (filter.go:162-173), else
-// 128 + B200S_REASON_NRT_ALIGN_POD.  Otherwise the score table of the container-scope nodes.
+// vectors come from shared memory (warp-uniform).  POD: the byte table of the pod-scope nodes -- entry = score (100 for
+// a non-Guaranteed vector, score.go:72-75) if resourcesAvailableInAnyNUMANodes finds a zone (filter.go:162-173), else
+// 128 + B200S_REASON_NRT_ALIGN_POD.  Otherwise the 16-bit table of the container-scope nodes: the vector's score in
+// the low byte and, in bits 8.., the zones it fits on the node as the snapshot has it -- the Filter verdict of every
+// init container and of the first app container, which see the zones before any subtraction (filter.go:43-66).
 template <int Z, int R, int SC, bool POD, bool WIDE>
-__global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* __restrict__ T) {
+__global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, void* __restrict__ Tout) {
   __shared__ VecRec sv[UT];
   const int row0 = blockIdx.y * UT, nrow = min(UT, a.nrows - row0);
   {
@@ -429,21 +441,18 @@ __global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* _
   __syncthreads();
   for (int j = 0; j < nrow; ++j) {
     const VecRec& v = sv[j];
-    uint32_t entry;
-    bool pass = true;
-    if constexpr (POD) {
-      uint32_t ok = 0;
+    // resourcesAvailableInAnyNUMANodes (filter.go:90-160) on the node as the snapshot has it: which zones fit
+    uint32_t ok = 0;
 #pragma unroll
-      for (int z = 0; z < Z; ++z) {
-        bool fits = true;
+    for (int z = 0; z < Z; ++z) {
+      bool fits = true;
 #pragma unroll
-        for (int r = 0; r < R; ++r) fits &= filt[z][r] >= v.eff[r];
-        ok |= fits ? 1u : 0u;
-      }
-      pass = ok != 0 && !(v.need & ~nrm);  // :107-113: a non-zero request must be reported at node level
+      for (int r = 0; r < R; ++r) fits &= filt[z][r] >= v.eff[r];
+      ok |= (fits ? 1u : 0u) << z;
     }
-    int32_t score = 100;
-    if (!POD || v.guar) {  // warp-uniform
+    if (v.need & ~nrm) ok = 0;  // :107-113: a non-zero request must be reported at node level
+    int32_t score = POD ? 100 : 0;
+    if (v.guar) {  // warp-uniform
       int32_t min_score = 0;
 #pragma unroll
       for (int z = 0; z < Z; ++z) {
@@ -499,8 +508,11 @@ __global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, uint8_t* _
       }
       score = min_score;
     }
-    entry = pass ? (uint32_t)score : 128u + B200S_REASON_NRT_ALIGN_POD;
-    T[(size_t)(row0 + j) * a.count + slot] = (uint8_t)entry;
+    if constexpr (POD)
+      static_cast<uint8_t*>(Tout)[(size_t)(row0 + j) * a.count + slot] =
+          (uint8_t)(ok != 0 ? (uint32_t)score : 128u + B200S_REASON_NRT_ALIGN_POD);
+    else  // container table: score of the vector (Guaranteed only) | zones that fit before any subtraction << 8
+      static_cast<uint16_t*>(Tout)[(size_t)(row0 + j) * a.count + slot] = (uint16_t)((uint32_t)score | (ok << 8));
   }
 }
 
@@ -524,7 +536,7 @@ struct ExpandArgs {
   const int32_t* pod_tc;   // [P][C_MAX] row of Tc or -1
   const int32_t* pod_tp;   // [P] row of Tp or -1
   const VecRec* vecs;
-  const uint8_t* Tc;  // [Uc][Sc]
+  const uint16_t* Tc;  // [Uc][Sc] score | fresh-node fit mask << 8
   const uint8_t* Tp;  // [Ue][Sp]
   const uint64_t* upstream;
   int words, N, Npad, P;
@@ -532,8 +544,6 @@ struct ExpandArgs {
 
 struct PodMeta {
   uint8_t qos, flags, n_init, n_app;
-  uint8_t kind[C_MAX];
-  uint8_t need[C_MAX];
   int32_t tp;
 };
 
@@ -550,6 +560,7 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
   __shared__ int32_t s_eff[PT][C_MAX][R];
   __shared__ int32_t s_sub[PT][C_MAX][R];
   __shared__ int32_t s_tc[PT][C_MAX];
+  __shared__ uint8_t s_code[PT][C_MAX];
   __shared__ PodMeta s_meta[PT];
   __shared__ uint8_t s_v[PT][TILE];
   const int tid = threadIdx.x;
@@ -557,7 +568,6 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
   for (int i = tid; i < pend * C_MAX; i += TILE) {
     const int pp = i / C_MAX, c = i % C_MAX;
     const int u = a.pod_vec[(size_t)(p0 + pp) * (C_MAX + 1) + c];
-    uint8_t need = 0;
     if (u >= 0) {
       const VecRec& v = a.vecs[u];
 #pragma unroll
@@ -565,7 +575,6 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
         s_eff[pp][c][r] = v.eff[r];
         s_sub[pp][c][r] = v.sub[r];
       }
-      need = v.need;
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -573,9 +582,12 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
         s_sub[pp][c][r] = 0;
       }
     }
-    s_meta[pp].need[c] = need;
-    s_meta[pp].kind[c] = a.kind[(size_t)(p0 + pp) * C_MAX + c];
-    s_tc[pp][c] = a.pod_tc[(size_t)(p0 + pp) * C_MAX + c];
+    // reason code if this container cannot be aligned: logging.go:68-73 names init containers with RestartPolicy
+    // Always "sidecar"; s_code is only read for init containers and the first app container
+    const uint8_t kind = a.kind[(size_t)(p0 + pp) * C_MAX + c];
+    s_code[pp][c] = c >= a.n_init[p0 + pp] ? B200S_REASON_NRT_ALIGN_CONTAINER
+                                           : (kind == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT);
+    s_tc[pp][c] = max(a.pod_tc[(size_t)(p0 + pp) * C_MAX + c], 0);
   }
   for (int i = tid; i < pend; i += TILE) {
     const int p = p0 + i;
@@ -590,64 +602,74 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
   __syncthreads();
   if (tid < ncs) {
     const int slot = c0 + tid;
+    const uint32_t nrm = a.nrm[slot];
     int32_t node[Z][R];
-#pragma unroll
-    for (int z = 0; z < Z; ++z)
-#pragma unroll
-      for (int r = 0; r < R; ++r) node[z][r] = a.filt[((size_t)z * R + r) * a.S + slot];
     bool nolist[R];  // no zone lists the (host-level) resource: nothing to subtract from (filter.go:139-142)
 #pragma unroll
-    for (int r = 0; r < R; ++r) nolist[r] = node[0][r] == S_MAX;
-    const uint32_t nrm = a.nrm[slot];
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int z = 0; z < Z; ++z) node[z][r] = a.filt[((size_t)z * R + r) * a.S + slot];
+      nolist[r] = node[0][r] == S_MAX;
+      // a resource the node does not report at node level rejects every non-zero request for it (:107-113):
+      // S_MIN fails `>= eff` for every needed resource and passes the unconstrained ones (eff == S_MIN)
+      if (!((nrm >> r) & 1u)) {
+#pragma unroll
+        for (int z = 0; z < Z; ++z) node[z][r] = S_MIN;
+      }
+    }
+    const uint16_t* tc = a.Tc + slot;
     for (int pp = 0; pp < pend; ++pp) {
       const PodMeta& m = s_meta[pp];
       if (m.flags & (B200S_NRT_POD_FILTER_BYPASS | B200S_NRT_POD_UNSUPPORTED)) continue;  // decided in phase 2
       const int n_init = m.n_init, steps = n_init + m.n_app;
-      int32_t zs[Z][R];
+      uint32_t reason = 0, sum = 0;
+      // init containers and the FIRST app container see the zones as the snapshot has them (init containers do
+      // not subtract, :43-55): their verdict is the fit mask the table kernel stored next to the score
+      const int first = min(n_init + 1, steps);
+      uint32_t ok = 0;
+      for (int s = 0; s < first; ++s) {
+        const uint32_t e = tc[(size_t)s_tc[pp][s] * a.Sc];
+        sum += e & 0xFFu;
+        ok = e >> 8;
+        reason = (reason == 0 && ok == 0) ? s_code[pp][s] : reason;
+      }
+      if (steps > first) {  // further app containers: the first-fit state machine with subtraction (:57-76)
+        int32_t zs[Z][R];
 #pragma unroll
-      for (int z = 0; z < Z; ++z)
+        for (int z = 0; z < Z; ++z)
 #pragma unroll
-        for (int r = 0; r < R; ++r) zs[z][r] = node[z][r];
-      uint32_t reason = 0;
-      for (int s = 0; s < steps; ++s) {
-        bool fit[Z];
-#pragma unroll
-        for (int z = 0; z < Z; ++z) fit[z] = true;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int32_t e = s_eff[pp][s][r];
-          if (e == S_MIN) continue;  // not requested / zero: constrains nothing (warp-uniform)
-#pragma unroll
-          for (int z = 0; z < Z; ++z) fit[z] &= zs[z][r] >= e;
-        }
-        uint32_t ok = 0;
-#pragma unroll
-        for (int z = 0; z < Z; ++z) ok |= (fit[z] ? 1u : 0u) << z;
-        if (m.need[s] & ~nrm) ok = 0;  // :107-113
-        const uint32_t code = s >= n_init ? B200S_REASON_NRT_ALIGN_CONTAINER
-                                          : (m.kind[s] == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR
-                                                                             : B200S_REASON_NRT_ALIGN_INIT);
-        reason = (reason == 0 && ok == 0) ? code : reason;
-        if (s >= n_init) {  // subtractResourcesFromNUMANodeList (numaresources.go:145-182) on the lowest fitting id
-          const int id = __ffs(ok) - 1;
+          for (int r = 0; r < R; ++r) zs[z][r] = node[z][r];
+        for (int s = first; s < steps; ++s) {
+          // the previous app container takes its request from the lowest fitting zone
+          // (subtractResourcesFromNUMANodeList, numaresources.go:145-182); the last one's subtraction is never read
+          const uint32_t low = ok & (0u - ok);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const int32_t q = s_sub[pp][s][r];
-            if (q == 0) continue;  // warp-uniform
-            const int32_t qq = nolist[r] ? 0 : q;
+            const int32_t q = nolist[r] ? 0 : s_sub[pp][s - 1][r];
 #pragma unroll
-            for (int z = 0; z < Z; ++z) zs[z][r] -= (z == id) ? qq : 0;
+            for (int z = 0; z < Z; ++z) zs[z][r] -= q * (int32_t)((low >> z) & 1u);
           }
+          bool fit[Z];
+#pragma unroll
+          for (int z = 0; z < Z; ++z) fit[z] = true;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int32_t e = s_eff[pp][s][r];
+#pragma unroll
+            for (int z = 0; z < Z; ++z) fit[z] &= zs[z][r] >= e;
+          }
+          ok = 0;
+#pragma unroll
+          for (int z = 0; z < Z; ++z) ok |= (fit[z] ? 1u : 0u) << z;
+          reason = (reason == 0 && ok == 0) ? (uint32_t)B200S_REASON_NRT_ALIGN_CONTAINER : reason;
+          sum += tc[(size_t)s_tc[pp][s] * a.Sc] & 0xFFu;
         }
       }
       uint32_t v = 128u + reason;
       if (reason == 0) {
-        v = 100;  // non-Guaranteed: score.go:72-75
-        if (m.qos == B200S_QOS_GUARANTEED) {
-          uint32_t sum = 0;  // containerScopeScore (score.go:152-165): mean over init + app containers, truncated
-          for (int s = 0; s < steps; ++s) sum += a.Tc[(size_t)s_tc[pp][s] * a.Sc + slot];
-          v = (sum * ((65536u + (uint32_t)steps - 1u) / (uint32_t)steps)) >> 16;  // sum <= 800: exact floor(sum / steps)
-        }
+        // containerScopeScore (score.go:152-165): mean over init + app containers, truncated (sum <= 800: the
+        // multiply-shift is the exact floor(sum / steps)); non-Guaranteed pods score 100 (:72-75)
+        v = m.qos == B200S_QOS_GUARANTEED ? (sum * ((65536u + (uint32_t)steps - 1u) / (uint32_t)steps)) >> 16 : 100u;
       }
       s_v[pp][tid] = (uint8_t)v;
     }
@@ -792,7 +814,7 @@ int nrt2_prepare(b200s_ctx* c) {
   if (wide) s->note = "batched, 64-bit Value() ratios";
   if (!s->lists_valid) B200S_TRY(build_lists(c, s));
   const size_t S = (size_t)s->Sc + s->Sp;
-  const size_t tc_bytes = (size_t)std::max<size_t>(s->tc_list.size(), 1) * s->Sc;
+  const size_t tc_bytes = (size_t)std::max<size_t>(s->tc_list.size(), 1) * s->Sc * 2;
   const size_t tp_bytes = (size_t)std::max<size_t>(s->tp_list.size(), 1) * s->Sp;
   if (tc_bytes + tp_bytes > ((size_t)16 << 30)) return decline("score tables above 16 GiB");
   // node columns of the two lists in the scaled encodings (per snapshot and scale)
@@ -911,7 +933,7 @@ void launch_tables(b200s_ctx* c, Nrt2* s) {
     a.nrows = (int)s->tc_list.size();
     a.count = s->Sc;
     dim3 grid((unsigned)(s->Sc / 128), (unsigned)((a.nrows + UT - 1) / UT));
-    nrt2_table_kernel<4, 4, SC, false, WIDE><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint8_t>());
+    nrt2_table_kernel<4, 4, SC, false, WIDE><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint16_t>());
     c->launches += 1;
   }
   if (!s->tp_list.empty() && s->Np > 0) {
@@ -959,7 +981,7 @@ int nrt2_eval(b200s_ctx* c, int dtype) {
   a.pod_tc = s->d_pod_tc.as<int32_t>();
   a.pod_tp = s->d_pod_tp.as<int32_t>();
   a.vecs = s->vecrec.as<VecRec>();
-  a.Tc = s->Tc.as<uint8_t>();
+  a.Tc = s->Tc.as<uint16_t>();
   a.Tp = s->Tp.as<uint8_t>();
   a.upstream = c->upstream_mask();
   a.words = c->Npad / 64;
