@@ -542,24 +542,35 @@ struct ExpandArgs {
   int words, N, Npad, P;
 };
 
-struct PodMeta {
-  uint8_t qos, flags, n_init, n_app;
-  int32_t tp;
+struct alignas(16) PodMeta {
+  uint8_t flags;   // bit 0 Filter bypass, bit 1 unsupported pod, bit 2 Guaranteed
+  uint8_t n_init, steps, first;  // init containers, init + app containers, containers that see the unmodified zones
+  uint32_t tpoff;      // row of Tp x Sp
+  uint32_t inv_steps;  // ceil(65536 / steps): (sum * inv_steps) >> 16 == sum / steps for sum <= 800
+  uint32_t pad;
 };
 
-// The P x N pass.  Phase 1: the container-scope nodes of this tile (a contiguous slot range, one per thread) run the
-// first-fit state machine of singleNUMAContainerLevelHandler (filter.go:39-78) per pod and gather the
-// container-scope score (score.go:152-165) from Tc; one byte per (pod, slot) goes to shared memory (< 128: feasible
-// with that score, >= 128: 128 + reason).  Phase 2: the threads sweep the tile's NATURAL node indices and expand pod
-// by pod -- flag-decided nodes, pod-scope nodes (one byte of Tp), container-scope nodes (the staged byte) -- into
-// coalesced rows.  All pod data is warp-uniform (shared-memory broadcasts, uniform branches): resources a container
-// does not request are skipped for the whole warp.
+__device__ __forceinline__ int32_t mad_lo(int32_t a, int32_t b, int32_t c) {  // a * b + c on the FMA pipe (IMAD)
+  int32_t d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// The P x N pass.  Phase 1: the container-scope nodes of this tile (a contiguous slot range, one per thread) run
+// singleNUMAContainerLevelHandler (filter.go:39-78) per pod -- table look-ups for the containers that see the
+// unmodified zones, the first-fit state machine with subtraction for the app containers after the first -- and
+// gather the container-scope score (score.go:152-165) from the same table entries; one byte per (pod, slot) goes
+// to shared memory (< 128: feasible with that score, >= 128: 128 + reason).  Phase 2: the threads sweep the tile's
+// NATURAL node indices and expand pod by pod -- flag-decided nodes, pod-scope nodes (one byte of Tp),
+// container-scope nodes (the staged byte) -- into coalesced rows.  All pod data is warp-uniform (shared-memory
+// broadcasts, uniform branches).
 template <int Z, int R, class OutT>
-__global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* __restrict__ out,
+__global__ void __launch_bounds__(TILE, 4) nrt2_expand_kernel(ExpandArgs a, OutT* __restrict__ out,
                                                            uint32_t* __restrict__ feas32, uint8_t* __restrict__ reasons) {
-  __shared__ int32_t s_eff[PT][C_MAX][R];
-  __shared__ int32_t s_sub[PT][C_MAX][R];
-  __shared__ int32_t s_tc[PT][C_MAX];
+  static_assert(R == 4, "the request vectors travel as int4");
+  __shared__ int4 s_eff[PT][C_MAX];
+  __shared__ int4 s_sub[PT][C_MAX];
+  __shared__ uint32_t s_tcoff[PT][C_MAX];  // row of Tc x Sc (0 for unused container slots)
   __shared__ uint8_t s_code[PT][C_MAX];
   __shared__ PodMeta s_meta[PT];
   __shared__ uint8_t s_v[PT][TILE];
@@ -568,34 +579,33 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
   for (int i = tid; i < pend * C_MAX; i += TILE) {
     const int pp = i / C_MAX, c = i % C_MAX;
     const int u = a.pod_vec[(size_t)(p0 + pp) * (C_MAX + 1) + c];
+    int4 e = make_int4(S_MIN, S_MIN, S_MIN, S_MIN), sb = make_int4(0, 0, 0, 0);
     if (u >= 0) {
-      const VecRec& v = a.vecs[u];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        s_eff[pp][c][r] = v.eff[r];
-        s_sub[pp][c][r] = v.sub[r];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        s_eff[pp][c][r] = S_MIN;
-        s_sub[pp][c][r] = 0;
-      }
+      const int4* v = reinterpret_cast<const int4*>(a.vecs + u);  // VecRec: eff[4], sub[4] lead the record
+      e = v[0];
+      sb = v[1];
     }
+    s_eff[pp][c] = e;
+    s_sub[pp][c] = sb;
     // reason code if this container cannot be aligned: logging.go:68-73 names init containers with RestartPolicy
-    // Always "sidecar"; s_code is only read for init containers and the first app container
+    // Always "sidecar"
     const uint8_t kind = a.kind[(size_t)(p0 + pp) * C_MAX + c];
     s_code[pp][c] = c >= a.n_init[p0 + pp] ? B200S_REASON_NRT_ALIGN_CONTAINER
                                            : (kind == B200S_CONT_SIDECAR ? B200S_REASON_NRT_ALIGN_SIDECAR : B200S_REASON_NRT_ALIGN_INIT);
-    s_tc[pp][c] = max(a.pod_tc[(size_t)(p0 + pp) * C_MAX + c], 0);
+    s_tcoff[pp][c] = (uint32_t)max(a.pod_tc[(size_t)(p0 + pp) * C_MAX + c], 0) * (uint32_t)a.Sc;
   }
   for (int i = tid; i < pend; i += TILE) {
     const int p = p0 + i;
-    s_meta[i].qos = a.qos[p];
-    s_meta[i].flags = a.flags[p];
-    s_meta[i].n_init = a.n_init[p];
-    s_meta[i].n_app = a.n_app[p];
-    s_meta[i].tp = a.pod_tp[p];
+    PodMeta m;
+    const int n_init = a.n_init[p], steps = n_init + a.n_app[p];
+    m.flags = (uint8_t)((a.flags[p] & 3u) | (a.qos[p] == B200S_QOS_GUARANTEED ? 4u : 0u));
+    m.n_init = (uint8_t)n_init;
+    m.steps = (uint8_t)steps;
+    m.first = (uint8_t)min(n_init + 1, steps);
+    m.tpoff = (uint32_t)max(a.pod_tp[p], 0) * (uint32_t)a.Sp;
+    m.inv_steps = (65536u + (uint32_t)max(steps, 1) - 1u) / (uint32_t)max(steps, 1);
+    m.pad = 0;
+    s_meta[i] = m;
   }
   const int n0 = a.tile_n0[blockIdx.x], n1 = a.tile_n0[blockIdx.x + 1];
   const int c0 = a.tile_c0[blockIdx.x], ncs = a.tile_c0[blockIdx.x + 1] - c0;
@@ -619,20 +629,25 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
     }
     const uint16_t* tc = a.Tc + slot;
     for (int pp = 0; pp < pend; ++pp) {
-      const PodMeta& m = s_meta[pp];
-      if (m.flags & (B200S_NRT_POD_FILTER_BYPASS | B200S_NRT_POD_UNSUPPORTED)) continue;  // decided in phase 2
-      const int n_init = m.n_init, steps = n_init + m.n_app;
-      uint32_t reason = 0, sum = 0;
-      // init containers and the FIRST app container see the zones as the snapshot has them (init containers do
-      // not subtract, :43-55): their verdict is the fit mask the table kernel stored next to the score
-      const int first = min(n_init + 1, steps);
-      uint32_t ok = 0;
-      for (int s = 0; s < first; ++s) {
-        const uint32_t e = tc[(size_t)s_tc[pp][s] * a.Sc];
-        sum += e & 0xFFu;
-        ok = e >> 8;
-        reason = (reason == 0 && ok == 0) ? s_code[pp][s] : reason;
+      const PodMeta m = s_meta[pp];
+      if (m.flags & 3u) continue;  // Filter bypass / unsupported pod: decided in phase 2
+      const int steps = m.steps, first = m.first;
+      // every container's table entry at once (independent loads): score in the low byte, zones it fits on the
+      // node as the snapshot has it in bits 8..
+      uint32_t e[C_MAX];
+#pragma unroll
+      for (int s = 0; s < C_MAX; ++s) e[s] = s < steps ? (uint32_t)tc[s_tcoff[pp][s]] : 0u;
+      // init containers and the FIRST app container see the unmodified zones (init containers do not subtract,
+      // :43-55): their verdict is the stored fit mask
+      uint32_t sum = 0, ok = 0, fail = 0;
+#pragma unroll
+      for (int s = 0; s < C_MAX; ++s) {
+        sum += e[s] & 0xFFu;
+        const bool look = s < first;
+        ok = look ? e[s] >> 8 : ok;
+        fail |= (look && e[s] < 256u) ? 1u << s : 0u;
       }
+      uint32_t reason = fail ? s_code[pp][__ffs(fail) - 1] : 0u;
       if (steps > first) {  // further app containers: the first-fit state machine with subtraction (:57-76)
         int32_t zs[Z][R];
 #pragma unroll
@@ -642,70 +657,68 @@ __global__ void __launch_bounds__(TILE) nrt2_expand_kernel(ExpandArgs a, OutT* _
         for (int s = first; s < steps; ++s) {
           // the previous app container takes its request from the lowest fitting zone
           // (subtractResourcesFromNUMANodeList, numaresources.go:145-182); the last one's subtraction is never read
+          const int4 sb = s_sub[pp][s - 1], ef = s_eff[pp][s];
+          const int32_t q[4] = {nolist[0] ? 0 : sb.x, nolist[1] ? 0 : sb.y, nolist[2] ? 0 : sb.z, nolist[3] ? 0 : sb.w};
+          const int32_t ee[4] = {ef.x, ef.y, ef.z, ef.w};
           const uint32_t low = ok & (0u - ok);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int32_t q = nolist[r] ? 0 : s_sub[pp][s - 1][r];
-#pragma unroll
-            for (int z = 0; z < Z; ++z) zs[z][r] -= q * (int32_t)((low >> z) & 1u);
-          }
-          bool fit[Z];
-#pragma unroll
-          for (int z = 0; z < Z; ++z) fit[z] = true;
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int32_t e = s_eff[pp][s][r];
-#pragma unroll
-            for (int z = 0; z < Z; ++z) fit[z] &= zs[z][r] >= e;
-          }
           ok = 0;
 #pragma unroll
-          for (int z = 0; z < Z; ++z) ok |= (fit[z] ? 1u : 0u) << z;
+          for (int z = 0; z < Z; ++z) {
+            const int32_t take = -(int32_t)((low >> z) & 1u);  // -1 for the chosen zone
+            bool fit = true;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              zs[z][r] = mad_lo(q[r], take, zs[z][r]);
+              fit &= zs[z][r] >= ee[r];
+            }
+            ok |= (fit ? 1u : 0u) << z;
+          }
           reason = (reason == 0 && ok == 0) ? (uint32_t)B200S_REASON_NRT_ALIGN_CONTAINER : reason;
-          sum += tc[(size_t)s_tc[pp][s] * a.Sc] & 0xFFu;
         }
       }
-      uint32_t v = 128u + reason;
-      if (reason == 0) {
-        // containerScopeScore (score.go:152-165): mean over init + app containers, truncated (sum <= 800: the
-        // multiply-shift is the exact floor(sum / steps)); non-Guaranteed pods score 100 (:72-75)
-        v = m.qos == B200S_QOS_GUARANTEED ? (sum * ((65536u + (uint32_t)steps - 1u) / (uint32_t)steps)) >> 16 : 100u;
-      }
-      s_v[pp][tid] = (uint8_t)v;
+      // containerScopeScore (score.go:152-165): mean over init + app containers, truncated; non-Guaranteed pods
+      // score 100 (:72-75)
+      const uint32_t score = (m.flags & 4u) ? (sum * m.inv_steps) >> 16 : 100u;
+      s_v[pp][tid] = (uint8_t)(reason ? 128u + reason : score);
     }
   }
   __syncthreads();
   // n0 and n1 are multiples of 32: a warp is entirely inside or outside the tile (the ballot below needs full warps)
+  const uint32_t* up32 = reinterpret_cast<const uint32_t*>(a.upstream);
   for (int n = n0 + tid; n < n1; n += TILE) {
+    // what decides this node (the reference's gates in order, filter.go:194-209 / score.go:79-94):
+    //   1 stale NRT -> "invalid node topology data"; 2 no NRT object / policy not single-numa-node -> pass, score 0
+    //   (100 for a non-Guaranteed pod); 3 shape outside the dense encoding; 4 pod-scope table; 5 container-scope byte
     const uint32_t nfl = n < a.N ? a.node_flags[n] : 0u;
     const int slot = a.slot[n];
-    const bool fresh = nfl & B200S_NRT_NODE_FRESH, handler = slot >= 0;
-    const bool pod_scope = nfl & B200S_NRT_NODE_SCOPE_POD;
-    const bool trivial_ok = !(nfl & B200S_NRT_NODE_HAS_NRT) || !(nfl & B200S_NRT_NODE_SINGLE_NUMA);
-    const int word = n >> 6;
-    for (int pp = 0; pp < pend; ++pp) {
-      const int p = p0 + pp;
-      const PodMeta& m = s_meta[pp];
-      uint32_t reason = 0, score = 0;
-      bool feasible = false;
-      if (n < a.N) {
-        const bool guar = m.qos == B200S_QOS_GUARANTEED;
-        uint32_t v;
-        if (m.flags & B200S_NRT_POD_FILTER_BYPASS) v = 100;                                  // filter.go:180-183
-        else if (!fresh) v = 128u + B200S_REASON_NRT_INVALID_TOPOLOGY;                       // :194-197
-        else if (trivial_ok) v = guar ? 0u : 100u;                                           // :198-209; score.go:83-94
-        else if (!handler || (m.flags & B200S_NRT_POD_UNSUPPORTED)) v = 128u + B200S_REASON_UNSUPPORTED;
-        else if (pod_scope) v = a.Tp[(size_t)m.tp * a.Sp + slot];
-        else v = s_v[pp][slot - c0];
-        reason = v >= 128u ? v - 128u : 0u;
-        const bool up = a.upstream ? ((a.upstream[(size_t)p * a.words + word] >> (n & 63)) & 1ull) : true;
-        feasible = reason == 0 && up;
-        if (reason == 0 && !up) reason = B200S_REASON_UPSTREAM;
-        score = feasible ? v : 0u;
-      }
-      const size_t o = (size_t)p * a.Npad + n;
-      out[o] = (OutT)score;
-      reasons[o] = (uint8_t)reason;
+    int kind;
+    if (n >= a.N) kind = 0;
+    else if (!(nfl & B200S_NRT_NODE_FRESH)) kind = 1;
+    else if (!(nfl & B200S_NRT_NODE_HAS_NRT) || !(nfl & B200S_NRT_NODE_SINGLE_NUMA)) kind = 2;
+    else if (slot < 0) kind = 3;
+    else kind = (nfl & B200S_NRT_NODE_SCOPE_POD) ? 4 : 5;
+    const uint32_t v_guar = kind == 1 ? 128u + B200S_REASON_NRT_INVALID_TOPOLOGY : (kind == 3 ? 128u + B200S_REASON_UNSUPPORTED : 0u);
+    const uint32_t v_other = kind == 2 ? 100u : v_guar;
+    const uint8_t* tp = a.Tp + (kind == 4 ? slot : 0);
+    const uint8_t* sv = &s_v[0][kind == 5 ? slot - c0 : 0];
+    size_t o = (size_t)p0 * a.Npad + n;
+    const size_t w32 = (size_t)(a.words * 2);
+    const uint32_t* upw = up32 ? up32 + (size_t)p0 * w32 + (n >> 5) : nullptr;
+#pragma unroll 4
+    for (int pp = 0; pp < pend; ++pp, o += a.Npad) {
+      const PodMeta m = s_meta[pp];
+      uint32_t v = (m.flags & 4u) ? v_guar : v_other;
+      if (kind == 4) v = tp[m.tpoff];
+      if (kind == 5) v = sv[pp * TILE];
+      if ((m.flags & 2u) && kind >= 3) v = 128u + B200S_REASON_UNSUPPORTED;
+      if (m.flags & 1u) v = 100u;  // filter.go:180-183
+      uint32_t reason = v >= 128u ? v - 128u : 0u;
+      bool up = true;
+      if (upw) up = (upw[(size_t)pp * w32] >> (n & 31)) & 1u;
+      const bool feasible = reason == 0 && up && kind != 0;
+      reason = (reason == 0 && !up) ? (uint32_t)B200S_REASON_UPSTREAM : reason;
+      out[o] = (OutT)(feasible ? v : 0u);
+      reasons[o] = (uint8_t)(kind != 0 ? reason : 0u);
       const uint32_t w = __ballot_sync(0xffffffffu, feasible);
       if ((tid & 31) == 0) feas32[o >> 5] = w;
     }
@@ -817,6 +830,7 @@ int nrt2_prepare(b200s_ctx* c) {
   const size_t tc_bytes = (size_t)std::max<size_t>(s->tc_list.size(), 1) * s->Sc * 2;
   const size_t tp_bytes = (size_t)std::max<size_t>(s->tp_list.size(), 1) * s->Sp;
   if (tc_bytes + tp_bytes > ((size_t)16 << 30)) return decline("score tables above 16 GiB");
+  if (tc_bytes / 2 >= ((size_t)1 << 32) || tp_bytes >= ((size_t)1 << 32)) return decline("score table above 2^32 entries");
   // node columns of the two lists in the scaled encodings (per snapshot and scale)
   if (s->node_prep_serial != c->snap_serial || s->node_prep_wide != wide || memcmp(s->node_prep_gm, gm, sizeof(gm)) != 0 ||
       memcmp(s->node_prep_gv, gv, sizeof(gv)) != 0) {
