@@ -400,6 +400,14 @@ void b200s_free_pinned(void* p);
  * duration and the number of launches since the last reset, then resets.  Synchronises. */
 int b200s_set_profiling(b200s_ctx* ctx, int on);
 int b200s_kernel_time(b200s_ctx* ctx, b200s_plugin plugin, double* total_ms, uint64_t* launches);
+/* Same bookkeeping for the phases of a sharded / combined evaluation that are not one plugin's kernel: the per-pod
+ * min/max all-reduce of the normalising plugins, the all-gather of the per-pod top-k winners, and the weighted sum +
+ * top-k + fold kernels of b200s_eval_combined. */
+#define B200S_PHASE_ALLREDUCE 0
+#define B200S_PHASE_ALLGATHER 1
+#define B200S_PHASE_COMBINE 2
+#define B200S_PHASE_COUNT 3
+int b200s_phase_time(b200s_ctx* ctx, int phase, double* total_ms, uint64_t* count);
 
 /* Test hook: the Trimaran kernels divide by per-node / per-launch invariants with a hoisted
  * reciprocal + FMA residual correction; this counts inputs where that differs (bitwise) from the

@@ -98,6 +98,27 @@ def gofaithful_alloc_batch(cols, res_names, weights, mode, pod_cpu_milli, pod_me
     return (out, secs.value) if return_seconds else out
 
 
+def gofaithful_alloc_cycles16(cols, res_names, weights, mode, pod_cpu_milli, pod_mem_bytes, feasible_words=None,
+                              pitch=None, workers=16):
+    """The same restatement in upstream's shape: pods one at a time, each cycle's Score calls over a `workers`-wide
+    Parallelizer (chunks of chunkSizeFor(n, workers) nodes), NormalizeScore serial.  Returns (scores, seconds per cycle)."""
+    cols = [_c(c, np.int64) for c in cols]
+    N, P = len(cols[0]), len(pod_cpu_milli)
+    pitch = pitch or N
+    w = _c(weights, np.int64)
+    arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    names = (C.c_char_p * len(cols))(*[n.encode() for n in res_names])
+    pc = _c(pod_cpu_milli, np.int64); pm = _c(pod_mem_bytes, np.int64)
+    out = np.zeros((P, pitch), dtype=np.int64)
+    fw = None if feasible_words is None else _c(feasible_words, np.uint64)
+    words = 0 if fw is None else fw.shape[1]
+    secs = np.zeros(P, dtype=np.float64)
+    lib().orc_gofaithful_alloc_cycles16(arr, names, C.c_int(len(cols)), C.c_int(N), _p(w), C.c_int(mode), C.c_int(P),
+                                        _p(pc), _p(pm), _p(fw), C.c_int(words), _p(out), C.c_int(pitch), C.c_int(workers),
+                                        _p(secs))
+    return out, secs
+
+
 def tlp_score(util, cap, missing, flags, pod_cpu, target=40) -> int:
     return int(lib().orc_tlp_score(util, cap, missing, flags, pod_cpu, target))
 

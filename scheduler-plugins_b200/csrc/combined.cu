@@ -257,6 +257,8 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
     stage1 = c->topk_slices.as<b200s_topk_entry>();
   }
   dim3 grid(P, S);
+  {
+  KernelTimer kt(c, B200S_PLUGIN_COUNT + B200S_PHASE_COMBINE);  // weighted sum + per-pod top-k + slice fold
   if (k == 1)
     combine_topk_kernel<1><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   else if (k <= 4)
@@ -264,12 +266,12 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
   else
     combine_topk_kernel<K_MAX><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   c->launches++;
-  B200S_CUDA_TRY(c, cudaGetLastError());
   if (S > 1) {
     fold_topk_kernel<<<(P + 127) / 128, 128, 0, c->stream>>>(stage1, S, P, k, local);
     c->launches++;
-    B200S_CUDA_TRY(c, cudaGetLastError());
   }
+  }
+  B200S_CUDA_TRY(c, cudaGetLastError());
   if (world > 1) {
     const size_t bytes = (size_t)P * k * sizeof(b200s_topk_entry);
     B200S_CUDA_TRY(c, c->topk_all.ensure(bytes * world));

@@ -106,6 +106,7 @@ __global__ void complement_kernel(int64_t* v, int n) {
 int comm_allreduce_minmax(b200s_ctx* c, int64_t* lo, int64_t* hi, int count) {
   if (!c->comm || c->comm->world == 1 || count == 0) return B200S_OK;
   Api* a = api();
+  KernelTimer kt(c, B200S_PLUGIN_COUNT + B200S_PHASE_ALLREDUCE);
   if (hi != lo + count) {  // not contiguous: two reductions
     B200S_NCCL_TRY(c, a->GroupStart());
     B200S_NCCL_TRY(c, a->AllReduce(lo, lo, (size_t)count, ncclInt64, ncclMin, c->comm->comm, c->stream));
@@ -127,6 +128,7 @@ int comm_allgather(b200s_ctx* c, const void* send, void* recv, size_t bytes_per_
       B200S_CUDA_TRY(c, cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, c->stream));
     return B200S_OK;
   }
+  KernelTimer kt(c, B200S_PLUGIN_COUNT + B200S_PHASE_ALLGATHER);
   B200S_NCCL_TRY(c, api()->AllGather(send, recv, bytes_per_rank, ncclUint8, c->comm->comm, c->stream));
   return B200S_OK;
 }

@@ -358,13 +358,12 @@ int b200s_set_profiling(b200s_ctx* c, int on) {
   return B200S_OK;
 }
 
-int b200s_kernel_time(b200s_ctx* c, b200s_plugin plugin, double* total_ms, uint64_t* launches) {
-  if (!c || (int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT || !total_ms || !launches) return B200S_ERR_INVALID;
+static int timer_read(b200s_ctx* c, int slot, double* total_ms, uint64_t* launches) {
   Guard g(c);
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   double ms = 0;
   uint64_t n = 0;
-  for (auto& pr : c->prof_pending[plugin]) {
+  for (auto& pr : c->prof_pending[slot]) {
     float t = 0;
     if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) {
       ms += t;
@@ -373,10 +372,20 @@ int b200s_kernel_time(b200s_ctx* c, b200s_plugin plugin, double* total_ms, uint6
     c->prof_pool.push_back(pr.first);
     c->prof_pool.push_back(pr.second);
   }
-  c->prof_pending[plugin].clear();
+  c->prof_pending[slot].clear();
   *total_ms = ms;
   *launches = n;
   return B200S_OK;
+}
+
+int b200s_kernel_time(b200s_ctx* c, b200s_plugin plugin, double* total_ms, uint64_t* launches) {
+  if (!c || (int)plugin < 0 || plugin >= B200S_PLUGIN_COUNT || !total_ms || !launches) return B200S_ERR_INVALID;
+  return timer_read(c, (int)plugin, total_ms, launches);
+}
+
+int b200s_phase_time(b200s_ctx* c, int phase, double* total_ms, uint64_t* count) {
+  if (!c || phase < 0 || phase >= B200S_PHASE_COUNT || !total_ms || !count) return B200S_ERR_INVALID;
+  return timer_read(c, B200S_PLUGIN_COUNT + phase, total_ms, count);
 }
 
 void* b200s_alloc_pinned(size_t bytes) {

@@ -223,7 +223,8 @@ struct b200s_ctx {
 
   // ---- harness profiling: event pairs around the dominant kernel of each eval ----
   bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending[B200S_PLUGIN_COUNT];
+  // slots 0..B200S_PLUGIN_COUNT-1: plugins; B200S_PLUGIN_COUNT + phase: the B200S_PHASE_* timers
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending[B200S_PLUGIN_COUNT + B200S_PHASE_COUNT];
   std::vector<cudaEvent_t> prof_pool;
   cudaEvent_t prof_get() {
     cudaEvent_t e = nullptr;
@@ -294,7 +295,8 @@ int build_norm_params(b200s_ctx* c, int P);  // pod_lo/pod_hi -> norm_params
 
 int ensure_out(b200s_ctx* c, int plugin, int dtype, bool feas, bool reasons);
 
-// Brackets the dominant kernel of an eval with events when profiling is on.
+// Brackets the dominant kernel of an eval (or a phase: slot B200S_PLUGIN_COUNT + B200S_PHASE_*) with events when
+// profiling is on.
 struct KernelTimer {
   b200s_ctx* c;
   int plugin;

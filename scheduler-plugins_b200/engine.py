@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("B200S_LIB") or os.path.join(_HERE, "lib", "libb200sch
 (PLUGIN_ALLOCATABLE, PLUGIN_TLP, PLUGIN_LVRB, PLUGIN_NRT, PLUGIN_NETWORK_OVERHEAD, PLUGIN_PEAKS,
  PLUGIN_LOW_RISK) = range(7)
 PLUGIN_COUNT = 7
+PLUGIN_NAMES = ["NodeResourcesAllocatable", "TargetLoadPacking", "LoadVariationRiskBalancing", "NodeResourceTopologyMatch",
+                "NetworkOverhead", "Peaks", "LowRiskOverCommitment"]
 OUT_I64, OUT_U8 = 0, 1
 ALLOC_LEAST, ALLOC_MOST = 0, 1
 NRT_MOST_ALLOCATED, NRT_BALANCED_ALLOCATION, NRT_LEAST_ALLOCATED, NRT_LEAST_NUMA_NODES = range(4)
@@ -25,6 +27,7 @@ NODE_ALIGN = 128
 NRT_MAX_ZONES = NRT_MAX_RES = NRT_MAX_CONT = 8
 NETOH_MISSING = -(2**63)
 NRT_PATH_AUTO, NRT_PATH_DIRECT, NRT_PATH_BATCHED = 0, 1, 2
+PHASE_ALLREDUCE, PHASE_ALLGATHER, PHASE_COMBINE = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NCCL, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 
 EXPORTS = [
@@ -42,7 +45,7 @@ EXPORTS = [
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
-    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note",
+    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time",
 ]
 
 
@@ -187,6 +190,12 @@ class Engine:
         """(summed ms, launches) of the plugin's dominant kernel since the last call."""
         ms, n = C.c_double(), C.c_uint64()
         self._chk(self.lib.b200s_kernel_time(self.ctx, C.c_int(plugin), C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    def phase_time(self, phase):
+        """(summed ms, count) of PHASE_ALLREDUCE / PHASE_ALLGATHER / PHASE_COMBINE since the last call."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._chk(self.lib.b200s_phase_time(self.ctx, C.c_int(phase), C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
     def debug_div_check(self, x, d) -> int:
