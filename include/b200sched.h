@@ -122,6 +122,14 @@ uint64_t b200s_launch_count(b200s_ctx* ctx);
 #define B200S_UNIQUE_ID_BYTES 128
 int b200s_comm_unique_id(void* out_id /* B200S_UNIQUE_ID_BYTES */);
 int b200s_comm_init(b200s_ctx* ctx, const void* id, int rank, int world);
+/* Optional, one process per GPU on one NVLink / NVSwitch node: after b200s_comm_init every rank exports the CUDA IPC
+ * handle of its symmetric exchange buffer, the host side all-gathers the handles (however it distributed the unique
+ * id) and every rank imports the table handles[world][B200S_PEER_HANDLE_BYTES].  From then on the two per-pod
+ * exchanges (min/max of the normalising plugins, top-k winners) are remote stores into peer memory + a flag instead
+ * of NCCL collectives; payloads above 4 MiB per rank keep NCCL.  Collective: all ranks or none. */
+#define B200S_PEER_HANDLE_BYTES 64
+int b200s_comm_peer_export(b200s_ctx* ctx, void* out_handle /* B200S_PEER_HANDLE_BYTES */);
+int b200s_comm_peer_import(b200s_ctx* ctx, const void* handles /* [world][B200S_PEER_HANDLE_BYTES] */);
 int b200s_comm_rank(b200s_ctx* ctx);
 int b200s_comm_world(b200s_ctx* ctx);
 

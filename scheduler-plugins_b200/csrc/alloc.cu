@@ -352,49 +352,84 @@ int alloc_eval(b200s_ctx* c, int dtype) {
     return B200S_OK;
   }
   B200S_TRY(alloc_prepare(c));
-  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));  // [lo | hi] contiguous: one all-reduce when sharded
-  int64_t* const lo_buf = c->pod_lo.as<int64_t>();
-  int64_t* const hi_buf = lo_buf + P;
+  B200S_CUDA_TRY(c, c->pod_lo.ensure((size_t)P * 16));  // per chunk [lo | hi] contiguous: one all-reduce when sharded
   const uint64_t* feas = c->upstream_mask();
   const bool sharded = comm_world(c) > 1;
   B200S_CUDA_TRY(c, c->norm_params.ensure((size_t)P * sizeof(NormParam)));
-  {
-    int threads = 128, warps_per_block = threads / 32;
-    alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
-        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo_buf, hi_buf,
-        sharded ? nullptr : c->norm_params.as<NormParam>());
-    c->launches++;
-    B200S_CUDA_TRY(c, cudaGetLastError());
-  }
-  if (sharded) {
-    B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
-    B200S_TRY(build_norm_params(c, P));
-  }
   PluginOut& o = c->out[B200S_PLUGIN_ALLOCATABLE];
-  KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
   static const bool use_tma = getenv("B200S_ALLOC_TMA") && atoi(getenv("B200S_ALLOC_TMA")) != 0;
-  if (dtype == B200S_OUT_I64 && use_tma) {
-    constexpr int PT = 64, PB = 4, NSTAGE = 4;
-    constexpr size_t smem = (size_t)NSTAGE * PB * 512 * 8;
-    auto kern = alloc_norm_tma_kernel<PT, PB, NSTAGE>;
-    B200S_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((Npad + 511) / 512, (P + PT - 1) / PT);
-    kern<<<grid, 256, smem, c->stream>>>(c->alloc_raw.as<int64_t>(), c->norm_params.as<NormParam>(), feas, words, N,
-                                         Npad, P, o.scores.as<int64_t>());
-  } else if (dtype == B200S_OUT_I64) {
-    constexpr int NPT = 2, PT = 64;
-    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
-    alloc_norm_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(),
-                                                                    c->norm_params.as<NormParam>(), feas, words, N,
-                                                                    Npad, P, o.scores.as<int64_t>());
+  // pods [a, a + n): lo / hi of the feasible set (first / last feasible entry of the sorted order)
+  auto launch_minmax = [&](int a, int n) {
+    const int threads = 128, warps_per_block = threads / 32;
+    int64_t* lo = c->pod_lo.as<int64_t>() + 2 * (size_t)a;
+    alloc_minmax_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
+        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas ? feas + (size_t)a * words : nullptr, words, N,
+        n, lo, lo + n, sharded ? nullptr : c->norm_params.as<NormParam>() + a);
+    c->launches++;
+  };
+  auto launch_norm = [&](int a, int n) {
+    KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
+    const NormParam* params = c->norm_params.as<NormParam>() + a;
+    const uint64_t* fm = feas ? feas + (size_t)a * words : nullptr;
+    if (dtype == B200S_OUT_I64 && use_tma) {
+      constexpr int PT = 64, PB = 4, NSTAGE = 4;
+      constexpr size_t smem = (size_t)NSTAGE * PB * 512 * 8;
+      auto kern = alloc_norm_tma_kernel<PT, PB, NSTAGE>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid((Npad + 511) / 512, (n + PT - 1) / PT);
+      kern<<<grid, 256, smem, c->stream>>>(c->alloc_raw.as<int64_t>(), params, fm, words, N, Npad, n,
+                                           o.scores.as<int64_t>() + (size_t)a * Npad);
+    } else if (dtype == B200S_OUT_I64) {
+      constexpr int NPT = 2, PT = 64;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (n + PT - 1) / PT);
+      alloc_norm_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(), params, fm, words, N, Npad,
+                                                                      n, o.scores.as<int64_t>() + (size_t)a * Npad);
+    } else {
+      constexpr int NPT = 8, PT = 64;
+      dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (n + PT - 1) / PT);
+      alloc_norm_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(), params, fm, words, N, Npad,
+                                                                      n, o.scores.as<uint8_t>() + (size_t)a * Npad);
+    }
+    c->launches++;
+  };
+  if (!sharded) {
+    launch_minmax(0, P);
+    launch_norm(0, P);
   } else {
-    constexpr int NPT = 8, PT = 64;
-    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
-    alloc_norm_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(),
-                                                                    c->norm_params.as<NormParam>(), feas, words, N,
-                                                                    Npad, P, o.scores.as<uint8_t>());
+    // Sharded NormalizeScore needs the per-pod min/max over ALL shards before any score can be written.  The batch
+    // goes in up to 4 pod chunks: every chunk's local min/max is launched first, each chunk's all-reduce runs on the
+    // communication stream as soon as its min/max is there, and the main stream starts the P x N pass of chunk i as
+    // soon as all-reduce i has landed -- so only the first (quarter-size) all-reduce is exposed, and it overlaps the
+    // remaining chunks' min/max kernels; the others hide behind the previous chunk's P x N pass.
+    B200S_TRY(comm_ensure_streams(c));
+    // (with the peer-memory exchange the min/max costs a few microseconds on the compute stream: one chunk)
+    const int nchunk = (P >= 2048 && !comm_has_peers(c)) ? 4 : 1;
+    const int step = ((P + nchunk - 1) / nchunk + 63) / 64 * 64;
+    int starts[5], k = 0;
+    for (int a = 0; a < P; a += step) starts[k++] = a;
+    starts[k] = P;
+    for (int i = 0; i < k; ++i) {
+      const int a = starts[i], n = starts[i + 1] - a;
+      launch_minmax(a, n);
+      int64_t* lo = c->pod_lo.as<int64_t>() + 2 * (size_t)a;
+      if (k == 1) {
+        B200S_TRY(comm_allreduce_minmax_on(c, c->stream, lo, lo + n, n));
+        continue;
+      }
+      B200S_CUDA_TRY(c, cudaEventRecord(c->ev_chunk[i], c->stream));
+      B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[i], 0));
+      B200S_TRY(comm_allreduce_minmax_on(c, c->comm_stream, lo, lo + n, n));
+      B200S_CUDA_TRY(c, cudaEventRecord(c->ev_reduced[i], c->comm_stream));
+    }
+    for (int i = 0; i < k; ++i) {
+      const int a = starts[i], n = starts[i + 1] - a;
+      if (k > 1) B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_reduced[i], 0));
+      const int64_t* lo = c->pod_lo.as<int64_t>() + 2 * (size_t)a;
+      norm_params_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(lo, lo + n, n, c->norm_params.as<NormParam>() + a);
+      c->launches++;
+      launch_norm(a, n);
+    }
   }
-  c->launches++;
   B200S_CUDA_TRY(c, cudaGetLastError());
   o.valid = true;
   return B200S_OK;

@@ -271,6 +271,14 @@ void b200s_shutdown(b200s_ctx* c) {
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   nrt2_destroy(c);
+  if (c->comm_stream) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamDestroy(c->comm_stream);
+    for (int i = 0; i < 4; ++i) {
+      cudaEventDestroy(c->ev_chunk[i]);
+      cudaEventDestroy(c->ev_reduced[i]);
+    }
+  }
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
                     &c->alloc_iota,      &c->sort_tmp,         &c->tlp_util,         &c->tlp_cap,
                     &c->tlp_missing,     &c->tlp_flags,        &c->lvrb_f64,         &c->lvrb_i64,

@@ -83,6 +83,9 @@ struct b200s_ctx {
   // already copies chunk i+1's inputs in (PCIe is full duplex) -- created on first use
   cudaStream_t d2h_stream = nullptr;
   cudaEvent_t ev_kernels = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+  // sharded NormalizeScore: all-reduces run here while the main stream computes (created on first use)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr}, ev_reduced[4] = {nullptr, nullptr, nullptr, nullptr};
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
@@ -284,7 +287,10 @@ void nrt2_note_direct(b200s_ctx* c);
 int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint64_t* mismatches);
 
 // comm.cu
-int comm_allreduce_minmax(b200s_ctx* c, int64_t* lo, int64_t* hi, int count);  // in place, device
+int comm_allreduce_minmax(b200s_ctx* c, int64_t* lo, int64_t* hi, int count);  // in place, device, on c->stream
+int comm_allreduce_minmax_on(b200s_ctx* c, cudaStream_t stream, int64_t* lo, int64_t* hi, int count);
+int comm_ensure_streams(b200s_ctx* c);  // comm_stream + the chunk events
+bool comm_has_peers(b200s_ctx* c);    // peer-memory exchange available (b200s_comm_peer_import done)
 int comm_allgather(b200s_ctx* c, const void* send, void* recv, size_t bytes_per_rank);
 int comm_rank(b200s_ctx* c);
 int comm_world(b200s_ctx* c);
@@ -300,17 +306,18 @@ int ensure_out(b200s_ctx* c, int plugin, int dtype, bool feas, bool reasons);
 struct KernelTimer {
   b200s_ctx* c;
   int plugin;
+  cudaStream_t stream;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  KernelTimer(b200s_ctx* ctx, int pl) : c(ctx), plugin(pl) {
+  KernelTimer(b200s_ctx* ctx, int pl, cudaStream_t st = nullptr) : c(ctx), plugin(pl), stream(st ? st : ctx->stream) {
     if (c->profiling) {
       e0 = c->prof_get();
       e1 = c->prof_get();
-      cudaEventRecord(e0, c->stream);
+      cudaEventRecord(e0, stream);
     }
   }
   ~KernelTimer() {
     if (e0) {
-      cudaEventRecord(e1, c->stream);
+      cudaEventRecord(e1, stream);
       c->prof_pending[plugin].push_back({e0, e1});
     }
   }

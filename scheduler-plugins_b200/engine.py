@@ -45,7 +45,7 @@ EXPORTS = [
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
-    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time",
+    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import",
 ]
 
 
@@ -208,6 +208,18 @@ class Engine:
         return PinnedBuffer(self.lib, nbytes)
 
     # -- multi-GPU ------------------------------------------------------------------------
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle of this rank's symmetric exchange buffer (after comm_init)."""
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.b200s_comm_peer_export(self.ctx, buf))
+        return buf.raw
+
+    def peer_import(self, handles):
+        """handles: list of every rank's peer_export() bytes, in rank order; switches the per-pod exchanges from NCCL
+        to stores into peer memory over NVLink."""
+        blob = b"".join(handles)
+        self._chk(self.lib.b200s_comm_peer_import(self.ctx, C.c_char_p(blob)))
+
     def unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()
         rc = self.lib.b200s_comm_unique_id(buf)

@@ -38,6 +38,10 @@ def main():
     uid = [eng.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     eng.comm_init(uid[0], rank, world)
+    if os.environ.get("B200S_TEST_PEER", "1") == "1":  # the per-pod exchanges over peer memory instead of NCCL
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.peer_export())
+        eng.peer_import(handles)
     load_engine(eng, E, d, cnt, P, feas, node_offset=off, n_global=N)
     weights = [2, 1, 1, 3, 5]
 
@@ -77,7 +81,8 @@ def main():
     assert np.array_equal(eng.fetch_scores(E.PLUGIN_PEAKS)[:, :cnt], want[:, sl]), f"rank {rank}: sharded Peaks differs"
     dist.barrier()
     if rank == 0:
-        print(f"mgpu ok: world={world} P={P} N={N} shards={sharding.shard_bounds(N, world)}")
+        print(f"mgpu ok: world={world} P={P} N={N} shards={sharding.shard_bounds(N, world)} "
+              f"exchange={'peer' if os.environ.get('B200S_TEST_PEER', '1') == '1' else 'nccl'}")
     eng.close()
     dist.destroy_process_group()
 

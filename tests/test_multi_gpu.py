@@ -10,7 +10,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_sharded_parity(built):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_gpu_sharded_parity(built, exchange):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -18,6 +19,7 @@ def test_two_gpu_sharded_parity(built):
     port = 29700 + os.getpid() % 200
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, B200S_TEST_PEER="1" if exchange == "peer" else "0"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "mgpu ok" in r.stdout
+    assert "mgpu ok" in r.stdout and f"exchange={exchange}" in r.stdout
