@@ -337,6 +337,7 @@ static int alloc_prepare(b200s_ctx* c) {
                                                       c->alloc_order.as<int32_t>(), N, 0, 64, c->stream));
   }
   c->alloc_prepared_key = key;
+  B200S_CUDA_TRY(c, cudaEventRecord(c->ev_inputs, c->stream));  // raw scores + sorted order queued up to here
   return B200S_OK;
 }
 
@@ -395,14 +396,57 @@ int alloc_eval(b200s_ctx* c, int dtype) {
   if (!sharded) {
     launch_minmax(0, P);
     launch_norm(0, P);
-  } else {
-    // Sharded NormalizeScore needs the per-pod min/max over ALL shards before any score can be written.  The batch
-    // goes in up to 4 pod chunks: every chunk's local min/max is launched first, each chunk's all-reduce runs on the
-    // communication stream as soon as its min/max is there, and the main stream starts the P x N pass of chunk i as
-    // soon as all-reduce i has landed -- so only the first (quarter-size) all-reduce is exposed, and it overlaps the
-    // remaining chunks' min/max kernels; the others hide behind the previous chunk's P x N pass.
+  } else if (comm_has_peers(c) && c->mask_override == nullptr) {
+    // Sharded NormalizeScore needs the per-pod min/max over ALL shards before any score can be written.  With the
+    // peer-memory exchange the whole pre-pass (local min/max, exchange, fold, parameters) is a handful of small
+    // kernels that depend on the batch's INPUTS only -- not on the previous eval.  It runs on the high-priority
+    // communication stream, so back-to-back evals overlap it with the previous eval's P x N kernel; the parameter
+    // buffers alternate between two copies, and a copy is reused only after the P x N kernel that read it is done.
     B200S_TRY(comm_ensure_streams(c));
-    // (with the peer-memory exchange the min/max costs a few microseconds on the compute stream: one chunk)
+    const int par = (int)(c->alloc_eval_seq++ & 1);
+    DevBuf& lo_b = par ? c->pod_lo_alt : c->pod_lo;
+    DevBuf& np_b = par ? c->norm_params_alt : c->norm_params;
+    B200S_CUDA_TRY(c, lo_b.ensure((size_t)P * 16));
+    B200S_CUDA_TRY(c, np_b.ensure((size_t)P * sizeof(NormParam)));
+    cudaStream_t cs = c->comm_stream;
+    B200S_CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_inputs, 0));
+    if (c->ev_norm_valid[par]) B200S_CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_norm_done[par], 0));
+    int64_t* lo = lo_b.as<int64_t>();
+    {
+      const int threads = 128, warps_per_block = threads / 32;
+      alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, cs>>>(
+          c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo, lo + P, nullptr);
+      c->launches++;
+    }
+    B200S_TRY(comm_allreduce_minmax_on(c, cs, lo, lo + P, P));
+    norm_params_kernel<<<(P + 255) / 256, 256, 0, cs>>>(lo, lo + P, P, np_b.as<NormParam>());
+    c->launches++;
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_params[par], cs));
+    B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_params[par], 0));
+    {
+      KernelTimer kt(c, B200S_PLUGIN_ALLOCATABLE);
+      const NormParam* params = np_b.as<NormParam>();
+      if (dtype == B200S_OUT_I64) {
+        constexpr int NPT = 2, PT = 64;
+        dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+        alloc_norm_kernel<int64_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(), params, feas, words, N,
+                                                                        Npad, P, o.scores.as<int64_t>());
+      } else {
+        constexpr int NPT = 8, PT = 64;
+        dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+        alloc_norm_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->alloc_raw.as<int64_t>(), params, feas, words, N,
+                                                                        Npad, P, o.scores.as<uint8_t>());
+      }
+      c->launches++;
+    }
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_norm_done[par], c->stream));
+    c->ev_norm_valid[par] = true;
+  } else {
+    // NCCL exchange (no peer mappings, or a filter chain feeding the mask on the main stream): the batch goes in up
+    // to 4 pod chunks; every chunk's local min/max is launched first, each chunk's all-reduce runs on the
+    // communication stream as soon as its min/max is there, and the main stream starts the P x N pass of chunk i as
+    // soon as all-reduce i has landed.
+    B200S_TRY(comm_ensure_streams(c));
     const int nchunk = (P >= 2048 && !comm_has_peers(c)) ? 4 : 1;
     const int step = ((P + nchunk - 1) / nchunk + 63) / 64 * 64;
     int starts[5], k = 0;

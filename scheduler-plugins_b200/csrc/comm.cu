@@ -253,6 +253,10 @@ int comm_ensure_streams(b200s_ctx* c) {
     B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_reduced[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < 2; ++i) {
+    B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_params[i], cudaEventDisableTiming));
+    B200S_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_norm_done[i], cudaEventDisableTiming));
+  }
   return B200S_OK;
 }
 

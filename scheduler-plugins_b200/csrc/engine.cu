@@ -256,6 +256,7 @@ int b200s_init(int device, b200s_ctx** out) {
   c->device = device;
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     tl_err = std::string("b200s_init: ") + cudaGetErrorString(e);
     delete c;
@@ -278,7 +279,14 @@ void b200s_shutdown(b200s_ctx* c) {
       cudaEventDestroy(c->ev_chunk[i]);
       cudaEventDestroy(c->ev_reduced[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(c->ev_params[i]);
+      cudaEventDestroy(c->ev_norm_done[i]);
+    }
   }
+  if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
+  c->pod_lo_alt.release();
+  c->norm_params_alt.release();
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
                     &c->alloc_iota,      &c->sort_tmp,         &c->tlp_util,         &c->tlp_cap,
                     &c->tlp_missing,     &c->tlp_flags,        &c->lvrb_f64,         &c->lvrb_i64,
@@ -623,6 +631,7 @@ int b200s_snapshot_commit(b200s_ctx* c) {
   c->snap_patching = false;
   c->snap_valid = true;
   c->snap_serial++;
+  B200S_CUDA_TRY(c, cudaEventRecord(c->ev_inputs, c->stream));
   return B200S_OK;
 }
 
@@ -1014,6 +1023,7 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
     for (int p = 0; p < P; ++p) c->netoh_max_deps = std::max(c->netoh_max_deps, q->dep_offset[p + 1] - q->dep_offset[p]);
   }
   B200S_TRY(up.flush(c));
+  B200S_CUDA_TRY(c, cudaEventRecord(c->ev_inputs, c->stream));  // the batch's columns are queued up to here
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
   if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& o : c->out) o.valid = false;

@@ -86,6 +86,12 @@ struct b200s_ctx {
   // sharded NormalizeScore: all-reduces run here while the main stream computes (created on first use)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr}, ev_reduced[4] = {nullptr, nullptr, nullptr, nullptr};
+  // cross-eval overlap of the sharded Allocatable pre-pass (min/max, exchange, parameters) with the previous eval's
+  // P x N kernel: inputs-ready marker on the main stream, per-parity parameter buffers and their hand-over events
+  cudaEvent_t ev_inputs = nullptr, ev_params[2] = {nullptr, nullptr}, ev_norm_done[2] = {nullptr, nullptr};
+  bool ev_norm_valid[2] = {false, false};
+  uint64_t alloc_eval_seq = 0;
+  b200s::DevBuf pod_lo_alt, norm_params_alt;  // parity-1 twins of pod_lo / norm_params
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
