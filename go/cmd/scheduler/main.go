@@ -1,0 +1,54 @@
+// kube-scheduler with the five data-parallel plugins behind libb200sched (replaces cmd/scheduler/main.go of the
+// reference; the registry NAMES are unchanged, so an existing KubeSchedulerConfiguration keeps working -- only the
+// factories of :50-67 are swapped).  Every *B200 factory degrades to the original plugin when no GPU is usable.
+// Never compiled in this repository (no Go toolchain).
+package main
+
+import (
+	"os"
+
+	"k8s.io/component-base/cli"
+	_ "k8s.io/component-base/metrics/prometheus/clientgo" // for rest client metric registration
+	_ "k8s.io/component-base/metrics/prometheus/version"  // for version metric registration
+	"k8s.io/kubernetes/cmd/kube-scheduler/app"
+
+	"sigs.k8s.io/scheduler-plugins/pkg/capacityscheduling"
+	"sigs.k8s.io/scheduler-plugins/pkg/coscheduling"
+	"sigs.k8s.io/scheduler-plugins/pkg/networkaware/networkoverhead"
+	"sigs.k8s.io/scheduler-plugins/pkg/networkaware/topologicalsort"
+	"sigs.k8s.io/scheduler-plugins/pkg/noderesources"
+	"sigs.k8s.io/scheduler-plugins/pkg/noderesourcetopology"
+	"sigs.k8s.io/scheduler-plugins/pkg/podstate"
+	"sigs.k8s.io/scheduler-plugins/pkg/preemptiontoleration"
+	"sigs.k8s.io/scheduler-plugins/pkg/qos"
+	"sigs.k8s.io/scheduler-plugins/pkg/sysched"
+	"sigs.k8s.io/scheduler-plugins/pkg/trimaran/loadvariationriskbalancing"
+	"sigs.k8s.io/scheduler-plugins/pkg/trimaran/lowriskovercommitment"
+	"sigs.k8s.io/scheduler-plugins/pkg/trimaran/peaks"
+	"sigs.k8s.io/scheduler-plugins/pkg/trimaran/targetloadpacking"
+
+	// Ensure scheme package is initialized.
+	_ "sigs.k8s.io/scheduler-plugins/apis/config/scheme"
+)
+
+func main() {
+	command := app.NewSchedulerCommand(
+		app.WithPlugin(capacityscheduling.Name, capacityscheduling.New),
+		app.WithPlugin(coscheduling.Name, coscheduling.New),
+		app.WithPlugin(loadvariationriskbalancing.Name, loadvariationriskbalancing.NewB200), // was loadvariationriskbalancing.New
+		app.WithPlugin(networkoverhead.Name, networkoverhead.NewB200),                       // was networkoverhead.New
+		app.WithPlugin(topologicalsort.Name, topologicalsort.New),
+		app.WithPlugin(noderesources.AllocatableName, noderesources.NewAllocatableB200), // was noderesources.NewAllocatable
+		app.WithPlugin(noderesourcetopology.Name, noderesourcetopology.NewB200),         // was noderesourcetopology.New
+		app.WithPlugin(preemptiontoleration.Name, preemptiontoleration.New),
+		app.WithPlugin(targetloadpacking.Name, targetloadpacking.NewB200), // was targetloadpacking.New
+		app.WithPlugin(lowriskovercommitment.Name, lowriskovercommitment.New),
+		app.WithPlugin(sysched.Name, sysched.New),
+		app.WithPlugin(peaks.Name, peaks.New),
+		app.WithPlugin(podstate.Name, podstate.New),
+		app.WithPlugin(qos.Name, qos.New),
+	)
+
+	code := cli.Run(command)
+	os.Exit(code)
+}
