@@ -4,6 +4,7 @@
 #include <pybind11/stl.h>
 
 #include "plugins.hpp"
+#include "nrt_scalar.hpp"
 
 namespace py = pybind11;
 using namespace b200host;
@@ -214,6 +215,17 @@ PYBIND11_MODULE(_b200host, m) {
       .def(py::init<>())
       .def_readwrite("scoring_strategy", &NodeResourceTopologyMatchArgs::scoring_strategy)
       .def_readwrite("resources", &NodeResourceTopologyMatchArgs::resources);
+  // the scalar path for shapes outside the dense encoding (host/nrt_scalar.cpp): exposed so that the reference's
+  // TestNUMANodesRequired vectors with unsorted / sparse NUMA ids are COMPUTED, not skipped
+  m.def("numa_nodes_required", [](int qos, const NodeResourceTopology& nrt, const ResourceList& resources) {
+    bool is_min = false;
+    auto ids = NumaNodesRequired((QOS)qos, CreateNUMANodeList(nrt), resources, &is_min);
+    return py::make_tuple(ids, is_min);
+  });
+  m.def("scalar_filter", [](const Pod& pod, const NodeInfo& ni, const NodeResourceTopology& nrt) { return ScalarFilter(pod, ni, nrt); });
+  m.def("scalar_score", [](const Pod& pod, const NodeResourceTopology& nrt, int strategy, const std::map<std::string, int64_t>& w) {
+    return ScalarScore(pod, nrt, strategy, w);
+  });
   py::class_<TopologyMatch>(m, "TopologyMatch")
       .def_static("new", &TopologyMatch::New)
       .def("name", &TopologyMatch::Name)

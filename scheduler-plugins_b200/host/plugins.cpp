@@ -1,5 +1,6 @@
 // C++ mirror of the five plugins: flatten -> C-ABI -> per-node lookup.  See plugins.hpp.
 #include "plugins.hpp"
+#include "nrt_scalar.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -773,6 +774,7 @@ std::shared_ptr<CycleResult> TopologyMatch::Run(CycleState& state, const Pod& po
         max_numa[i] = (uint16_t)tm.max_numa_nodes;
         if (!ok[i]) {
           fl |= B200S_NRT_NODE_UNSUPPORTED;
+          c->unsupported_nodes.insert(i);
         } else {
           nz[i] = (uint8_t)zl[i].size();
           for (size_t z = 0; z < zl[i].size(); ++z) {
@@ -882,7 +884,14 @@ Status TopologyMatch::Filter(CycleState& state, const Pod& pod, const NodeInfo& 
     case B200S_REASON_NRT_ALIGN_SIDECAR: return {Code::Unschedulable, "cannot align sidecar container"};
     case B200S_REASON_NRT_ACCOUNTING: return {Code::Error, "inconsistent resource accounting"};
     case B200S_REASON_UNSUPPORTED:
-      return ErrorStatus("shape outside the dense encoding: evaluate this node with the embedded Go plugin");
+      // shape outside the dense encoding (NUMA ids not 0..k-1 in order, > 8 zones / resources / containers): this
+      // pair is answered by the scalar path on the host objects -- what the embedded Go plugin is in the Go shim.
+      // The reference's gates up to here (fresh, NRT present, single-numa-node) already passed in the kernel.
+      try {
+        return ScalarFilter(pod, nodeInfo, *h_->nrts.at(nodeInfo.GetNode()->name));
+      } catch (const std::exception& e) {
+        return ErrorStatus(e.what());
+      }
     default: return ErrorStatus("unexpected reason code");
   }
 }
@@ -893,6 +902,19 @@ std::pair<int64_t, Status> TopologyMatch::Score(CycleState& state, const Pod& po
   if (!c->engine_error.empty()) return {0, ErrorStatus(c->engine_error)};
   auto it = c->index.find(nodeInfo.GetNode()->name);
   if (it == c->index.end()) return {0, ErrorStatus("node not in the cycle's snapshot")};
+  if (c->reasons[it->second] == B200S_REASON_UNSUPPORTED ||
+      (c->unsupported_nodes.count(it->second) && GetPodQOS(pod) == QOS::Guaranteed)) {
+    // outside the dense encoding: the scalar path (score.go:88-101 after the QoS / freshness / nil-NRT gates)
+    try {
+      std::map<std::string, int64_t> w;
+      for (auto& rs : args_.resources) w[rs.name] = rs.weight;
+      auto nf = h_->nrt_not_fresh.find(nodeInfo.GetNode()->name);
+      if (nf != h_->nrt_not_fresh.end() && nf->second) return {0, Status{}};
+      return {ScalarScore(pod, *h_->nrts.at(nodeInfo.GetNode()->name), strategy_, w), Status{}};
+    } catch (const std::exception& e) {
+      return {0, ErrorStatus(e.what())};
+    }
+  }
   // upstream only scores nodes that passed every filter; a node this plugin rejected has no score
   return {(int64_t)c->scores[it->second], Status{}};
 }

@@ -12,6 +12,7 @@
 #pragma once
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -89,6 +90,7 @@ struct CycleResult {
   std::vector<uint64_t> feasible;
   std::vector<uint8_t> reasons;
   std::string engine_error;              // non-empty: the engine call failed
+  std::set<int32_t> unsupported_nodes;   // NodeResourceTopologyMatch: columns whose NRT is outside the dense encoding
   bool score_equally = false;            // NetworkOverhead
   std::vector<int64_t> satisfied, violated;  // diagnostics for NetworkOverhead's message (host-side recount)
 };

@@ -256,6 +256,29 @@ def test_topology_match_scores(H):
         H.TopologyMatch.new(bad, nrt_handle(H, fixture))
 
 
+def test_topology_match_outside_the_dense_encoding(H):
+    """Reason code 9 has somewhere to go: nodes whose zone list is not in NUMA-id order (or is sparse) are answered by
+    the host's scalar path (host/nrt_scalar.cpp) -- Filter statuses and Least/Most/Balanced scores equal those of the
+    same node listed in id order, which the engine evaluates itself."""
+    g = load("nrt_filter.json")
+    for suite in g["suites"]:
+        straight = nrt_handle(H, suite["nodes"])
+        shuffled = nrt_handle(H, [dict(n, zones=list(reversed(n["zones"]))) for n in suite["nodes"]])
+        for strategy in ("LeastAllocated", "MostAllocated", "BalancedAllocation"):
+            args = H.NodeResourceTopologyMatchArgs()
+            args.scoring_strategy = strategy
+            a, b = H.TopologyMatch.new(args, straight), H.TopologyMatch.new(args, shuffled)
+            for case in suite["cases"][:12]:
+                pod = make_pod(H, case["pod"])
+                sa, sb = H.CycleState(), H.CycleState()
+                for i in range(len(suite["nodes"])):
+                    fa, fb = a.filter(sa, pod, straight.node_infos[i]), b.filter(sb, pod, shuffled.node_infos[i])
+                    assert (fa.code, fa.message) == (fb.code, fb.message), (suite["suite"], case["name"], i)
+                    if fa.is_success():
+                        assert a.score(sa, pod, straight.node_infos[i])[0] == b.score(sb, pod, shuffled.node_infos[i])[0], \
+                            (suite["suite"], case["name"], i, strategy)
+
+
 def test_topology_match_stale_and_missing_nrt(H):
     """filter.go:194-200 / score.go:79-86."""
     g = load("nrt_score.json")["suites"][0]

@@ -199,3 +199,96 @@ def test_resource_classes_reference_vectors(H, name, host_level, affine):
     the NRT snapshot's res_flags -- on the C++ host and in the Python flatten rules."""
     assert H.is_host_level_resource(name) is host_level and F.is_host_level(name) is host_level
     assert H.is_numa_affine_resource(name) is affine and F.is_numa_affine(name) is affine
+
+
+# ------------------------------------------------------------------ the scalar path for shapes outside the dense encoding
+def _nrt_of(H, zones):
+    t = H.NodeResourceTopology()
+    zs = []
+    for z in zones:
+        zz = H.Zone()
+        zz.name, zz.type = f"node-{z['id']}", "Node"
+        zz.resources = {r: H.ZoneResource(H.parse_quantity(q), H.parse_quantity(q)) for r, q in z["resources"].items()}
+        zz.costs = {f"node-{d}": c for d, c in z["costs"].items()}
+        zs.append(zz)
+    t.zones = zs
+    return t
+
+
+def _nnr_cases():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "numa_nodes_required.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _nnr_cases(), ids=lambda c: c["name"][:70])
+def test_numa_nodes_required_all_vectors_through_the_host_scalar_path(H, case):
+    """TestNUMANodesRequired (least_numa_test.go:35-704), ALL ten vectors -- including the five whose NUMA ids are
+    unsorted or sparse, which the dense encoding flags UNSUPPORTED: reason code 9 is answered by
+    host/nrt_scalar.cpp, which follows the reference's list-order / id-keyed semantics and computes them."""
+    ids, is_min = H.numa_nodes_required(0, _nrt_of(H, case["zones"]), H.resource_list(case["pod"]))
+    if case["expected_bits"] is None:
+        assert ids == []
+        return
+    assert ids == sorted(case["expected_bits"])
+    assert is_min == case["expected_min_distance"]
+
+
+def test_scalar_filter_and_score_do_not_depend_on_zone_list_order(H):
+    """Filter picks the LOWEST NUMA id (filter.go:154) and the Least/Most/Balanced scores take a minimum over zones
+    (score.go:110-124): listing the zones in another order must not change either.  Checks the scalar path against
+    itself on every filter_test.go case with the zone list reversed (ids then no longer match list positions)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    g = json.load(open(os.path.join(GOLDEN, "nrt_filter.json")))
+    checked = 0
+    for suite in g["suites"]:
+        for case in suite["cases"]:
+            n = suite["nodes"][case["node"]]
+            def build(zones):
+                t = H.NodeResourceTopology()
+                t.name = n["name"]
+                t.topology_policies = n["policies"]
+                t.attributes = n.get("attributes", {})
+                zs = []
+                for z in zones:
+                    zz = H.Zone()
+                    zz.name, zz.type = z["name"], z.get("type", "Node")
+                    zz.resources = {r: H.ZoneResource(H.parse_quantity(q["capacity"]), H.parse_quantity(q["available"]))
+                                    for r, q in z["resources"].items()}
+                    zz.costs = z.get("costs", {})
+                    zs.append(zz)
+                t.zones = zs
+                return t
+            alloc = {}
+            for z in n["zones"]:
+                for r, q in z["resources"].items():
+                    alloc[r] = alloc.get(r, 0) + F.milli(q["available"])
+            node = H.Node()
+            node.name = n["name"]
+            node.allocatable = H.resource_list({**{r: f"{v}m" for r, v in alloc.items()}, **n.get("node_extra", {})})
+            ni = H.NodeInfo(node)
+            pod = mkpod_from_golden(H, case["pod"])
+            a = H.scalar_filter(pod, ni, build(n["zones"]))
+            b = H.scalar_filter(pod, ni, build(list(reversed(n["zones"]))))
+            assert (a.code, a.message) == (b.code, b.message), case["name"]
+            # ScalarFilter is the stage after the freshness / nil-NRT gates: on every case whose expectation does not
+            # come from those gates it must give the reference's verdict by itself
+            want = case["want"]["message"] if case["want"] else None
+            if want != "invalid node topology data":
+                assert (a.message if not a.is_success() else None) == want or (want and a.message.startswith(want)), case["name"]
+            checked += 1
+    assert checked == 71
+
+
+def mkpod_from_golden(H, spec):
+    """the golden pod format of tests/golden/nrt_filter.json ('init' / 'containers' lists with requests / limits)"""
+    return mkpod(H, {"init": spec.get("init", spec.get("init_containers", [])), "containers": spec.get("containers", []),
+                     "overhead": spec.get("overhead")})
