@@ -906,6 +906,7 @@ std::pair<int64_t, Status> TopologyMatch::Score(CycleState& state, const Pod& po
       (c->unsupported_nodes.count(it->second) && GetPodQOS(pod) == QOS::Guaranteed)) {
     // outside the dense encoding: the scalar path (score.go:88-101 after the QoS / freshness / nil-NRT gates)
     try {
+      if (GetPodQOS(pod) != QOS::Guaranteed) return {100, Status{}};  // score.go:72-75 comes before everything
       std::map<std::string, int64_t> w;
       for (auto& rs : args_.resources) w[rs.name] = rs.weight;
       auto nf = h_->nrt_not_fresh.find(nodeInfo.GetNode()->name);
