@@ -333,13 +333,18 @@ def cycle_latency(E, synth, device, N, cycles=1000):
     res["NodeResourcesAllocatable"] = p50(lambda: eng.score_batch(E.PLUGIN_ALLOCATABLE, batch, E.OUT_U8, row))
     w = PROFILE_WEIGHTS
 
-    def combined():
-        eng._chk(eng.lib.b200s_pods_upload(eng.ctx, C.byref(batch)))
-        eng.P = 1
-        eng.eval_combined(0b11111, w, k=1, write_total=False)
-        eng.fetch_topk()
+    topk1 = np.empty((1, 1), dtype=E.TOPK_DTYPE)
+
+    def combined():  # ONE C-ABI call: pod columns in, winner out (b200s_schedule_batch)
+        eng.schedule_batch(batch, 0b11111, w, k=1, out=topk1)
 
     res["all_five_plugins_top1"] = p50(combined)
+    res["all_five_plugins_top1"]["path"] = "b200s_schedule_batch -> cycle.cu: one cooperative kernel for the whole cycle"
+    fused_winner = (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"]))
+    eng.config_fused_cycle(False)  # the plugin-by-plugin path of round 1 (13 launches) for comparison
+    res["all_five_plugins_top1_plugin_by_plugin"] = p50(combined)
+    assert (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"])) == fused_winner, "fused cycle and plugin-by-plugin path disagree"
+    eng.config_fused_cycle(True)
 
     # snapshot refresh between two cycles: a node event changes a few NodeInfos.  Either the host
     # re-uploads every column of all five plugins, or it patches the 16 rows that changed; both leave the engine

@@ -385,6 +385,15 @@ int b200s_eval_combined(b200s_ctx* ctx, uint32_t plugin_mask,
                         const int64_t* weights /* [B200S_PLUGIN_COUNT] */, int32_t k,
                         int write_total_matrix);
 int b200s_fetch_topk(b200s_ctx* ctx, b200s_topk_entry* out, size_t bytes); /* [P][k] */
+/* Small batches (<= 4 pods -- the real scheduler runs one pod per cycle) on a single GPU go through ONE cooperative
+ * kernel that does the whole cycle (filters, scores, NormalizeScore, weighted sum, top-k) without materialising any
+ * per-plugin matrix; b200s_fetch_total_feasible still works, b200s_fetch_scores of the individual plugins does not.
+ * on = 0 keeps the plugin-by-plugin path for every batch size (parity tests, A/B timing).  Default on. */
+int b200s_config_fused_cycle(b200s_ctx* ctx, int on);
+/* The engine-only profile in ONE call with ONE synchronisation: upload the batch's pod columns (HOST pointers),
+ * evaluate the weighted combination, copy the [n_pods][k] winners to topk_out (HOST). */
+int b200s_schedule_batch(b200s_ctx* ctx, const b200s_pod_batch* batch, uint32_t plugin_mask,
+                         const int64_t* weights /* [B200S_PLUGIN_COUNT] */, int32_t k, b200s_topk_entry* topk_out);
 int b200s_fetch_total(b200s_ctx* ctx, int64_t* out, size_t bytes);          /* [P][Npad] */
 int b200s_fetch_total_feasible(b200s_ctx* ctx, uint64_t* out, size_t bytes);
 

@@ -310,7 +310,7 @@ int build_norm_params(b200s_ctx* c, int P) {
   return B200S_OK;
 }
 
-static int alloc_prepare(b200s_ctx* c) {
+int alloc_prepare(b200s_ctx* c) {
   uint64_t key = c->snap_serial * 1000003ull + c->alloc_cfg_gen;
   if (c->alloc_prepared_key == key) return B200S_OK;
   const int N = c->N, Npad = c->Npad;

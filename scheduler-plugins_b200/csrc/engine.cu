@@ -286,6 +286,8 @@ void b200s_shutdown(b200s_ctx* c) {
   }
   if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
   c->pod_lo_alt.release();
+  c->cycle_scratch.release();
+  if (c->small_bounce) cudaFreeHost(c->small_bounce);
   c->norm_params_alt.release();
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
                     &c->alloc_iota,      &c->sort_tmp,         &c->tlp_util,         &c->tlp_cap,
@@ -1065,6 +1067,15 @@ static int fetch(b200s_ctx* c, const DevBuf& src, void* out, size_t bytes, size_
   if (!out) return c->set_err(B200S_ERR_INVALID, std::string(what) + ": null output");
   if (bytes < want) return c->set_err(B200S_ERR_INVALID, std::string(what) + ": output buffer too small");
   if (want == 0) return B200S_OK;
+  if (want <= (size_t)4096 && !c->defer_sync) {
+    // small results (a cycle's winners): a device-to-host copy into PAGEABLE memory takes the driver's slow staged
+    // path (~10 us); bounce through the engine's pinned page instead
+    if (!c->small_bounce) B200S_CUDA_TRY(c, cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocDefault));
+    B200S_CUDA_TRY(c, cudaMemcpyAsync(c->small_bounce, src.p, want, cudaMemcpyDeviceToHost, c->stream));
+    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, c->small_bounce, want);
+    return B200S_OK;
+  }
   B200S_CUDA_TRY(c, cudaMemcpyAsync(out, src.p, want, cudaMemcpyDeviceToHost, c->stream));
   if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return B200S_OK;
@@ -1214,6 +1225,39 @@ static int score_batch_chunked(b200s_ctx* c, b200s_plugin plugin, const b200s_po
     B200S_CUDA_TRY(c, cudaEventRecord(c->ev_d2h, c->d2h_stream));
   }
   return rc;
+}
+
+int b200s_config_fused_cycle(b200s_ctx* c, int on) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->fused_cycle = on != 0;
+  return B200S_OK;
+}
+
+int b200s_schedule_batch(b200s_ctx* c, const b200s_pod_batch* batch, uint32_t plugin_mask, const int64_t* weights, int32_t k,
+                         b200s_topk_entry* topk_out) {
+  if (!c || !topk_out) return B200S_ERR_INVALID;
+  Guard g(c);
+  struct Defer {
+    b200s_ctx* c;
+    explicit Defer(b200s_ctx* x) : c(x) { c->defer_sync = true; }
+    ~Defer() { c->defer_sync = false; }
+  } defer(c);
+  int rc = pods_upload_locked(c, batch);
+  if (rc == B200S_OK) rc = combined_eval(c, plugin_mask, weights, k, 0);
+  const size_t want = rc == B200S_OK ? (size_t)c->P * k * sizeof(b200s_topk_entry) : 0;
+  void* dst = topk_out;
+  if (want > 0 && want <= 4096) {  // pinned bounce page: a copy into pageable memory takes the driver's slow path
+    if (!c->small_bounce && cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocDefault) != cudaSuccess) c->small_bounce = nullptr;
+    if (c->small_bounce) dst = c->small_bounce;
+  }
+  if (want > 0 && cudaMemcpyAsync(dst, c->topk_final.p, want, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+    rc = c->set_err(B200S_ERR_CUDA, "schedule_batch: copy of the winners failed");
+  cudaError_t e = cudaStreamSynchronize(c->stream);  // also on the error path: inputs must not be in flight on return
+  if (rc != B200S_OK) return rc;
+  if (e != cudaSuccess) return c->set_err(B200S_ERR_CUDA, std::string("schedule_batch: ") + cudaGetErrorString(e));
+  if (dst != topk_out) memcpy(topk_out, dst, want);
+  return B200S_OK;
 }
 
 int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,

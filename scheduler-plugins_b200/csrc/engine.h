@@ -227,6 +227,11 @@ struct b200s_ctx {
   b200s::DevBuf topk_all;    // [world][P][k]
   b200s::DevBuf topk_final;  // [P][k]
   b200s::DevBuf topk_slices; // [slices][P][k] per-node-slice winners of a small batch
+  void* small_bounce = nullptr;  // one pinned page for small device-to-host results (a cycle's winners)
+  void* cycle_cells_base = nullptr;
+  bool cycle_cells_zero = false; // the fused cycle's min/max cells are zero (the folding CTA resets them)
+  bool fused_cycle = true;      // b200s_config_fused_cycle: small batches go through cycle.cu's single kernel
+  b200s::DevBuf cycle_scratch;  // fused cycle kernel: min/max cells, per-node partial scores, per-block winners
   int topk_k = 0;
   bool total_valid = false, topk_valid = false;
 
@@ -276,6 +281,10 @@ int netoh_eval(b200s_ctx* c, int dtype);
 int peaks_eval(b200s_ctx* c, int dtype);
 int lowrisk_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
+int alloc_prepare(b200s_ctx* c);  // raw scores + sorted order of the snapshot (cached per snapshot / args)
+// cycle.cu: the whole cycle as one cooperative kernel (small P, single GPU)
+bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total);
+int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k);
 
 // nrt2.cu: batched NodeResourceTopologyMatch path (score tables per distinct request vector + coalesced expansion)
 void nrt2_destroy(b200s_ctx* c);

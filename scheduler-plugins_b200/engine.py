@@ -45,7 +45,8 @@ EXPORTS = [
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
-    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import",
+    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import", "b200s_config_fused_cycle",
+    "b200s_schedule_batch",
 ]
 
 
@@ -501,6 +502,20 @@ class Engine:
         self._chk(self.lib.b200s_eval_combined(self.ctx, C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k),
                                                C.c_int(1 if write_total else 0)))
         self._k = k
+
+    def config_fused_cycle(self, on: bool):
+        self._chk(self.lib.b200s_config_fused_cycle(self.ctx, C.c_int(1 if on else 0)))
+
+    def schedule_batch(self, batch, plugin_mask, weights, k=1, out=None):
+        """upload + eval_combined + winners to host in ONE call / ONE synchronisation; returns [P][k] TOPK_DTYPE"""
+        w = np.zeros(PLUGIN_COUNT, dtype=np.int64)
+        w[:len(weights)] = np.asarray(weights, dtype=np.int64)
+        P = int(batch.n_pods)
+        if out is None:
+            out = np.empty((P, k), dtype=TOPK_DTYPE)
+        self._chk(self.lib.b200s_schedule_batch(self.ctx, C.byref(batch), C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k), _ptr(out)))
+        self.P, self._k = P, k
+        return out
 
     def fetch_topk(self):
         out = np.empty((self.P, self._k), dtype=TOPK_DTYPE)

@@ -104,3 +104,37 @@ def test_combined_without_total_matrix_and_no_upstream_mask(eng, engine_mod):
     _, _, want = oracle_combined(d, P, N, eng.Npad, None, weights, 2, 0b11111, nrt_strategy=3)
     for p in range(P):
         assert [(int(e["score"]), int(e["node"])) for e in got[p]] == want[p]
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+@pytest.mark.parametrize("mask,k,strategy", [(0b11111, 1, 2), (0b11111, 4, 0), (0b11111, 16, 1), (0b01001, 3, 2), (0b10110, 2, 2),
+                                             (0b00001, 1, 2), (0b10000, 5, 2), (0b01000, 2, 1)])
+def test_fused_cycle_matches_oracle_and_the_plugin_by_plugin_path(eng, engine_mod, P, mask, k, strategy):
+    """cycle.cu: the whole cycle of a handful of pods as ONE cooperative kernel -- the same winners and the same final
+    feasible set as the oracle's restatement of the upstream cycle and as the plugin-by-plugin path."""
+    E = engine_mod
+    N = 3000 + 37 * P
+    seed = synth.BASE_SEED + 5 + P
+    d = build_inputs(seed, P, N)
+    feas = synth.gen_feasible_words(seed, P, N, E.npad_of(N)) if mask != 0b00001 else None
+    load_engine(eng, E, d, N, P, feas, nrt_strategy=strategy)
+    weights = [2, 1, 1, 3, 5]
+    launches0 = eng.launches
+    eng.eval_combined(mask, weights, k=k, write_total=False)
+    assert eng.launches - launches0 <= 5  # three small launches (+ the snapshot-time Allocatable raw / sort on first use)
+    got, got_feas = eng.fetch_topk(), eng.fetch_total_feasible()
+    _, want_feas, want = oracle_combined(d, P, N, eng.Npad, feas, weights, k, mask, nrt_strategy=strategy)
+    assert np.array_equal(got_feas, want_feas)
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in got[p]] == want[p], p
+    eng.config_fused_cycle(False)
+    eng.eval_combined(mask, weights, k=k, write_total=False)
+    slow = eng.fetch_topk()
+    eng.config_fused_cycle(True)
+    assert np.array_equal(slow["score"], got["score"]) and np.array_equal(slow["node"], got["node"])
+    # the one-call form: upload + cycle + winners to host with a single synchronisation
+    batch, keep = eng.make_batch(P, feasible=feas, tlp_pod_cpu_milli=d["pods"]["tlp_pod_cpu_milli"],
+                                 lvrb_req_cpu_milli=d["pods"]["req_cpu_milli"], lvrb_req_mem_bytes=d["pods"]["req_mem_bytes"],
+                                 nrt=d["nrt_pods"], netoh=d["net"])
+    one = eng.schedule_batch(batch, mask, weights, k=k)
+    assert np.array_equal(one["score"], got["score"]) and np.array_equal(one["node"], got["node"])
