@@ -236,6 +236,10 @@ void nrt2_on_pods(b200s_ctx* c, const b200s_nrt_pods* q, int P) {
   const int R = c->nrt_R;
   s->pods_note = "no NodeResourceTopologyMatch pod columns / more than 4 zones or resource slots";
   if (!q || P <= 0 || R > 4 || c->nrt_Z > 4) return;
+  if (P < 32 && s->force != 2) {  // a scheduling cycle (P = 1) never takes the batched path: skip the dictionary
+    s->pods_note = "fewer than 32 pods";
+    return;
+  }
   s->pods_note = "";
   s->pod_vec.assign((size_t)P * (C_MAX + 1), -1);
   size_t cap = 64;
