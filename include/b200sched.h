@@ -394,6 +394,17 @@ int b200s_config_fused_cycle(b200s_ctx* ctx, int on);
  * evaluate the weighted combination, copy the [n_pods][k] winners to topk_out (HOST). */
 int b200s_schedule_batch(b200s_ctx* ctx, const b200s_pod_batch* batch, uint32_t plugin_mask,
                          const int64_t* weights /* [B200S_PLUGIN_COUNT] */, int32_t k, b200s_topk_entry* topk_out);
+/* Speculative placement of a whole batch, pod by pod, without leaving the device: the cycle of pod i
+ * runs on the snapshot as pods 0..i-1 left it; after each cycle the winner is ASSUMED on the device --
+ * NodeResourceTopologyMatch: the pod's effective request comes off every zone of the winner node that lists the
+ * resource (OverReserve cache: overreserve.go:148-182 -> store.go:101-160); TargetLoadPacking: the node's missing
+ * utilisation grows by the pod's predicted CPU (handler.go:131-167) -- and the next pod's cycle sees it.  One call, one
+ * synchronisation, winners_out[n_pods] (node = -1: unschedulable).  The resident snapshot columns are modified IN
+ * PLACE: when a bind later fails the caller resyncs that node's rows (b200s_snapshot_patch_*).  NetworkOverhead's
+ * dependency entries are those of the upload (pods of the batch do not become each other's placed dependencies).
+ * Single GPU, <= 4 zones x <= 4 resource slots, Least/Most/BalancedAllocation. */
+int b200s_schedule_sequence(b200s_ctx* ctx, const b200s_pod_batch* batch, uint32_t plugin_mask,
+                            const int64_t* weights /* [B200S_PLUGIN_COUNT] */, b200s_topk_entry* winners_out);
 int b200s_fetch_total(b200s_ctx* ctx, int64_t* out, size_t bytes);          /* [P][Npad] */
 int b200s_fetch_total_feasible(b200s_ctx* ctx, uint64_t* out, size_t bytes);
 

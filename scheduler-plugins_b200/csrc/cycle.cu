@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(256) cycle_phase2_kernel(CycleArgs a) {
 }  // namespace
 
 // Whether the fused cycle applies to (snapshot, batch, args); see the header comment.
-bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total) {
-  if (!c->fused_cycle || write_total || c->P < 1 || c->P > PMAX || k < 1 || k > KMAX || comm_world(c) > 1) return false;
+bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total, bool any_p) {
+  if (!c->fused_cycle || write_total || c->P < 1 || (!any_p && c->P > PMAX) || k < 1 || k > KMAX || comm_world(c) > 1) return false;
   if (mask & ~0x1Fu) return false;  // Peaks / LowRiskOverCommitment keep the plugin-by-plugin path
   if (mask & (1u << B200S_PLUGIN_NRT)) {
     if (c->nrt_strategy == B200S_NRT_LEAST_NUMA_NODES || c->nrt_Z > Z || c->nrt_R > R) return false;
@@ -428,12 +428,12 @@ bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total) {
   return true;
 }
 
-int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
-  const int P = c->P, Npad = c->Npad;
+// pods [p0, p0 + np) of the uploaded batch; winners to out[np][k] (device)
+static int cycle_launch(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int p0, int np, b200s_topk_entry* out) {
+  const int P = np, Npad = c->Npad;
   const int sc = (mask & (1u << B200S_PLUGIN_NRT)) && c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION ? 1 : 0;
   const int blocks = (Npad + 255) / 256;  // phase 2 CTAs = rows of the per-block winners
   B200S_CUDA_TRY(c, c->cycle_scratch.ensure((size_t)256 + (size_t)P * Npad * 12 + (size_t)P * blocks * k * sizeof(b200s_topk_entry) + 64));
-  B200S_CUDA_TRY(c, c->topk_final.ensure((size_t)P * k * sizeof(b200s_topk_entry)));
   char* base = c->cycle_scratch.as<char>();
   CycleArgs a;
   memset(&a, 0, sizeof(a));
@@ -445,15 +445,15 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
   a.node_off = c->node_off;
   a.k = k;
   for (int j = 0; j < B200S_PLUGIN_COUNT; ++j) a.w[j] = weights[j];
-  a.upstream = c->has_feasible ? c->feasible_in.as<uint64_t>() : nullptr;
+  a.upstream = c->has_feasible ? c->feasible_in.as<uint64_t>() + (size_t)p0 * (Npad / 64) : nullptr;
   a.lohi = reinterpret_cast<unsigned long long*>(base);
   a.done = reinterpret_cast<unsigned int*>(base + PMAX * 4 * 8);
   a.cost = reinterpret_cast<int64_t*>(base + 256);
   a.part = reinterpret_cast<uint32_t*>(base + 256 + (size_t)P * Npad * 8);
   a.block_best = reinterpret_cast<b200s_topk_entry*>(base + 256 + (size_t)P * Npad * 12);
-  a.out = c->topk_final.as<b200s_topk_entry>();
-  B200S_CUDA_TRY(c, c->total_feas.ensure((size_t)P * (Npad / 64) * 8));
-  a.feas32 = c->total_feas.as<uint32_t>();
+  a.out = out;
+  B200S_CUDA_TRY(c, c->total_feas.ensure((size_t)c->P * (Npad / 64) * 8));
+  a.feas32 = c->total_feas.as<uint32_t>() + (size_t)p0 * (Npad / 32);
   if (mask & (1u << B200S_PLUGIN_ALLOCATABLE)) {
     if (!c->has_alloc || !c->alloc_cfg) return c->set_err(B200S_ERR_STATE, "NodeResourcesAllocatable: snapshot columns / args missing");
     B200S_TRY(alloc_prepare(c));
@@ -465,7 +465,7 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
     a.tlp_cap = c->tlp_cap.as<int64_t>();
     a.tlp_missing = c->tlp_missing.as<int64_t>();
     a.tlp_flags = c->tlp_flags.as<uint8_t>();
-    a.tlp_pod = c->tlp_pod_cpu.as<int64_t>();
+    a.tlp_pod = c->tlp_pod_cpu.as<int64_t>() + p0;
     a.tlp_target = c->tlp_target;
   }
   if (mask & (1u << B200S_PLUGIN_LVRB)) {
@@ -473,8 +473,8 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
     a.lvrb_f64 = c->lvrb_f64.as<double>();
     a.lvrb_i64 = c->lvrb_i64.as<int64_t>();
     a.lvrb_flags = c->lvrb_flags.as<uint8_t>();
-    a.lvrb_req_cpu = c->lvrb_req_cpu.as<int64_t>();
-    a.lvrb_req_mem = c->lvrb_req_mem.as<int64_t>();
+    a.lvrb_req_cpu = c->lvrb_req_cpu.as<int64_t>() + p0;
+    a.lvrb_req_mem = c->lvrb_req_mem.as<int64_t>() + p0;
     a.margin = c->lvrb_margin;
     a.sens = c->lvrb_sens;
   }
@@ -487,13 +487,13 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
     a.nrt_avail = c->nrt_avail.as<int64_t>();
     a.nrt_Zs = c->nrt_Z;
     a.nrt_Rs = c->nrt_R;
-    a.pod_qos = c->nrt_pod_qos.as<uint8_t>();
-    a.pod_flags = c->nrt_pod_flags.as<uint8_t>();
-    a.pod_ninit = c->nrt_pod_ninit.as<uint8_t>();
-    a.pod_napp = c->nrt_pod_napp.as<uint8_t>();
-    a.pod_kind = c->nrt_pod_kind.as<uint8_t>();
-    a.pod_req_mask = c->nrt_pod_req_mask.as<uint8_t>();
-    a.pod_req = c->nrt_pod_req.as<int64_t>();
+    a.pod_qos = c->nrt_pod_qos.as<uint8_t>() + p0;
+    a.pod_flags = c->nrt_pod_flags.as<uint8_t>() + p0;
+    a.pod_ninit = c->nrt_pod_ninit.as<uint8_t>() + p0;
+    a.pod_napp = c->nrt_pod_napp.as<uint8_t>() + p0;
+    a.pod_kind = c->nrt_pod_kind.as<uint8_t>() + (size_t)p0 * C_MAX;
+    a.pod_req_mask = c->nrt_pod_req_mask.as<uint8_t>() + (size_t)p0 * (C_MAX + 1);
+    a.pod_req = c->nrt_pod_req.as<int64_t>() + (size_t)p0 * (C_MAX + 1) * c->nrt_R;
     a.cfg.strategy = c->nrt_strategy;
     for (int r = 0; r < B200S_NRT_MAX_RES; ++r) {
       a.cfg.w[r] = c->nrt_w[r];
@@ -507,8 +507,8 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
     a.topo.K = c->netoh_K;
     a.region = c->netoh_region.as<uint16_t>();
     a.zone = c->netoh_zone.as<uint16_t>();
-    a.equal = c->netoh_equal.as<uint8_t>();
-    a.dep_off = c->netoh_dep_off.as<int32_t>();
+    a.equal = c->netoh_equal.as<uint8_t>() + p0;
+    a.dep_off = c->netoh_dep_off.as<int32_t>() + p0;
     a.deps = c->netoh_deps.as<b200s_netoh_dep>();
   }
   if (!c->cycle_cells_zero || c->cycle_scratch.p != c->cycle_cells_base) {  // first use / reallocation: the fold resets them afterwards
@@ -526,9 +526,63 @@ int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
   cycle_phase2_kernel<<<blocks, 256, 0, c->stream>>>(a);
   c->launches += 2;
   B200S_CUDA_TRY(c, cudaGetLastError());
+  return B200S_OK;
+}
+
+int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k) {
+  B200S_CUDA_TRY(c, c->topk_final.ensure((size_t)c->P * k * sizeof(b200s_topk_entry)));
+  B200S_TRY(cycle_launch(c, mask, weights, k, 0, c->P, c->topk_final.as<b200s_topk_entry>()));
   c->topk_k = k;
   c->topk_valid = true;
   c->total_valid = false;
+  return B200S_OK;
+}
+
+namespace {
+// "Assume" of the pod that was just placed, on the device: what the scheduler's caches do between two cycles.
+//   NodeResourceTopologyMatch (OverReserve cache): ReserveNodeResources records the pod's effective request
+//     (cache/store.go:101-112, pkg/util/resource.go:51-85) and GetCachedNRTCopy -> UpdateNRT takes it off EVERY zone of
+//     the node that lists the resource: available < q ? 0 : available - q (store.go:129-160)
+//   TargetLoadPacking: the bind handler adds the pod to ScheduledPodsCache (handler.go:131-167), so the node's
+//     "missing" utilisation grows by the pod's predicted CPU (targetloadpacking.go:151-167)
+// One CTA, thread (z, r) of the winner node.
+__global__ void assume_kernel(const b200s_topk_entry* __restrict__ winner, int node_off, int N, size_t npad, int Zs, int Rs,
+                              const uint8_t* __restrict__ zmask, int64_t* __restrict__ avail, const int64_t* __restrict__ eff_req,
+                              uint32_t eff_mask_ptr_valid, const uint8_t* __restrict__ eff_mask, int64_t* __restrict__ tlp_missing,
+                              const int64_t* __restrict__ tlp_pod) {
+  const int n = winner->node - node_off;
+  if (winner->node < 0 || n < 0 || n >= N) return;  // unschedulable pod, or placed on another shard
+  const int t = threadIdx.x;
+  if (avail && t < Zs * Rs) {
+    const int z = t / Rs, r = t % Rs;
+    if (((zmask[(size_t)z * npad + n] >> r) & 1u) && ((eff_mask[0] >> r) & 1u)) {
+      int64_t* cell = avail + ((size_t)z * Rs + r) * npad + n;
+      const int64_t q = eff_req[r], v = *cell;
+      *cell = v < q ? 0 : v - q;
+    }
+  }
+  if (tlp_missing && t == 0) tlp_missing[n] = wrap_add(tlp_missing[n], tlp_pod[0]);
+  (void)eff_mask_ptr_valid;
+}
+}  // namespace
+
+// Speculative placement of a whole batch, pod by pod, without leaving the device: cycle of pod i on the snapshot as
+// pods 0..i-1 left it, winner, assume, next.  The snapshot columns are modified IN PLACE (the caller resyncs rows
+// whose bind failed with b200s_snapshot_patch_*).  winners: [P] (k = 1), device.
+int cycle_sequence(b200s_ctx* c, uint32_t mask, const int64_t* weights, b200s_topk_entry* winners) {
+  const bool nrt = mask & (1u << B200S_PLUGIN_NRT), tlp = mask & (1u << B200S_PLUGIN_TLP);
+  for (int p = 0; p < c->P; ++p) {
+    B200S_TRY(cycle_launch(c, mask, weights, 1, p, 1, winners + p));
+    if (!nrt && !tlp) continue;
+    assume_kernel<<<1, 64, 0, c->stream>>>(
+        winners + p, c->node_off, c->N, (size_t)c->Npad, c->nrt_Z, c->nrt_R, nrt ? c->nrt_zone_res_mask.as<uint8_t>() : nullptr,
+        nrt ? c->nrt_avail.as<int64_t>() : nullptr,
+        nrt ? c->nrt_pod_req.as<int64_t>() + ((size_t)p * (C_MAX + 1) + C_MAX) * c->nrt_R : nullptr, 1u,
+        nrt ? c->nrt_pod_req_mask.as<uint8_t>() + (size_t)p * (C_MAX + 1) + C_MAX : nullptr,
+        tlp ? c->tlp_missing.as<int64_t>() : nullptr, tlp ? c->tlp_pod_cpu.as<int64_t>() + p : nullptr);
+    c->launches++;
+  }
+  B200S_CUDA_TRY(c, cudaGetLastError());
   return B200S_OK;
 }
 

@@ -1260,6 +1260,44 @@ int b200s_schedule_batch(b200s_ctx* c, const b200s_pod_batch* batch, uint32_t pl
   return B200S_OK;
 }
 
+int b200s_schedule_sequence(b200s_ctx* c, const b200s_pod_batch* batch, uint32_t plugin_mask, const int64_t* weights,
+                            b200s_topk_entry* winners_out) {
+  if (!c || !winners_out || !weights) return B200S_ERR_INVALID;
+  Guard g(c);
+  struct Defer {
+    b200s_ctx* c;
+    explicit Defer(b200s_ctx* x) : c(x) { c->defer_sync = true; }
+    ~Defer() { c->defer_sync = false; }
+  } defer(c);
+  int rc = pods_upload_locked(c, batch);
+  if (rc == B200S_OK && !cycle_applies(c, plugin_mask, 1, 0, true))
+    rc = c->set_err(B200S_ERR_UNSUPPORTED, "schedule_sequence: needs the fused cycle (single GPU, the five plugins, <= 4 zones x <= 4 "
+                                           "resource slots, not LeastNUMANodes)");
+  const size_t want = rc == B200S_OK ? (size_t)c->P * sizeof(b200s_topk_entry) : 0;
+  if (rc == B200S_OK && want > 0) {
+    if (cudaSuccess != c->topk_final.ensure(want)) rc = c->set_err(B200S_ERR_NOMEM, "schedule_sequence: winners buffer");
+    if (rc == B200S_OK) rc = cycle_sequence(c, plugin_mask, weights, c->topk_final.as<b200s_topk_entry>());
+    if (rc == B200S_OK && batch->nrt && (plugin_mask & (1u << B200S_PLUGIN_NRT)) && c->nrt_R <= 4) {
+      // the deductions keep the columns multiples of gcd(snapshot unit, request unit): tell the batched path's bookkeeping
+      const int R = c->nrt_R, Cn = B200S_NRT_MAX_CONT;
+      std::vector<int64_t> ded((size_t)R * c->P);
+      for (int p = 0; p < c->P; ++p)
+        for (int r = 0; r < R; ++r) ded[(size_t)r * c->P + p] = batch->nrt->req[((size_t)p * (Cn + 1) + Cn) * R + r];
+      nrt2_on_deduct(c, c->P, ded.data());
+    }
+    // the columns changed under the derived data (batched NRT node columns): a new snapshot serial refreshes them
+    c->snap_serial++;
+    for (auto& o : c->out) o.valid = false;
+    c->topk_valid = c->total_valid = false;
+    if (rc == B200S_OK && cudaMemcpyAsync(winners_out, c->topk_final.p, want, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      rc = c->set_err(B200S_ERR_CUDA, "schedule_sequence: copy of the winners failed");
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (rc != B200S_OK) return rc;
+  if (e != cudaSuccess) return c->set_err(B200S_ERR_CUDA, std::string("schedule_sequence: ") + cudaGetErrorString(e));
+  return B200S_OK;
+}
+
 int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* batch, b200s_out_dtype dtype,
                       void* scores_out, uint64_t* feasible_out, uint8_t* reasons_out) {
   if (!c) return B200S_ERR_INVALID;

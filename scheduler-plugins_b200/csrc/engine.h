@@ -283,8 +283,9 @@ int lowrisk_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
 int alloc_prepare(b200s_ctx* c);  // raw scores + sorted order of the snapshot (cached per snapshot / args)
 // cycle.cu: the whole cycle as one cooperative kernel (small P, single GPU)
-bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total);
+bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total, bool any_p = false);
 int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k);
+int cycle_sequence(b200s_ctx* c, uint32_t mask, const int64_t* weights, b200s_topk_entry* winners);
 
 // nrt2.cu: batched NodeResourceTopologyMatch path (score tables per distinct request vector + coalesced expansion)
 void nrt2_destroy(b200s_ctx* c);

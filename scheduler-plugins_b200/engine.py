@@ -46,7 +46,7 @@ EXPORTS = [
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
     "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import", "b200s_config_fused_cycle",
-    "b200s_schedule_batch",
+    "b200s_schedule_batch", "b200s_schedule_sequence",
 ]
 
 
@@ -515,6 +515,16 @@ class Engine:
             out = np.empty((P, k), dtype=TOPK_DTYPE)
         self._chk(self.lib.b200s_schedule_batch(self.ctx, C.byref(batch), C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k), _ptr(out)))
         self.P, self._k = P, k
+        return out
+
+    def schedule_sequence(self, batch, plugin_mask, weights):
+        """speculative placement of the batch pod by pod with the on-device assume; returns [P] TOPK_DTYPE winners"""
+        w = np.zeros(PLUGIN_COUNT, dtype=np.int64)
+        w[:len(weights)] = np.asarray(weights, dtype=np.int64)
+        P = int(batch.n_pods)
+        out = np.empty(P, dtype=TOPK_DTYPE)
+        self._chk(self.lib.b200s_schedule_sequence(self.ctx, C.byref(batch), C.c_uint32(plugin_mask), _ptr(w), _ptr(out)))
+        self.P = P
         return out
 
     def fetch_topk(self):

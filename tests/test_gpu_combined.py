@@ -138,3 +138,66 @@ def test_fused_cycle_matches_oracle_and_the_plugin_by_plugin_path(eng, engine_mo
                                  nrt=d["nrt_pods"], netoh=d["net"])
     one = eng.schedule_batch(batch, mask, weights, k=k)
     assert np.array_equal(one["score"], got["score"]) and np.array_equal(one["node"], got["node"])
+
+
+@pytest.mark.parametrize("mask,strategy", [(0b11111, 2), (0b01010, 0), (0b01000, 1)])
+def test_schedule_sequence_with_on_device_assume(eng, engine_mod, mask, strategy):
+    """SURVEY.md §8f-4, second half: a batch is placed pod by pod WITHOUT leaving the device -- after each cycle the
+    winner is assumed (OverReserve deduction on every listing zone of the winner node, store.go:129-160;
+    TargetLoadPacking's missing utilisation, handler.go:131-167) and the next pod sees it.  Checked against the same
+    loop on the host: oracle cycle of one pod, then the oracle's own deduction, then the next pod."""
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+
+    E = engine_mod
+    P, N = 14, 1400
+    seed = synth.BASE_SEED + 9
+    d = build_inputs(seed, P, N)
+    # make the assume matter: every pod is Guaranteed with a sizeable request, few roomy nodes
+    feas = synth.gen_feasible_words(seed, P, N, E.npad_of(N))
+    load_engine(eng, E, d, N, P, feas, nrt_strategy=strategy)
+    weights = [2, 1, 1, 3, 5]
+    batch, keep = eng.make_batch(P, feasible=feas, tlp_pod_cpu_milli=d["pods"]["tlp_pod_cpu_milli"],
+                                 lvrb_req_cpu_milli=d["pods"]["req_cpu_milli"], lvrb_req_mem_bytes=d["pods"]["req_mem_bytes"],
+                                 nrt=d["nrt_pods"], netoh=d["net"])
+    got = eng.schedule_sequence(batch, mask, weights)
+    # ---- the same loop on the host
+    state = dict(d, nrt_nodes=dict(d["nrt_nodes"], avail=d["nrt_nodes"]["avail"].copy()),
+                 tri=dict(d["tri"], missing_milli=d["tri"]["missing_milli"].copy()))
+    Z, R = state["nrt_nodes"]["n_zones"], state["nrt_nodes"]["n_res"]
+    net = d["net"]
+    placed_on_a_deducted_node = 0
+    touched = set()
+    for p in range(P):
+        one = dict(state, pods={k: (v[p:p + 1] if isinstance(v, np.ndarray) else v) for k, v in d["pods"].items()},
+                   nrt_pods={k: (v[p:p + 1] if isinstance(v, np.ndarray) else v) for k, v in d["nrt_pods"].items()})
+        a, b = int(net["dep_offset"][p]), int(net["dep_offset"][p + 1])
+        one["net"] = dict(net, score_equally=net["score_equally"][p:p + 1], dep_offset=np.array([0, b - a], dtype=np.int32),
+                          deps=net["deps"][a:b])
+        _, _, topk = oracle_combined(one, 1, N, eng.Npad, feas[p:p + 1], weights, 1, mask, nrt_strategy=strategy)
+        want = topk[0][0]
+        assert (int(got[p]["score"]), int(got[p]["node"])) == tuple(want), (p, got[p], want)
+        n = int(want[1])
+        if n < 0:
+            continue
+        placed_on_a_deducted_node += n in touched
+        touched.add(n)
+        if mask & 8:  # OverReserve: the pod's effective request comes off every listing zone of node n
+            req, rm = d["nrt_pods"]["req"][p, 8], int(d["nrt_pods"]["req_mask"][p, 8])
+            av = np.ascontiguousarray(state["nrt_nodes"]["avail"][:, :, n])
+            zm = np.ascontiguousarray(state["nrt_nodes"]["zone_res_mask"][:, n])
+            ded = np.ascontiguousarray(req.astype(np.int64))
+            orc.lib().orc_nrt_overreserve_deduct(C.c_void_p(av.ctypes.data), C.c_void_p(zm.ctypes.data), C.c_int(Z), C.c_int(R),
+                                                 C.c_uint8(rm), C.c_void_p(ded.ctypes.data))
+            state["nrt_nodes"]["avail"][:, :, n] = av
+        if mask & 2:
+            state["tri"]["missing_milli"][n] += d["pods"]["tlp_pod_cpu_milli"][p]
+    # the engine's resident columns are the host loop's final state: a plain evaluation afterwards agrees
+    if mask & 8:
+        from oracle import pyoracle_nrt
+
+        eng.pods_upload(P, feasible=feas, nrt=d["nrt_pods"])
+        eng.eval(E.PLUGIN_NRT)
+        ws, wf, wr = pyoracle_nrt.nrt_batch(state["nrt_nodes"], d["nrt_pods"], strategy, [1, 1, 1, 1], feas, pitch=eng.Npad)
+        assert np.array_equal(eng.fetch_reasons(E.PLUGIN_NRT), wr) and np.array_equal(eng.fetch_scores(E.PLUGIN_NRT), ws)
