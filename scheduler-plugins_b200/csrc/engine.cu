@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <unordered_map>
@@ -27,6 +28,53 @@ int upload_col(b200s_ctx* c, DevBuf& dst, size_t dst_off_elems, const T* src, in
   B200S_CUDA_TRY(c, cudaMemcpyAsync(d, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   if (npad > n) B200S_CUDA_TRY(c, cudaMemsetAsync(d + n, 0, sizeof(T) * (size_t)(npad - n), c->stream));
   return B200S_OK;
+}
+
+// Row sanity for the score-table path of the Trimaran plugins: with finite, non-negative inputs every score lies in
+// 0..100 (targetloadpacking.go:170-186; analysis.go:41-59 clamps) and fits a byte table; anything else (a NaN metric, a
+// negative capacity) keeps the direct int64 kernels, which reproduce Go's MinInt64 / wrapped results.
+bool tlp_rows_sane(const double* util, const int64_t* cap, const int64_t* missing, int n) {
+  for (int i = 0; i < n; ++i)
+    if (!(util[i] >= 0 && util[i] <= 1e12) || cap[i] < 0 || missing[i] < 0) return false;
+  return true;
+}
+bool lvrb_rows_sane(const double* a, const double* b, const double* c2, const double* d, const int64_t* ac, const int64_t* am, int n) {
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(a[i]) || !std::isfinite(b[i]) || !std::isfinite(c2[i]) || !std::isfinite(d[i]) || ac[i] < 0 || am[i] < 0)
+      return false;
+  return true;
+}
+
+// distinct values of a pod column (pairs: a second column): row_of_pod + the distinct keys in first-seen order
+void dedup_keys(const int64_t* k0, const int64_t* k1, int P, std::vector<int32_t>& row, std::vector<int64_t>& u0,
+                std::vector<int64_t>& u1) {
+  row.resize((size_t)P);
+  u0.clear();
+  u1.clear();
+  size_t cap = 64;
+  while (cap < (size_t)P * 2) cap <<= 1;
+  std::vector<int32_t> table(cap, -1);
+  for (int p = 0; p < P; ++p) {
+    const uint64_t a = (uint64_t)k0[p], b = k1 ? (uint64_t)k1[p] : 0;
+    uint64_t h = (a * 0x9e3779b97f4a7c15ull) ^ ((b + 0x7f4a7c15ull) * 0xbf58476d1ce4e5b9ull);
+    h ^= h >> 29;
+    size_t i = (size_t)h & (cap - 1);
+    for (;;) {
+      const int32_t id = table[i];
+      if (id < 0) {
+        table[i] = (int32_t)u0.size();
+        row[(size_t)p] = (int32_t)u0.size();
+        u0.push_back(k0[p]);
+        if (k1) u1.push_back(k1[p]);
+        break;
+      }
+      if (u0[(size_t)id] == k0[p] && (!k1 || u1[(size_t)id] == k1[p])) {
+        row[(size_t)p] = id;
+        break;
+      }
+      i = (i + 1) & (cap - 1);
+    }
+  }
 }
 
 // NRT thread-slot permutation.  Major key: the control-flow class (flags, zone count), so that pod-scope and
@@ -305,7 +353,8 @@ void b200s_shutdown(b200s_ctx* c) {
                     &c->netoh_pair_sv,   &c->nrt_perm,         &c->topk_slices,      &c->peaks_util,
                     &c->peaks_cap,       &c->peaks_flags,      &c->peaks_k,          &c->lowrisk_f64,
                     &c->lowrisk_i64,     &c->lowrisk_flags,    &c->lowrisk_load,     &c->peaks_pod_cpu,
-                    &c->lowrisk_pod};
+                    &c->lowrisk_pod,     &c->tlp_uniq,         &c->tlp_row,          &c->lvrb_uniq_cpu,
+                    &c->lvrb_uniq_mem,   &c->lvrb_row,         &c->score_table};
   for (DevBuf* b : bufs) b->release();
   for (auto& o : c->out) {
     o.scores.release();
@@ -469,6 +518,7 @@ int b200s_snapshot_tlp(b200s_ctx* c, const double* util, const int64_t* cap, con
   B200S_TRY(upload_col<uint8_t>(c, c->tlp_flags, 0, flags, c->N, c->Npad));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->has_tlp = true;
+  c->tlp_sane = tlp_rows_sane(util, cap, missing, c->N);
   return B200S_OK;
 }
 
@@ -493,6 +543,8 @@ int b200s_snapshot_lvrb(b200s_ctx* c, const double* cpu_avg, const double* cpu_s
   B200S_TRY(upload_col<uint8_t>(c, c->lvrb_flags, 0, flags, c->N, c->Npad));
   B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->has_lvrb = true;
+  c->lvrb_sane = lvrb_rows_sane(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, c->N);
+  c->lvrb_sane = lvrb_rows_sane(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, c->N);
   return B200S_OK;
 }
 
@@ -680,6 +732,7 @@ int b200s_snapshot_patch_tlp(b200s_ctx* c, int32_t count, const int32_t* node_id
   p.add<int64_t>(c->tlp_cap, 0, cap);
   p.add<int64_t>(c->tlp_missing, 0, missing);
   p.add<uint8_t>(c->tlp_flags, 0, flags);
+  c->tlp_sane = c->tlp_sane && tlp_rows_sane(util, cap, missing, count);
   return p.run(node_idx);
 }
 
@@ -701,6 +754,7 @@ int b200s_snapshot_patch_lvrb(b200s_ctx* c, int32_t count, const int32_t* node_i
   p.add<int64_t>(c->lvrb_i64, 0 * np, alloc_cpu);
   p.add<int64_t>(c->lvrb_i64, 1 * np, alloc_mem);
   p.add<uint8_t>(c->lvrb_flags, 0, flags);
+  c->lvrb_sane = c->lvrb_sane && lvrb_rows_sane(cpu_avg, cpu_std, mem_avg, mem_std, alloc_cpu, alloc_mem, count);
   return p.run(node_idx);
 }
 
@@ -976,6 +1030,27 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   if (c->has_lvrb_pods && P > 0) {
     up.add(&c->lvrb_req_cpu, b->lvrb_req_cpu_milli, (size_t)P * 8);
     up.add(&c->lvrb_req_mem, b->lvrb_req_mem_bytes, (size_t)P * 8);
+  }
+  // distinct request keys of a large batch (score-table path of TargetLoadPacking / LoadVariationRiskBalancing)
+  c->tlp_U = c->lvrb_U = 0;
+  constexpr int kDedupMinPods = 256;
+  if (c->has_tlp_pods && P >= kDedupMinPods) {
+    bool ok = true;
+    for (int p = 0; p < P && ok; ++p) ok = b->tlp_pod_cpu_milli[p] >= 0 && b->tlp_pod_cpu_milli[p] < ((int64_t)1 << 53);
+    if (ok) {
+      std::vector<int64_t> none;
+      dedup_keys(b->tlp_pod_cpu_milli, nullptr, P, c->tlp_row_h, c->tlp_uniq_h, none);
+      c->tlp_U = (int)c->tlp_uniq_h.size();
+      up.add(&c->tlp_uniq, c->tlp_uniq_h.data(), (size_t)c->tlp_U * 8);
+      up.add(&c->tlp_row, c->tlp_row_h.data(), (size_t)P * 4);
+    }
+  }
+  if (c->has_lvrb_pods && P >= kDedupMinPods) {
+    dedup_keys(b->lvrb_req_cpu_milli, b->lvrb_req_mem_bytes, P, c->lvrb_row_h, c->lvrb_uniq_cpu_h, c->lvrb_uniq_mem_h);
+    c->lvrb_U = (int)c->lvrb_uniq_cpu_h.size();
+    up.add(&c->lvrb_uniq_cpu, c->lvrb_uniq_cpu_h.data(), (size_t)c->lvrb_U * 8);
+    up.add(&c->lvrb_uniq_mem, c->lvrb_uniq_mem_h.data(), (size_t)c->lvrb_U * 8);
+    up.add(&c->lvrb_row, c->lvrb_row_h.data(), (size_t)P * 4);
   }
   c->has_peaks_pods = b->peaks_pod_cpu_milli != nullptr;
   if (c->has_peaks_pods && P > 0) up.add(&c->peaks_pod_cpu, b->peaks_pod_cpu_milli, (size_t)P * 8);

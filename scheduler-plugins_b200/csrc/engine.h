@@ -129,12 +129,14 @@ struct b200s_ctx {
   b200s::DevBuf tlp_util, tlp_cap, tlp_missing, tlp_flags;
   bool tlp_cfg = false;
   int64_t tlp_target = 40;
+  bool tlp_sane = false;  // every row finite and non-negative: the scores are in 0..100 (a byte table can hold them)
 
   // LoadVariationRiskBalancing
   bool has_lvrb = false;
   b200s::DevBuf lvrb_f64;  // [4][Npad] cpuAvg cpuStd memAvg memStd
   b200s::DevBuf lvrb_i64;  // [2][Npad] allocCpuMilli allocMemBytes
   b200s::DevBuf lvrb_flags;
+  bool lvrb_sane = false;  // every metric finite, allocatable non-negative: no NaN can reach a score
   bool lvrb_cfg = false;
   double lvrb_margin = 1.0, lvrb_sens = 1.0;
 
@@ -208,6 +210,12 @@ struct b200s_ctx {
   b200s::DevBuf nrt_pod_qos, nrt_pod_flags, nrt_pod_ninit, nrt_pod_napp, nrt_pod_kind, nrt_pod_req_mask,
       nrt_pod_req;
   b200s::DevBuf netoh_equal, netoh_dep_off, netoh_deps;
+  // distinct pod keys of the batch (score-table path of the Trimaran plugins: pending pods of one Deployment / Job
+  // carry identical request columns, so a plugin's row depends on the pod only through a key few pods are alone with)
+  int tlp_U = 0, lvrb_U = 0;  // 0 = no dictionary (small batch, or a negative / absurd request)
+  std::vector<int64_t> tlp_uniq_h, lvrb_uniq_cpu_h, lvrb_uniq_mem_h;
+  std::vector<int32_t> tlp_row_h, lvrb_row_h;
+  b200s::DevBuf tlp_uniq, tlp_row, lvrb_uniq_cpu, lvrb_uniq_mem, lvrb_row, score_table;
   int netoh_total_deps = 0, netoh_max_deps = 0;
 
   // ---- per-pod scratch ----

@@ -14,6 +14,8 @@
 // traffic is the streaming store of the score matrix.
 #include <math_constants.h>
 
+#include <cmath>
+
 #include "engine.h"
 #include "trimaran_device.cuh"
 
@@ -198,13 +200,69 @@ int debug_div_check(b200s_ctx* c, const double* x, const double* d, int n, uint6
   return B200S_OK;
 }
 
+// Score-table path: pending pods share few distinct request keys (pods of one Deployment / Job are identical), and a
+// Trimaran score depends on the pod only through that key.  The plugin's kernel runs once per DISTINCT key into a byte
+// table T[key][node] (L2-resident: tens of rows), and this kernel expands it to the [P][Npad] matrix -- a streaming store
+// at the HBM write rate instead of ~70-110 fp64-heavy instructions per (pod, node).  Results are the same bytes.
+template <class OutT, int NPT, int PT>
+__global__ void __launch_bounds__(256)
+expand_rows_kernel(const uint8_t* __restrict__ T, const int32_t* __restrict__ row_of_pod, int Npad, int P, OutT* __restrict__ out) {
+  constexpr int CHUNK = 256 * NPT;
+  __shared__ int32_t s_row[PT];
+  const int nb = blockIdx.x * CHUNK + threadIdx.x * NPT, p0 = blockIdx.y * PT;
+  for (int i = threadIdx.x; i < PT; i += 256)
+    if (p0 + i < P) s_row[i] = row_of_pod[p0 + i];
+  __syncthreads();
+  if (nb >= Npad) return;
+  const int pend = min(PT, P - p0);
+  OutT* orow = out + (size_t)p0 * Npad + nb;
+  for (int pp = 0; pp < pend; ++pp, orow += Npad) {
+    const uint8_t* src = T + (size_t)s_row[pp] * Npad + nb;
+    if constexpr (sizeof(OutT) == 8) {
+      static_assert(sizeof(OutT) != 8 || NPT == 2, "int64 rows: two nodes per thread, one 16-byte store");
+      const uint32_t v = *reinterpret_cast<const uint16_t*>(src);
+      st_stream_v2(reinterpret_cast<int64_t*>(orow), (int64_t)(v & 255u), (int64_t)(v >> 8));
+    } else {
+      static_assert(sizeof(OutT) == 8 || NPT == 16, "u8 rows: sixteen nodes per thread, one 16-byte load and store");
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      __stcs(reinterpret_cast<uint4*>(orow), v);
+    }
+  }
+}
+
+template <class OutT>
+void launch_expand(b200s_ctx* c, const uint8_t* T, const int32_t* row, int P, OutT* out) {
+  constexpr int PT = 64, NPT = sizeof(OutT) == 8 ? 2 : 16;
+  dim3 grid((c->Npad + 256 * NPT - 1) / (256 * NPT), (P + PT - 1) / PT);
+  expand_rows_kernel<OutT, NPT, PT><<<grid, 256, 0, c->stream>>>(T, row, c->Npad, P, out);
+  c->launches++;
+}
+
 int tlp_eval(b200s_ctx* c, int dtype) {
   if (!c->has_tlp) return c->set_err(B200S_ERR_STATE, "TargetLoadPacking: snapshot has no TLP columns");
   if (!c->has_tlp_pods) return c->set_err(B200S_ERR_STATE, "TargetLoadPacking: pod batch has no tlp_pod_cpu_milli");
   const int P = c->P, N = c->N, Npad = c->Npad;
   B200S_TRY(ensure_out(c, B200S_PLUGIN_TLP, dtype, false, false));
   PluginOut& o = c->out[B200S_PLUGIN_TLP];
-  if (P > 0) {
+  // few distinct predicted-CPU values among the pods: one table row per value + the expansion
+  const bool table = P > 0 && c->tlp_U > 0 && c->tlp_U * 2 <= P && c->tlp_sane && c->tlp_target > 0 && c->tlp_target < 100;
+  if (table) {
+    constexpr int PT = 64, NPT = 2;
+    KernelTimer kt(c, B200S_PLUGIN_TLP);
+    const int U = c->tlp_U;
+    B200S_CUDA_TRY(c, c->score_table.ensure((size_t)U * Npad));
+    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (U + PT - 1) / PT);
+    tlp_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->tlp_util.as<double>(), c->tlp_cap.as<int64_t>(),
+                                                             c->tlp_missing.as<int64_t>(), c->tlp_flags.as<uint8_t>(),
+                                                             c->tlp_uniq.as<int64_t>(), c->tlp_target, N, Npad, U,
+                                                             c->score_table.as<uint8_t>());
+    c->launches++;
+    if (dtype == B200S_OUT_I64)
+      launch_expand<int64_t>(c, c->score_table.as<uint8_t>(), c->tlp_row.as<int32_t>(), P, o.scores.as<int64_t>());
+    else
+      launch_expand<uint8_t>(c, c->score_table.as<uint8_t>(), c->tlp_row.as<int32_t>(), P, o.scores.as<uint8_t>());
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  } else if (P > 0) {
     constexpr int PT = 64;
     KernelTimer kt(c, B200S_PLUGIN_TLP);
     if (dtype == B200S_OUT_I64) {
@@ -235,7 +293,26 @@ int lvrb_eval(b200s_ctx* c, int dtype) {
   const int P = c->P, N = c->N, Npad = c->Npad;
   B200S_TRY(ensure_out(c, B200S_PLUGIN_LVRB, dtype, false, false));
   PluginOut& o = c->out[B200S_PLUGIN_LVRB];
-  if (P > 0) {
+  // few distinct (cpu, memory) request pairs among the pods: one table row per pair + the expansion
+  const bool table = P > 0 && c->lvrb_U > 0 && c->lvrb_U * 2 <= P && c->lvrb_sane && std::isfinite(c->lvrb_margin) &&
+                     std::isfinite(c->lvrb_sens);
+  if (table) {
+    constexpr int PT = 64, NPT = 2;
+    KernelTimer kt(c, B200S_PLUGIN_LVRB);
+    const int U = c->lvrb_U;
+    B200S_CUDA_TRY(c, c->score_table.ensure((size_t)U * Npad));
+    dim3 grid((Npad + 256 * NPT - 1) / (256 * NPT), (U + PT - 1) / PT);
+    lvrb_kernel<uint8_t, NPT, PT><<<grid, 256, 0, c->stream>>>(c->lvrb_f64.as<double>(), c->lvrb_i64.as<int64_t>(),
+                                                              c->lvrb_flags.as<uint8_t>(), c->lvrb_uniq_cpu.as<int64_t>(),
+                                                              c->lvrb_uniq_mem.as<int64_t>(), c->lvrb_margin, c->lvrb_sens, N, Npad,
+                                                              U, c->score_table.as<uint8_t>());
+    c->launches++;
+    if (dtype == B200S_OUT_I64)
+      launch_expand<int64_t>(c, c->score_table.as<uint8_t>(), c->lvrb_row.as<int32_t>(), P, o.scores.as<int64_t>());
+    else
+      launch_expand<uint8_t>(c, c->score_table.as<uint8_t>(), c->lvrb_row.as<int32_t>(), P, o.scores.as<uint8_t>());
+    B200S_CUDA_TRY(c, cudaGetLastError());
+  } else if (P > 0) {
     constexpr int PT = 64;
     KernelTimer kt(c, B200S_PLUGIN_LVRB);
     if (dtype == B200S_OUT_I64) {

@@ -91,3 +91,43 @@ def test_config5_shard_chunk_full_size(eng, engine_mod, oracle):
     assert np.array_equal(topk["score"][has, 0], best[has])
     assert np.array_equal(nodes_won[has], np.argmax(tot[has] == best[has, None], axis=1))
     assert not total[:, :N][~bits].any()
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_trimaran_score_table_path(eng, engine_mod, oracle, shared):
+    """TargetLoadPacking / LoadVariationRiskBalancing on a batch whose pods share a few request keys go through one
+    table row per distinct key + a streaming expansion (2 launches); a batch of all-distinct keys, or a snapshot with a
+    non-finite metric, keeps the direct kernel (1 launch).  Same scores either way."""
+    E = engine_mod
+    P, N = 700, 2100
+    seed = 4242
+    nodes, pods = synth.gen_nodes(seed, N), synth.gen_pods(seed, P)
+    tri = synth.gen_trimaran(seed, nodes)
+    if not shared:
+        pods = dict(pods, tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"] + np.arange(P), req_cpu_milli=pods["req_cpu_milli"] + np.arange(P))
+    for poison in (False, True):
+        t = dict(tri, cpu_avg=tri["cpu_avg"].copy())
+        if poison:
+            t["cpu_avg"][17] = np.nan  # Go: NaN propagates to MinInt64 in the int64 score -- not a byte-table value
+        eng.snapshot_begin(N)
+        eng.snapshot_tlp(t["cpu_avg"], nodes["cap_cpu_milli"], t["missing_milli"], t["tlp_flags"])
+        eng.snapshot_lvrb(t["cpu_avg"], t["cpu_std"], t["mem_avg"], t["mem_std"], nodes["alloc_cpu_milli"],
+                          nodes["alloc_mem_bytes"], t["lvrb_flags"])
+        eng.snapshot_commit()
+        eng.config_tlp(40)
+        eng.config_lvrb(1.0, 1.0)
+        eng.pods_upload(P, tlp_pod_cpu_milli=pods["tlp_pod_cpu_milli"], lvrb_req_cpu_milli=pods["req_cpu_milli"],
+                        lvrb_req_mem_bytes=pods["req_mem_bytes"])
+        want = {E.PLUGIN_TLP: oracle.tlp_batch(t["cpu_avg"], nodes["cap_cpu_milli"], t["missing_milli"], t["tlp_flags"],
+                                               pods["tlp_pod_cpu_milli"], 40, pitch=eng.Npad),
+                E.PLUGIN_LVRB: oracle.lvrb_batch(t["cpu_avg"], t["cpu_std"], t["mem_avg"], t["mem_std"], nodes["alloc_cpu_milli"],
+                                                 nodes["alloc_mem_bytes"], t["lvrb_flags"], pods["req_cpu_milli"],
+                                                 pods["req_mem_bytes"], 1.0, 1.0, pitch=eng.Npad)}
+        for plugin in (E.PLUGIN_TLP, E.PLUGIN_LVRB):
+            l0 = eng.launches
+            eng.eval(plugin, E.OUT_I64)
+            assert eng.launches - l0 == (2 if shared and not poison else 1)
+            assert np.array_equal(eng.fetch_scores(plugin), want[plugin])
+            if not poison:
+                eng.eval(plugin, E.OUT_U8)
+                assert np.array_equal(eng.fetch_scores(plugin, E.OUT_U8).astype(np.int64), want[plugin])
