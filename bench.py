@@ -339,7 +339,7 @@ def cycle_latency(E, synth, device, N, cycles=1000):
         eng.schedule_batch(batch, 0b11111, w, k=1, out=topk1)
 
     res["all_five_plugins_top1"] = p50(combined)
-    res["all_five_plugins_top1"]["path"] = "b200s_schedule_batch -> cycle.cu: one cooperative kernel for the whole cycle"
+    res["all_five_plugins_top1"]["path"] = "b200s_schedule_batch -> cycle.cu: two launches for the whole cycle, no per-plugin matrix"
     fused_winner = (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"]))
     eng.config_fused_cycle(False)  # the plugin-by-plugin path of round 1 (13 launches) for comparison
     res["all_five_plugins_top1_plugin_by_plugin"] = p50(combined)

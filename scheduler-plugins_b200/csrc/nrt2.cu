@@ -107,6 +107,8 @@ struct Nrt2 {
   uint64_t gm[4] = {0, 0, 0, 0}, gv[4] = {0, 0, 0, 0};  // gcd of listed zone Available (milli / Value()); 0 = none
   int64_t maxm[4] = {0, 0, 0, 0};
   bool neg = false;          // a listed Available is negative: the scaled encoding does not apply
+  uint64_t stats_serial = ~0ull;  // snapshot serial the four lines above were reduced at
+  DevBuf stats_part;              // per-CTA partials of the reduction
   bool lists_valid = false;  // class lists match the flags mirror
   int Nc = 0, Np = 0, Sc = 0, Sp = 0;  // container-scope / pod-scope handler nodes; padded to 128
   DevBuf slot, list, tile_n0, tile_c0;  // [Npad] int32, [Sc + Sp] int32, [tiles + 1] first node / first container slot
@@ -136,7 +138,7 @@ struct Nrt2 {
   const char* note = "";  // why the batched path was declined last time (static string)
   int force = 0;      // 0 auto, 1 direct, 2 table when applicable
   ~Nrt2() {
-    for (DevBuf* b : {&slot, &list, &tile_n0, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
+    for (DevBuf* b : {&stats_part, &slot, &list, &tile_n0, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
                       &d_tc_list, &d_tp_list, &Tc, &Tp})
       b->release();
   }
@@ -155,68 +157,18 @@ int nrt2_last_path(b200s_ctx* c) { return c->nrt2 ? c->nrt2->last_path : 0; }
 const char* nrt2_note(b200s_ctx* c) { return c->nrt2 ? c->nrt2->note : ""; }
 void nrt2_note_direct(b200s_ctx* c) { nrt2_get(c)->last_path = 1; }
 
-// ---- snapshot-side bookkeeping (called by engine.cu with the caller's host columns) -----------------------------
-namespace {
-void fold_rows(Nrt2* s, int Z, int R, int count, const uint8_t* nz, const uint8_t* zmask, const int64_t* avail) {
-  // zmask [Z][count], avail [Z][R][count]
-  for (int z = 0; z < Z; ++z)
-    for (int r = 0; r < R && r < 4; ++r) {
-      const int64_t* col = avail + ((size_t)z * R + r) * count;
-      const uint8_t* zm = zmask + (size_t)z * count;
-      uint64_t gm = s->gm[r], gv = s->gv[r];
-      int64_t mx = s->maxm[r];
-      for (int i = 0; i < count; ++i) {
-        if (z >= nz[i] || !((zm[i] >> r) & 1u)) continue;
-        const int64_t v = col[i];
-        if (v < 0) {
-          s->neg = true;
-          continue;
-        }
-        if (gm != 1) gm = gcd_u64(gm, (uint64_t)v);
-        if (gv != 1) gv = gcd_u64(gv, (uint64_t)qty_value_h(v));
-        mx = std::max(mx, v);
-      }
-      s->gm[r] = gm;
-      s->gv[r] = gv;
-      s->maxm[r] = mx;
-    }
-}
-}  // namespace
-
-void nrt2_on_snapshot_full(b200s_ctx* c, const b200s_nrt_nodes* nn) {
+// ---- snapshot-side statistics ---------------------------------------------------------------------------------------
+// The units (gcd of the listed zone Available per resource, in milli-units and as Quantity.Value()), the largest
+// value and the presence of a negative value are reduced ON THE DEVICE from the resident columns, once per snapshot
+// serial and only when a batch asks for the batched path: full uploads, row patches, OverReserve deductions and the
+// on-device assume all just bump the serial -- no host-side bookkeeping that could drift from the columns.
+void nrt2_on_snapshot_full(b200s_ctx* c, const b200s_nrt_nodes*) {
   Nrt2* s = nrt2_get(c);
-  for (int r = 0; r < 4; ++r) s->gm[r] = s->gv[r] = 0, s->maxm[r] = 0;
-  s->neg = false;
   s->lists_valid = false;
-  if (nn->n_zones <= 4 && nn->n_res <= 4 && c->N > 0)
-    fold_rows(s, nn->n_zones, nn->n_res, c->N, nn->n_zones_node, nn->zone_res_mask, nn->avail);
+  s->stats_serial = ~0ull;
 }
-// patched rows: any common divisor of old and new values stays valid, so the gcds only ever shrink
-void nrt2_on_patch_rows(b200s_ctx* c, int count, const b200s_nrt_nodes* rows) {
-  Nrt2* s = nrt2_get(c);
-  if (c->nrt_Z <= 4 && c->nrt_R <= 4 && count > 0)
-    fold_rows(s, c->nrt_Z, c->nrt_R, count, rows->n_zones_node, rows->zone_res_mask, rows->avail);
-}
-// OverReserve deduction: available - q (or 0) is a multiple of g' = gcd(g, q).  Value() of a difference is not the
-// difference of the Value()s in general -- but when g' is a whole number of units (a multiple of 1000 milli) every
-// value is whole, Value(x) = x / 1000, and the Value()s are multiples of g' / 1000.
-void nrt2_on_deduct(b200s_ctx* c, int count, const int64_t* deduct /* [R][count] */) {
-  Nrt2* s = nrt2_get(c);
-  if (c->nrt_R > 4) return;
-  for (int r = 0; r < c->nrt_R; ++r) {
-    uint64_t gq = 0;
-    for (int i = 0; i < count; ++i) {
-      const int64_t q = deduct[(size_t)r * count + i];
-      if (q < 0)
-        s->neg = true;
-      else
-        gq = gcd_u64(gq, (uint64_t)q);
-    }
-    if (gq == 0) continue;  // nothing taken off this resource
-    s->gm[r] = gcd_u64(s->gm[r], gq);
-    s->gv[r] = (s->gm[r] % 1000 == 0) ? gcd_u64(s->gv[r], s->gm[r] / 1000) : 1;
-  }
-}
+void nrt2_on_patch_rows(b200s_ctx* c, int, const b200s_nrt_nodes*) { nrt2_get(c)->stats_serial = ~0ull; }
+void nrt2_on_deduct(b200s_ctx* c, int, const int64_t*) { nrt2_get(c)->stats_serial = ~0ull; }
 void nrt2_on_class_change(b200s_ctx* c) {
   if (c->nrt2) c->nrt2->lists_valid = false;
 }
@@ -317,6 +269,69 @@ void nrt2_on_pods(b200s_ctx* c, const b200s_nrt_pods* q, int P) {
 namespace {
 
 // ---- device code ----------------------------------------------------------------------------------------------------
+
+// per-resource {gcd of milli values, gcd of Value()s, max, any negative} over the listed cells: thread-local
+// accumulation over a grid-stride loop, warp shuffle + shared-memory fold (gcd is associative and commutative),
+// one partial per CTA; the host folds the <= 64 partials.
+struct StatsPart {
+  unsigned long long gm[4], gv[4];
+  long long mx[4];
+  unsigned int neg, pad;
+};
+__device__ __forceinline__ unsigned long long dgcd(unsigned long long a, unsigned long long b) {
+  while (b) {
+    const unsigned long long t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+__global__ void __launch_bounds__(256) nrt2_stats_kernel(const uint8_t* __restrict__ nz, const uint8_t* __restrict__ zmask,
+                                                         const int64_t* __restrict__ avail, int Zs, int Rs, int N, int Npad,
+                                                         StatsPart* __restrict__ out) {
+  __shared__ StatsPart sp[8];
+  StatsPart a;
+  for (int r = 0; r < 4; ++r) a.gm[r] = a.gv[r] = 0, a.mx[r] = 0;
+  a.neg = 0;
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < N; n += gridDim.x * 256) {
+    const int nzn = min((int)nz[n], Zs);
+    for (int z = 0; z < nzn; ++z) {
+      const uint32_t m = zmask[(size_t)z * Npad + n];
+      for (int r = 0; r < Rs && r < 4; ++r) {
+        if (!((m >> r) & 1u)) continue;
+        const long long v = avail[((size_t)z * Rs + r) * Npad + n];
+        if (v < 0) {
+          a.neg = 1;
+          continue;
+        }
+        if (a.gm[r] != 1) a.gm[r] = dgcd(a.gm[r], (unsigned long long)v);
+        if (a.gv[r] != 1) a.gv[r] = dgcd(a.gv[r], (unsigned long long)((v + 999) / 1000));
+        a.mx[r] = max(a.mx[r], v);
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    for (int r = 0; r < 4; ++r) {
+      a.gm[r] = dgcd(a.gm[r], __shfl_xor_sync(0xffffffffu, a.gm[r], o));
+      a.gv[r] = dgcd(a.gv[r], __shfl_xor_sync(0xffffffffu, a.gv[r], o));
+      a.mx[r] = max(a.mx[r], __shfl_xor_sync(0xffffffffu, a.mx[r], o));
+    }
+    a.neg |= __shfl_xor_sync(0xffffffffu, a.neg, o);
+  }
+  if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      for (int r = 0; r < 4; ++r) {
+        a.gm[r] = dgcd(a.gm[r], sp[w].gm[r]);
+        a.gv[r] = dgcd(a.gv[r], sp[w].gv[r]);
+        a.mx[r] = max(a.mx[r], sp[w].mx[r]);
+      }
+      a.neg |= sp[w].neg;
+    }
+    out[blockIdx.x] = a;
+  }
+}
 
 struct NodePrepArgs {
   const uint8_t* node_flags;
@@ -794,6 +809,30 @@ inline uint32_t magic_of(uint32_t d) { return d <= 1 ? 0xFFFFFFFFu : (uint32_t)(
 
 }  // namespace
 
+static int nrt2_refresh_stats(b200s_ctx* c, Nrt2* s) {
+  constexpr int kBlocks = 64;
+  B200S_CUDA_TRY(c, s->stats_part.ensure(sizeof(StatsPart) * kBlocks));
+  nrt2_stats_kernel<<<kBlocks, 256, 0, c->stream>>>(c->nrt_nz.as<uint8_t>(), c->nrt_zone_res_mask.as<uint8_t>(),
+                                                   c->nrt_avail.as<int64_t>(), c->nrt_Z, c->nrt_R, c->N, c->Npad,
+                                                   s->stats_part.as<StatsPart>());
+  c->launches++;
+  StatsPart h[kBlocks];
+  B200S_CUDA_TRY(c, cudaMemcpyAsync(h, s->stats_part.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < 4; ++r) s->gm[r] = s->gv[r] = 0, s->maxm[r] = 0;
+  s->neg = false;
+  for (int b = 0; b < kBlocks; ++b) {
+    for (int r = 0; r < 4; ++r) {
+      s->gm[r] = gcd_u64(s->gm[r], h[b].gm[r]);
+      s->gv[r] = gcd_u64(s->gv[r], h[b].gv[r]);
+      s->maxm[r] = std::max<int64_t>(s->maxm[r], h[b].mx[r]);
+    }
+    s->neg = s->neg || h[b].neg;
+  }
+  s->stats_serial = c->snap_serial;
+  return B200S_OK;
+}
+
 // Decides whether the batched path applies to (snapshot, pod batch, args) and prepares its device state.
 // Returns 1 = applicable and prepared, 0 = keep the direct kernel, < 0 = error.
 int nrt2_prepare(b200s_ctx* c) {
@@ -805,6 +844,7 @@ int nrt2_prepare(b200s_ctx* c) {
   if (c->nrt_Z > 4 || c->nrt_R > 4 || c->N <= 0) return decline("more than 4 zones or 4 resource slots");
   if (s->force != 2 && c->P < 32) return decline("fewer than 32 pods");  // a P = 1 cycle is one pass of the direct kernel
   if (!s->pods_ok) return decline(s->pods_note);
+  if (s->stats_serial != c->snap_serial) B200S_TRY(nrt2_refresh_stats(c, s));
   if (s->neg) return decline("negative zone availability");
   if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION && !s->balanced_ok)
     return decline("BalancedAllocation with a Guaranteed request naming < 2 resources");

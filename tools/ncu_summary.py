@@ -17,6 +17,10 @@ def num(v):
         return None
 
 
+def ratio(a, b):
+    return a / b if a is not None and b else None
+
+
 def summarize(path):
     rows = list(csv.reader(open(path)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -51,8 +55,11 @@ def summarize(path):
             pipe_alu_pct=g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", False),
             pipe_fma_pct=g("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", False),
             pipe_lsu_pct=g("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", False),
-            st_sectors_per_request=g("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio", False),
-            ld_sectors_per_request=g("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio", False),
+            st_sectors_per_request=ratio(g("l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", False),
+                                         g("l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", False)),
+            ld_sectors_per_request=ratio(g("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", False),
+                                         g("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", False)),
+            st_bytes_used_per_sector=g("smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio", False),
             l2_hit_pct=g("lts__t_sector_hit_rate.pct", False),
             top_stalls=[[k, round(v, 3)] for k, v in top], source=path.split("/")[-1]))
     return out
