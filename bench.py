@@ -335,12 +335,16 @@ def cycle_latency(E, synth, device, N, cycles=1000):
 
     topk1 = np.empty((1, 1), dtype=E.TOPK_DTYPE)
 
-    def combined():  # ONE C-ABI call: pod columns in, winner out (b200s_schedule_batch)
-        eng.schedule_batch(batch, 0b11111, w, k=1, out=topk1)
+    # ONE C-ABI call: pod columns in, winner out (b200s_schedule_batch); ctypes arguments marshalled once, as cgo's are
+    combined = eng.prepare_schedule_batch(batch, 0b11111, w, 1, topk1)
 
     res["all_five_plugins_top1"] = p50(combined)
-    res["all_five_plugins_top1"]["path"] = "b200s_schedule_batch -> cycle.cu: two launches for the whole cycle, no per-plugin matrix"
+    res["all_five_plugins_top1"]["path"] = ("b200s_schedule_batch -> cycle.cu: copy of the pod columns + two kernels as one "
+                                            "graph launch, winner written to a mapped host page, no per-plugin matrix")
     fused_winner = (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"]))
+    eng.config_fused_cycle(2)  # the same two kernels issued as plain launches + copies
+    res["all_five_plugins_top1_plain_launches"] = p50(combined)
+    assert (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"])) == fused_winner, "graph and plain-launch cycle disagree"
     eng.config_fused_cycle(False)  # the plugin-by-plugin path of round 1 (13 launches) for comparison
     res["all_five_plugins_top1_plugin_by_plugin"] = p50(combined)
     assert (int(topk1[0, 0]["score"]), int(topk1[0, 0]["node"])) == fused_winner, "fused cycle and plugin-by-plugin path disagree"

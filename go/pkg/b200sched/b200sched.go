@@ -333,6 +333,22 @@ func (e *Engine) FetchTopK(out *Pinned, bytes int) error {
 	return e.err(C.b200s_fetch_topk(e.ctx, (*C.b200s_topk_entry)(out.p), C.size_t(bytes)), "fetch_topk")
 }
 
+// ScheduleBatch is the engine-only profile in one call with one synchronisation: upload the batch's pod columns,
+// evaluate the weighted combination, copy the [NPods][k] winners to out (pinned).  For NPods <= 4 on one GPU this is
+// two kernel launches and no per-plugin matrix (cycle.cu).
+func (e *Engine) ScheduleBatch(b *C.b200s_pod_batch, pluginMask uint32, weights [C.B200S_PLUGIN_COUNT]int64, k int, out *Pinned) error {
+	return e.err(C.b200s_schedule_batch(e.ctx, b, C.uint32_t(pluginMask), (*C.int64_t)(unsafe.Pointer(&weights[0])), C.int32_t(k),
+		(*C.b200s_topk_entry)(out.p)), "schedule_batch")
+}
+
+// ScheduleSequence places a whole batch pod by pod with the assume step on the device (the OverReserve deduction of
+// overreserve.go:148-182 / store.go:129-160 and the Trimaran bind cache of handler.go:131-167).  The resident snapshot
+// is modified in place: a failed bind resyncs that node's rows through the patch calls.
+func (e *Engine) ScheduleSequence(b *C.b200s_pod_batch, pluginMask uint32, weights [C.B200S_PLUGIN_COUNT]int64, out *Pinned) error {
+	return e.err(C.b200s_schedule_sequence(e.ctx, b, C.uint32_t(pluginMask), (*C.int64_t)(unsafe.Pointer(&weights[0])),
+		(*C.b200s_topk_entry)(out.p)), "schedule_sequence")
+}
+
 // ---- multi-GPU: one Engine per shard ---------------------------------------------------------------------------------
 
 func CommUniqueID() ([C.B200S_UNIQUE_ID_BYTES]byte, error) {

@@ -385,8 +385,8 @@ int b200s_eval_combined(b200s_ctx* ctx, uint32_t plugin_mask,
                         const int64_t* weights /* [B200S_PLUGIN_COUNT] */, int32_t k,
                         int write_total_matrix);
 int b200s_fetch_topk(b200s_ctx* ctx, b200s_topk_entry* out, size_t bytes); /* [P][k] */
-/* Small batches (<= 4 pods -- the real scheduler runs one pod per cycle) on a single GPU go through ONE cooperative
- * kernel that does the whole cycle (filters, scores, NormalizeScore, weighted sum, top-k) without materialising any
+/* Small batches (<= 4 pods -- the real scheduler runs one pod per cycle) on a single GPU go through TWO launches
+ * that do the whole cycle (filters, scores, NormalizeScore, weighted sum, top-k) without materialising any
  * per-plugin matrix; b200s_fetch_total_feasible still works, b200s_fetch_scores of the individual plugins does not.
  * on = 0 keeps the plugin-by-plugin path for every batch size (parity tests, A/B timing).  Default on. */
 int b200s_config_fused_cycle(b200s_ctx* ctx, int on);

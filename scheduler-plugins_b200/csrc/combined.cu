@@ -188,7 +188,7 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
   if (!weights) return c->set_err(B200S_ERR_INVALID, "eval_combined: null weights");
   if ((mask & ((1u << B200S_PLUGIN_COUNT) - 1)) == 0) return c->set_err(B200S_ERR_INVALID, "eval_combined: no plugin enabled");
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
-  c->total_valid = c->topk_valid = false;
+  c->total_valid = c->topk_valid = c->feas_valid = false;
   c->mask_override = nullptr;
   if (cycle_applies(c, mask, k, write_total)) {  // a handful of pods on one GPU: the whole cycle as ONE kernel
     for (auto& o : c->out) o.valid = false;

@@ -117,7 +117,7 @@ __device__ __forceinline__ int64_t netoh_norm(int64_t s, int64_t lo, int64_t hi,
 // phase 1: one thread per node slot (through the class-sorted permutation when NodeResourceTopologyMatch is on, so the
 // lanes of a warp share their control flow)
 template <int SC>
-__global__ void __launch_bounds__(128) cycle_phase1_kernel(CycleArgs a) {
+__global__ void __launch_bounds__(128, 3) cycle_phase1_kernel(CycleArgs a) {
   __shared__ PodS<R> sp[PMAX];
   __shared__ unsigned long long s_red[PMAX][4];
   const int t = threadIdx.x, P = a.P;
@@ -428,14 +428,16 @@ bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total, bool any
   return true;
 }
 
-// pods [p0, p0 + np) of the uploaded batch; winners to out[np][k] (device)
-static int cycle_launch(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int p0, int np, b200s_topk_entry* out) {
+// The two launches of pods [p0, p0 + np) of the uploaded batch: arguments (winners to out[np][k]), kernel variant and
+// grid.  May queue snapshot-time work (Allocatable's raw score / sort, the first zeroing of the min/max cells) on the
+// engine stream; the caller launches after it.
+static int cycle_build(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int p0, int np, b200s_topk_entry* out,
+                       CycleArgs& a, int& sc, int& blocks) {
   const int P = np, Npad = c->Npad;
-  const int sc = (mask & (1u << B200S_PLUGIN_NRT)) && c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION ? 1 : 0;
-  const int blocks = (Npad + 255) / 256;  // phase 2 CTAs = rows of the per-block winners
+  sc = (mask & (1u << B200S_PLUGIN_NRT)) && c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION ? 1 : 0;
+  blocks = (Npad + 255) / 256;  // phase 2 CTAs = rows of the per-block winners
   B200S_CUDA_TRY(c, c->cycle_scratch.ensure((size_t)256 + (size_t)P * Npad * 12 + (size_t)P * blocks * k * sizeof(b200s_topk_entry) + 64));
   char* base = c->cycle_scratch.as<char>();
-  CycleArgs a;
   memset(&a, 0, sizeof(a));
   a.mask = mask;
   a.P = P;
@@ -518,14 +520,135 @@ static int cycle_launch(b200s_ctx* c, uint32_t mask, const int64_t* weights, int
   }
   a.blocks2 = blocks;
   a.perm = (mask & (1u << B200S_PLUGIN_NRT)) ? c->nrt_perm.as<int32_t>() : nullptr;
+  return B200S_OK;
+}
+
+// pods [p0, p0 + np) of the uploaded batch; winners to out[np][k] (device)
+static int cycle_launch(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int p0, int np, b200s_topk_entry* out) {
+  CycleArgs a;
+  int sc, blocks;
+  B200S_TRY(cycle_build(c, mask, weights, k, p0, np, out, a, sc, blocks));
   KernelTimer kt(c, B200S_PLUGIN_COUNT + B200S_PHASE_COMBINE);
   if (sc)
-    cycle_phase1_kernel<1><<<Npad / 128, 128, 0, c->stream>>>(a);
+    cycle_phase1_kernel<1><<<c->Npad / 128, 128, 0, c->stream>>>(a);
   else
-    cycle_phase1_kernel<0><<<Npad / 128, 128, 0, c->stream>>>(a);
+    cycle_phase1_kernel<0><<<c->Npad / 128, 128, 0, c->stream>>>(a);
   cycle_phase2_kernel<<<blocks, 256, 0, c->stream>>>(a);
   c->launches += 2;
   B200S_CUDA_TRY(c, cudaGetLastError());
+  return B200S_OK;
+}
+
+// ---- b200s_schedule_batch's cycle as ONE graph launch ------------------------------------------------------------------
+// A scheduling cycle of one pod is bound by the host's driver calls, not by the device: copy of the pod columns, two
+// kernel launches, copy of the winners.  The three device-side operations are a CUDA graph that is instantiated once
+// and re-launched; the pod columns always travel through the same pinned staging block into the same arena, so between
+// two cycles normally nothing but the CONTENT of that block changes.  Whatever does change (the size of the copy when a
+// pod has more NetworkOverhead dependencies, buffer addresses after a snapshot upload, weights, strategy) is patched
+// into the instantiated graph with the ExecSetParams calls -- compared bytewise, so a stale parameter cannot survive.
+// The winners are written by the folding CTA straight into the engine's pinned, device-mapped result page.
+namespace {
+struct CycleGraph {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t x = nullptr;
+  cudaGraphNode_t copy = nullptr, k1 = nullptr, k2 = nullptr;
+  CycleArgs a;
+  int sc = -1, grid1 = 0, grid2 = 0;
+  void* cp_dst = nullptr;
+  const void* cp_src = nullptr;
+  size_t cp_bytes = 0;
+};
+
+void fill_kernel_params(cudaKernelNodeParams& kp, void** argv, int sc, int phase, int grid) {
+  memset(&kp, 0, sizeof(kp));
+  kp.func = phase == 1 ? (sc ? (void*)cycle_phase1_kernel<1> : (void*)cycle_phase1_kernel<0>) : (void*)cycle_phase2_kernel;
+  kp.gridDim = dim3(grid);
+  kp.blockDim = dim3(phase == 1 ? 128 : 256);
+  kp.sharedMemBytes = 0;
+  kp.kernelParams = argv;
+  kp.extra = nullptr;
+}
+}  // namespace
+
+void cycle_graph_free(b200s_ctx* c) {
+  CycleGraph* G = static_cast<CycleGraph*>(c->cycle_graph);
+  if (!G) return;
+  if (G->x) cudaGraphExecDestroy(G->x);
+  if (G->g) cudaGraphDestroy(G->g);
+  delete G;
+  c->cycle_graph = nullptr;
+}
+
+// The held copy of the pod columns (c->held_*), both launches, winners to host_out (pinned + mapped, [P][k]).
+int cycle_graph_run(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, b200s_topk_entry* host_out) {
+  b200s_topk_entry* dev_out = nullptr;
+  B200S_CUDA_TRY(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_out), host_out, 0));
+  CycleArgs a;
+  int sc, blocks;
+  B200S_TRY(cycle_build(c, mask, weights, k, 0, c->P, dev_out, a, sc, blocks));
+  const int grid1 = c->Npad / 128;
+  CycleGraph* G = static_cast<CycleGraph*>(c->cycle_graph);
+  void* argv[1] = {&a};
+  cudaKernelNodeParams kp;
+  if (G && G->sc != sc) {  // another kernel function: rebuild (a strategy change, once)
+    cycle_graph_free(c);
+    G = nullptr;
+  }
+  if (!G) {
+    G = new CycleGraph();
+    c->cycle_graph = G;
+    cudaError_t e = cudaGraphCreate(&G->g, 0);
+    if (e == cudaSuccess)
+      e = cudaGraphAddMemcpyNode1D(&G->copy, G->g, nullptr, 0, c->held_dst, c->held_src, c->held_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      fill_kernel_params(kp, argv, sc, 1, grid1);
+      e = cudaGraphAddKernelNode(&G->k1, G->g, &G->copy, 1, &kp);
+    }
+    if (e == cudaSuccess) {
+      fill_kernel_params(kp, argv, sc, 2, blocks);
+      e = cudaGraphAddKernelNode(&G->k2, G->g, &G->k1, 1, &kp);
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&G->x, G->g, 0);
+    if (e != cudaSuccess) {
+      cycle_graph_free(c);
+      return c->set_err(B200S_ERR_CUDA, std::string("schedule_batch: building the cycle graph: ") + cudaGetErrorString(e));
+    }
+    G->a = a;
+    G->sc = sc;
+    G->grid1 = grid1;
+    G->grid2 = blocks;
+    G->cp_dst = c->held_dst;
+    G->cp_src = c->held_src;
+    G->cp_bytes = c->held_bytes;
+  } else {
+    cudaError_t e = cudaSuccess;
+    if (G->cp_dst != c->held_dst || G->cp_src != c->held_src || G->cp_bytes != c->held_bytes) {
+      e = cudaGraphExecMemcpyNodeSetParams1D(G->x, G->copy, c->held_dst, c->held_src, c->held_bytes, cudaMemcpyHostToDevice);
+      G->cp_dst = c->held_dst;
+      G->cp_src = c->held_src;
+      G->cp_bytes = c->held_bytes;
+    }
+    if (e == cudaSuccess && (memcmp(&G->a, &a, sizeof(a)) != 0 || G->grid1 != grid1 || G->grid2 != blocks)) {
+      fill_kernel_params(kp, argv, sc, 1, grid1);
+      e = cudaGraphExecKernelNodeSetParams(G->x, G->k1, &kp);
+      if (e == cudaSuccess) {
+        fill_kernel_params(kp, argv, sc, 2, blocks);
+        e = cudaGraphExecKernelNodeSetParams(G->x, G->k2, &kp);
+      }
+      G->a = a;
+      G->grid1 = grid1;
+      G->grid2 = blocks;
+    }
+    if (e != cudaSuccess) {
+      cycle_graph_free(c);
+      return c->set_err(B200S_ERR_CUDA, std::string("schedule_batch: updating the cycle graph: ") + cudaGetErrorString(e));
+    }
+  }
+  c->held_bytes = 0;  // the graph's first node is the copy
+  B200S_CUDA_TRY(c, cudaGraphLaunch(G->x, c->stream));
+  c->launches += 2;
+  c->topk_valid = c->total_valid = false;  // the winners went to the caller, not to the engine's top-k buffer
+  c->feas_valid = true;                    // ... the final feasible set is resident
   return B200S_OK;
 }
 

@@ -335,6 +335,7 @@ void b200s_shutdown(b200s_ctx* c) {
   if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
   c->pod_lo_alt.release();
   c->cycle_scratch.release();
+  cycle_graph_free(c);
   if (c->small_bounce) cudaFreeHost(c->small_bounce);
   c->norm_params_alt.release();
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
@@ -482,7 +483,7 @@ int b200s_snapshot_begin(b200s_ctx* c, uint64_t generation, int32_t n_nodes, int
   c->Nglobal = n_nodes_global;
   c->has_alloc = c->has_tlp = c->has_lvrb = c->has_nrt = c->has_netoh = c->has_peaks = c->has_lowrisk = false;
   for (auto& o : c->out) o.valid = false;
-  c->total_valid = c->topk_valid = false;
+  c->total_valid = c->topk_valid = c->feas_valid = false;
   return B200S_OK;
 }
 
@@ -700,7 +701,7 @@ int b200s_snapshot_patch_begin(b200s_ctx* c, uint64_t generation) {
   c->snap_valid = false;
   c->gen = generation;
   for (auto& o : c->out) o.valid = false;
-  c->total_valid = c->topk_valid = false;
+  c->total_valid = c->topk_valid = c->feas_valid = false;
   c->netoh_raw_P = -1;
   return B200S_OK;
 }
@@ -985,15 +986,17 @@ struct PodUpload {
     size_t total = 0;
     for (auto& it : items)
       if (it.bytes <= kSmall) total += (it.bytes + kAlign - 1) / kAlign * kAlign;
+    // held for the cycle graph: the copy is rounded up to 4 KiB so that its size rarely changes between cycles
+    const size_t need = c->hold_upload ? (total + 4095) / 4096 * 4096 : total;
     if (total > 0) {
-      if (total > c->pods_stage_cap) {
+      if (need > c->pods_stage_cap) {
         if (c->pods_stage) cudaFreeHost(c->pods_stage);
         c->pods_stage = nullptr;
         c->pods_stage_cap = 0;
-        B200S_CUDA_TRY(c, cudaHostAlloc(&c->pods_stage, total * 2, cudaHostAllocDefault));
-        c->pods_stage_cap = total * 2;
+        B200S_CUDA_TRY(c, cudaHostAlloc(&c->pods_stage, need * 2, cudaHostAllocDefault));
+        c->pods_stage_cap = need * 2;
       }
-      B200S_CUDA_TRY(c, c->pods_arena.ensure(total));
+      B200S_CUDA_TRY(c, c->pods_arena.ensure(need));
     }
     size_t off = 0;
     for (auto& it : items) {
@@ -1006,8 +1009,14 @@ struct PodUpload {
         B200S_CUDA_TRY(c, cudaMemcpyAsync(it.d->p, it.s, it.bytes, cudaMemcpyHostToDevice, c->stream));
       }
     }
-    if (total > 0)
+    c->held_bytes = 0;
+    if (total > 0 && c->hold_upload) {  // b200s_schedule_batch: the copy is the first node of the cycle graph
+      c->held_dst = c->pods_arena.p;
+      c->held_src = c->pods_stage;
+      c->held_bytes = need;
+    } else if (total > 0) {
       B200S_CUDA_TRY(c, cudaMemcpyAsync(c->pods_arena.p, c->pods_stage, total, cudaMemcpyHostToDevice, c->stream));
+    }
     return B200S_OK;
   }
 };
@@ -1104,7 +1113,7 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
   if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& o : c->out) o.valid = false;
-  c->total_valid = c->topk_valid = false;
+  c->total_valid = c->topk_valid = c->feas_valid = false;
   c->pods_valid = true;
   return B200S_OK;
 }
@@ -1145,7 +1154,7 @@ static int fetch(b200s_ctx* c, const DevBuf& src, void* out, size_t bytes, size_
   if (want <= (size_t)4096 && !c->defer_sync) {
     // small results (a cycle's winners): a device-to-host copy into PAGEABLE memory takes the driver's slow staged
     // path (~10 us); bounce through the engine's pinned page instead
-    if (!c->small_bounce) B200S_CUDA_TRY(c, cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocDefault));
+    if (!c->small_bounce) B200S_CUDA_TRY(c, cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocMapped));
     B200S_CUDA_TRY(c, cudaMemcpyAsync(c->small_bounce, src.p, want, cudaMemcpyDeviceToHost, c->stream));
     B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     memcpy(out, c->small_bounce, want);
@@ -1247,7 +1256,7 @@ int b200s_fetch_total(b200s_ctx* c, int64_t* out, size_t bytes) {
 int b200s_fetch_total_feasible(b200s_ctx* c, uint64_t* out, size_t bytes) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
-  if (!c->topk_valid) return c->set_err(B200S_ERR_STATE, "fetch_total_feasible: eval_combined not run");
+  if (!c->topk_valid && !c->feas_valid) return c->set_err(B200S_ERR_STATE, "fetch_total_feasible: eval_combined not run");
   return fetch(c, c->total_feas, out, bytes, (size_t)c->P * (c->Npad / 64) * 8, "fetch_total_feasible");
 }
 
@@ -1305,7 +1314,7 @@ static int score_batch_chunked(b200s_ctx* c, b200s_plugin plugin, const b200s_po
 int b200s_config_fused_cycle(b200s_ctx* c, int on) {
   if (!c) return B200S_ERR_INVALID;
   Guard g(c);
-  c->fused_cycle = on != 0;
+  c->fused_cycle = on == 2 ? 2 : (on != 0 ? 1 : 0);
   return B200S_OK;
 }
 
@@ -1318,12 +1327,36 @@ int b200s_schedule_batch(b200s_ctx* c, const b200s_pod_batch* batch, uint32_t pl
     explicit Defer(b200s_ctx* x) : c(x) { c->defer_sync = true; }
     ~Defer() { c->defer_sync = false; }
   } defer(c);
+  // a handful of pods on one GPU: copy of the pod columns + both launches of the cycle as ONE graph launch (cycle.cu)
+  const bool try_graph = c->fused_cycle == 1 && !c->profiling && weights && batch && batch->n_pods >= 1 && batch->n_pods <= 4 &&
+                         k >= 1 && (size_t)batch->n_pods * k * sizeof(b200s_topk_entry) <= 4096;
+  c->hold_upload = try_graph;
   int rc = pods_upload_locked(c, batch);
+  c->hold_upload = false;
+  if (rc == B200S_OK && c->held_bytes > 0) {
+    if (!c->small_bounce && cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocMapped) != cudaSuccess) c->small_bounce = nullptr;
+    if (c->small_bounce && cycle_applies(c, plugin_mask, k, 0)) {
+      const size_t bytes = (size_t)c->P * k * sizeof(b200s_topk_entry);
+      c->mask_override = nullptr;
+      for (auto& o : c->out) o.valid = false;
+      rc = cycle_graph_run(c, plugin_mask, weights, k, static_cast<b200s_topk_entry*>(c->small_bounce));
+      cudaError_t e = cudaStreamSynchronize(c->stream);
+      c->held_bytes = 0;
+      if (rc != B200S_OK) return rc;
+      if (e != cudaSuccess) return c->set_err(B200S_ERR_CUDA, std::string("schedule_batch: ") + cudaGetErrorString(e));
+      memcpy(topk_out, c->small_bounce, bytes);
+      return B200S_OK;
+    }
+    // not a fused-cycle shape after all: move the staged columns now and take the general path
+    cudaError_t e = cudaMemcpyAsync(c->held_dst, c->held_src, c->held_bytes, cudaMemcpyHostToDevice, c->stream);
+    c->held_bytes = 0;
+    if (e != cudaSuccess) rc = c->set_err(B200S_ERR_CUDA, "schedule_batch: copy of the pod columns failed");
+  }
   if (rc == B200S_OK) rc = combined_eval(c, plugin_mask, weights, k, 0);
   const size_t want = rc == B200S_OK ? (size_t)c->P * k * sizeof(b200s_topk_entry) : 0;
   void* dst = topk_out;
   if (want > 0 && want <= 4096) {  // pinned bounce page: a copy into pageable memory takes the driver's slow path
-    if (!c->small_bounce && cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocDefault) != cudaSuccess) c->small_bounce = nullptr;
+    if (!c->small_bounce && cudaHostAlloc(&c->small_bounce, 4096, cudaHostAllocMapped) != cudaSuccess) c->small_bounce = nullptr;
     if (c->small_bounce) dst = c->small_bounce;
   }
   if (want > 0 && cudaMemcpyAsync(dst, c->topk_final.p, want, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
@@ -1363,7 +1396,7 @@ int b200s_schedule_sequence(b200s_ctx* c, const b200s_pod_batch* batch, uint32_t
     // the columns changed under the derived data (batched NRT node columns): a new snapshot serial refreshes them
     c->snap_serial++;
     for (auto& o : c->out) o.valid = false;
-    c->topk_valid = c->total_valid = false;
+    c->topk_valid = c->total_valid = c->feas_valid = false;
     if (rc == B200S_OK && cudaMemcpyAsync(winners_out, c->topk_final.p, want, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
       rc = c->set_err(B200S_ERR_CUDA, "schedule_sequence: copy of the winners failed");
   }
@@ -1403,7 +1436,7 @@ int b200s_score_batch(b200s_ctx* c, b200s_plugin plugin, const b200s_pod_batch* 
     // the engine-resident matrices hold the last chunk only: nothing may be fetched from them afterwards
     c->pods_valid = false;
     for (auto& o : c->out) o.valid = false;
-    c->total_valid = c->topk_valid = false;
+    c->total_valid = c->topk_valid = c->feas_valid = false;
     if (rc != B200S_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return c->set_err(B200S_ERR_CUDA, std::string("score_batch: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

@@ -238,10 +238,16 @@ struct b200s_ctx {
   void* small_bounce = nullptr;  // one pinned page for small device-to-host results (a cycle's winners)
   void* cycle_cells_base = nullptr;
   bool cycle_cells_zero = false; // the fused cycle's min/max cells are zero (the folding CTA resets them)
-  bool fused_cycle = true;      // b200s_config_fused_cycle: small batches go through cycle.cu's single kernel
+  int fused_cycle = 1;          // b200s_config_fused_cycle: 0 off, 1 small batches go through cycle.cu (b200s_schedule_batch as
+                                //   one graph launch), 2 the same without the graph
+  void* cycle_graph = nullptr;  // cycle.cu: the instantiated graph of b200s_schedule_batch (copy + two kernels)
+  bool hold_upload = false;     // b200s_schedule_batch: stage the pod columns, let the graph's copy node move them
+  void* held_dst = nullptr;
+  const void* held_src = nullptr;
+  size_t held_bytes = 0;
   b200s::DevBuf cycle_scratch;  // fused cycle kernel: min/max cells, per-node partial scores, per-block winners
   int topk_k = 0;
-  bool total_valid = false, topk_valid = false;
+  bool total_valid = false, topk_valid = false, feas_valid = false;  // feas_valid: total_feas without a resident top-k
 
   // ---- harness profiling: event pairs around the dominant kernel of each eval ----
   bool profiling = false;
@@ -293,6 +299,8 @@ int alloc_prepare(b200s_ctx* c);  // raw scores + sorted order of the snapshot (
 // cycle.cu: the whole cycle as one cooperative kernel (small P, single GPU)
 bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total, bool any_p = false);
 int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k);
+int cycle_graph_run(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, b200s_topk_entry* host_out);
+void cycle_graph_free(b200s_ctx* c);
 int cycle_sequence(b200s_ctx* c, uint32_t mask, const int64_t* weights, b200s_topk_entry* winners);
 
 // nrt2.cu: batched NodeResourceTopologyMatch path (score tables per distinct request vector + coalesced expansion)

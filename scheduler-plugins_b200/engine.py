@@ -503,8 +503,10 @@ class Engine:
                                                C.c_int(1 if write_total else 0)))
         self._k = k
 
-    def config_fused_cycle(self, on: bool):
-        self._chk(self.lib.b200s_config_fused_cycle(self.ctx, C.c_int(1 if on else 0)))
+    def config_fused_cycle(self, on):
+        """False / 0: plugin-by-plugin for every batch size; True / 1: fused cycle, b200s_schedule_batch as one graph
+        launch; 2: fused cycle with plain launches (A/B timing)"""
+        self._chk(self.lib.b200s_config_fused_cycle(self.ctx, C.c_int(2 if on == 2 else (1 if on else 0))))
 
     def schedule_batch(self, batch, plugin_mask, weights, k=1, out=None):
         """upload + eval_combined + winners to host in ONE call / ONE synchronisation; returns [P][k] TOPK_DTYPE"""
@@ -516,6 +518,23 @@ class Engine:
         self._chk(self.lib.b200s_schedule_batch(self.ctx, C.byref(batch), C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k), _ptr(out)))
         self.P, self._k = P, k
         return out
+
+    def prepare_schedule_batch(self, batch, plugin_mask, weights, k, out):
+        """b200s_schedule_batch with every ctypes argument built once: returns a zero-argument callable whose cost is the
+        C-ABI call itself (latency measurements; the cgo call of the Go shim has no marshalling either).  `batch`, `out`
+        and the returned callable's captured arrays must stay alive and unchanged in layout."""
+        w = np.zeros(PLUGIN_COUNT, dtype=np.int64)
+        w[:len(weights)] = np.asarray(weights, dtype=np.int64)
+        fn, ctx, bref = self.lib.b200s_schedule_batch, self.ctx, C.byref(batch)
+        m, wp, kk, op = C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k), _ptr(out)
+        self.P, self._k = int(batch.n_pods), k
+
+        def call(_keep=(w, batch, out)):
+            rc = fn(ctx, bref, m, wp, kk, op)
+            if rc != OK:
+                self._chk(rc)
+
+        return call
 
     def schedule_sequence(self, batch, plugin_mask, weights):
         """speculative placement of the batch pod by pod with the on-device assume; returns [P] TOPK_DTYPE winners"""

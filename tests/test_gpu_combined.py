@@ -110,7 +110,7 @@ def test_combined_without_total_matrix_and_no_upstream_mask(eng, engine_mod):
 @pytest.mark.parametrize("mask,k,strategy", [(0b11111, 1, 2), (0b11111, 4, 0), (0b11111, 16, 1), (0b01001, 3, 2), (0b10110, 2, 2),
                                              (0b00001, 1, 2), (0b10000, 5, 2), (0b01000, 2, 1)])
 def test_fused_cycle_matches_oracle_and_the_plugin_by_plugin_path(eng, engine_mod, P, mask, k, strategy):
-    """cycle.cu: the whole cycle of a handful of pods as ONE cooperative kernel -- the same winners and the same final
+    """cycle.cu: the whole cycle of a handful of pods in two launches -- the same winners and the same final
     feasible set as the oracle's restatement of the upstream cycle and as the plugin-by-plugin path."""
     E = engine_mod
     N = 3000 + 37 * P
@@ -138,6 +138,20 @@ def test_fused_cycle_matches_oracle_and_the_plugin_by_plugin_path(eng, engine_mo
                                  nrt=d["nrt_pods"], netoh=d["net"])
     one = eng.schedule_batch(batch, mask, weights, k=k)
     assert np.array_equal(one["score"], got["score"]) and np.array_equal(one["node"], got["node"])
+    assert np.array_equal(eng.fetch_total_feasible(), want_feas)
+    # ... which is one graph launch for <= 4 pods: re-launched as is, patched when arguments change, and identical to the
+    # same two kernels issued as plain launches
+    again = eng.schedule_batch(batch, mask, weights, k=k)
+    assert np.array_equal(again["score"], got["score"]) and np.array_equal(again["node"], got["node"])
+    w2 = [1, 4, 2, 1, 1]
+    _, _, want2 = oracle_combined(d, P, N, eng.Npad, feas, w2, k, mask, nrt_strategy=strategy)
+    other = eng.schedule_batch(batch, mask, w2, k=k)
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in other[p]] == want2[p], p
+    eng.config_fused_cycle(2)
+    plain = eng.schedule_batch(batch, mask, w2, k=k)
+    eng.config_fused_cycle(True)
+    assert np.array_equal(plain["score"], other["score"]) and np.array_equal(plain["node"], other["node"])
 
 
 @pytest.mark.parametrize("mask,strategy", [(0b11111, 2), (0b01010, 0), (0b01000, 1)])

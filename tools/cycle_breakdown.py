@@ -42,6 +42,10 @@ def p50(fn, n=2000):
 
 res = {"nodes": N}
 res["schedule_batch_us"] = p50(lambda: eng.schedule_batch(batch, 0b11111, w, 1, out))
+res["schedule_batch_prepared_call_us"] = p50(eng.prepare_schedule_batch(batch, 0b11111, w, 1, out))
+eng.config_fused_cycle(2)
+res["schedule_batch_prepared_call_plain_launches_us"] = p50(eng.prepare_schedule_batch(batch, 0b11111, w, 1, out))
+eng.config_fused_cycle(True)
 res["pods_upload_us"] = p50(lambda: eng._chk(eng.lib.b200s_pods_upload(eng.ctx, C.byref(batch))))
 eng.P = 1
 res["eval_combined_plus_sync_us"] = p50(lambda: (eng.eval_combined(0b11111, w, 1, False), eng.sync()))
