@@ -561,8 +561,8 @@ def main():
     plugins = {"c2": [E.PLUGIN_ALLOCATABLE], "c3": [E.PLUGIN_TLP, E.PLUGIN_LVRB], "c4": [E.PLUGIN_NRT],
                "c5": [E.PLUGIN_NRT, E.PLUGIN_NETWORK_OVERHEAD, E.PLUGIN_ALLOCATABLE, E.PLUGIN_TLP, E.PLUGIN_LVRB]}[cfg]
     dom = {"c2": (E.PLUGIN_ALLOCATABLE, "alloc_norm_kernel<int64>"), "c3": (E.PLUGIN_LVRB, "lvrb_kernel<int64>"),
-           "c4": (E.PLUGIN_NRT, "nrt2_table_kernel x2 + nrt2_expand_kernel<int64>"),
-           "c5": (E.PLUGIN_NRT, "nrt2_table_kernel x2 + nrt2_expand_kernel<u8>")}[cfg]
+           "c4": (E.PLUGIN_NRT, "nrt2_q_kernel + nrt2_tableq_kernel x2 + nrt2_expand_kernel<int64>"),
+           "c5": (E.PLUGIN_NRT, "nrt2_q_kernel + nrt2_tableq_kernel x2 + nrt2_expand_kernel<u8>")}[cfg]
     topk_rows = {}  # c5: chunk index -> fetched [chunk][1] winners of the last step
 
     if cfg == "c5":

@@ -13,6 +13,17 @@
  *     published Cephes description; log, pow, tgamma and lgamma come from libm.  Pinned against the reference's
  *     unit-test vectors (tests/golden/lowrisk.json: the sigma = 0 paths and beta(2,2)) and cross-checked against
  *     scipy.special.betainc to 1e-12 -- "parity partial": bit-identity with gonum cannot be claimed.
+ *
+ * UPSTREAM NOTICES (restatements, not copies; full texts in NOTICE.md).
+ *   math.Exp: Copyright (c) 2009 The Go Authors (BSD-style licence); the algorithm and constants are FreeBSD's
+ *   lib/msun/src/e_exp.c, which came with this notice:
+ *     ====================================================
+ *     Copyright (C) 2004 by Sun Microsystems, Inc. All rights reserved.
+ *     Permission to use, copy, modify, and distribute this software is freely granted, provided that this notice
+ *     is preserved.
+ *     ====================================================
+ *   incbet: Cephes Math Library Release 2.3, Copyright 1984, 1995 by Stephen L. Moshier; gonum's port
+ *   Copyright (c) 2016 The Gonum Authors (BSD-style licence).
  */
 #include <math.h>
 

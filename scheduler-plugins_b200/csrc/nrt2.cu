@@ -26,8 +26,10 @@
 // (cv - rv) * 100 / cv are invariant under the common factor, so results are bit-identical to the 64-bit path as long as
 // the scaled values fit (checked on the host; otherwise nrt_eval keeps the direct 64-bit kernel of nrt.cu).
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
 
 #include "engine.h"
@@ -133,13 +135,17 @@ struct Nrt2 {
   uint64_t prep_gm[4] = {0, 0, 0, 0}, prep_gv[4] = {0, 0, 0, 0};
   bool prep_ok = false;
   DevBuf vecrec, d_pod_vec, d_pod_tc, d_pod_tp, d_tc_list, d_tp_list;
+  // quotient-table form of the table kernels (Least / MostAllocated): distinct (resource, request value) keys
+  bool use_q = false;
+  int n_qkeys = 0;
+  DevBuf qkeys, rowq_c, rowq_p, Q;  // [K] QKey, [rows] RowQ x2, [K][S] u32 (one byte per zone)
   DevBuf Tc, Tp;
   int last_path = 0;  // 1 direct, 2 table (what the last nrt_eval ran)
   const char* note = "";  // why the batched path was declined last time (static string)
   int force = 0;      // 0 auto, 1 direct, 2 table when applicable
   ~Nrt2() {
     for (DevBuf* b : {&stats_part, &slot, &list, &tile_n0, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
-                      &d_tc_list, &d_tp_list, &Tc, &Tp})
+                      &d_tc_list, &d_tp_list, &Tc, &Tp, &qkeys, &rowq_c, &rowq_p, &Q})
       b->release();
   }
 };
@@ -532,6 +538,121 @@ __global__ void __launch_bounds__(128) nrt2_table_kernel(TableArgs a, void* __re
           (uint8_t)(ok != 0 ? (uint32_t)score : 128u + B200S_REASON_NRT_ALIGN_POD);
     else  // container table: score of the vector (Guaranteed only) | zones that fit before any subtraction << 8
       static_cast<uint16_t*>(Tout)[(size_t)(row0 + j) * a.count + slot] = (uint16_t)((uint32_t)score | (ok << 8));
+  }
+}
+
+// ---- quotient tables -----------------------------------------------------------------------------------------------------
+// A table entry is a function of (request vector, node), but each of its 16 divisions is a function of ONE request VALUE
+// and one (zone, resource) cell: floor((cv - rv) * 100 / cv) (least_allocated.go:57-66; rv * 100 / cv for
+// most_allocated.go:56-63) and the Filter comparison available >= request (filter.go:127-135).  A batch names few distinct
+// values per resource (c4: ~30 against 3 700 vectors), so the quotients are computed once per (value, cell) -- Q[key][slot],
+// one byte per zone: quotient | fits << 7 -- and a table entry is four coalesced word loads, a 16-bit-lane weighted sum,
+// four exact divisions by the weight sum and the minimum over the zones.
+struct QKey {
+  int32_t eff, rq, rv, r;  // Filter threshold, scaled request (milli), scaled Value(), resource slot
+};
+struct alignas(16) RowQ {   // one table row = one distinct request vector
+  uint16_t j[4];            // key of each resource slot
+  uint16_t w[4];            // weight if the resource is named, else 0 (sum <= 655: 100 x sum fits a 16-bit lane)
+  uint32_t wsum, wmagic;
+  uint8_t need, guar;
+  uint16_t pad;
+  uint32_t pad2;
+};
+static_assert(sizeof(RowQ) == 32, "RowQ layout");
+constexpr int QT = 16;    // keys per CTA of the quotient kernel
+constexpr int RT = 64;    // rows per CTA of the quotient-table kernel
+
+struct QArgs {
+  const int32_t* filt;  // [Z][R][S]
+  const int32_t* capv;
+  const uint32_t* magic;
+  const QKey* keys;
+  int K, S, most;
+};
+
+template <int Z, int R, bool WIDE>
+__global__ void __launch_bounds__(128) nrt2_q_kernel(QArgs a, uint32_t* __restrict__ Q) {
+  __shared__ QKey sk[QT];
+  const int k0 = blockIdx.y * QT, nk = min(QT, a.K - k0);
+  if ((int)threadIdx.x < nk) sk[threadIdx.x] = a.keys[k0 + threadIdx.x];
+  __syncthreads();
+  const int slot = blockIdx.x * 128 + threadIdx.x;
+  if (slot >= a.S) return;
+  for (int j = 0; j < nk; ++j) {
+    const QKey key = sk[j];  // warp-uniform
+    uint32_t word = 0;
+#pragma unroll
+    for (int z = 0; z < Z; ++z) {
+      const size_t o = ((size_t)z * R + key.r) * a.S + slot;
+      const int32_t f = a.filt[o], c = a.capv[o];
+      const uint32_t mg = a.magic[o];
+      const bool fits = f >= key.eff;
+      const bool zero = c == 0 || key.rq > f;  // capacity 0 (or resource missing) or request > capacity
+      const uint32_t av = zero ? 0u : (uint32_t)(a.most ? key.rv : c - key.rv);
+      const uint32_t q = WIDE ? div100_wide(av, (uint32_t)(c == 0 ? 1 : c), __uint_as_float(mg))
+                              : div_magic(av * 100u, (uint32_t)(c == 0 ? 1 : c), mg);
+      word |= (min(q, 127u) | (fits ? 128u : 0u)) << (8 * z);
+    }
+    Q[(size_t)(k0 + j) * a.S + slot] = word;
+  }
+}
+
+struct TableQArgs {
+  const uint32_t* Q;   // + class base already applied; stride S
+  const uint8_t* nzs;  // + class base
+  const uint8_t* nrm;
+  const RowQ* rows;
+  int nrows, S, count;
+};
+
+// Same entries as nrt2_table_kernel<4, 4, 0, POD, *> (bit for bit: the per-cell quotients and comparisons are those of
+// nrt2_q_kernel, the combination below is the rest of that kernel).
+template <bool POD>
+__global__ void __launch_bounds__(128) nrt2_tableq_kernel(TableQArgs a, void* __restrict__ Tout) {
+  __shared__ RowQ sr[RT];
+  const int row0 = blockIdx.y * RT, nrow = min(RT, a.nrows - row0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.rows + row0);
+    uint4* dst = reinterpret_cast<uint4*>(sr);
+    for (int i = threadIdx.x; i < nrow * 2; i += 128) dst[i] = src[i];
+  }
+  const int slot = blockIdx.x * 128 + threadIdx.x;
+  const int nz = a.nzs[slot];
+  const uint32_t nrm = a.nrm[slot];
+  const uint32_t* q = a.Q + slot;
+  __syncthreads();
+#pragma unroll 2
+  for (int j = 0; j < nrow; ++j) {
+    const RowQ v = sr[j];
+    const uint32_t w0 = q[(size_t)v.j[0] * a.S], w1 = q[(size_t)v.j[1] * a.S], w2 = q[(size_t)v.j[2] * a.S],
+                   w3 = q[(size_t)v.j[3] * a.S];
+    // bit 7 of byte z of every word: zone z fits resource r; gather the four bits of the AND into a nibble
+    uint32_t ok = ((((w0 & w1 & w2 & w3) >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    if (v.need & ~nrm) ok = 0;  // filter.go:107-113: a non-zero request must be reported at node level
+    uint32_t score = POD ? 100u : 0u;
+    if (v.guar) {  // warp-uniform
+      // zones 0 / 2 in the 16-bit lanes of A, zones 1 / 3 in those of B
+      const uint32_t A = (w0 & 0x007f007fu) * v.w[0] + (w1 & 0x007f007fu) * v.w[1] + (w2 & 0x007f007fu) * v.w[2] +
+                         (w3 & 0x007f007fu) * v.w[3];
+      const uint32_t B = ((w0 >> 8) & 0x007f007fu) * v.w[0] + ((w1 >> 8) & 0x007f007fu) * v.w[1] +
+                         ((w2 >> 8) & 0x007f007fu) * v.w[2] + ((w3 >> 8) & 0x007f007fu) * v.w[3];
+      const uint32_t acc[4] = {A & 0xffffu, B & 0xffffu, A >> 16, B >> 16};
+      uint32_t min_score = 0;
+#pragma unroll
+      for (int z = 0; z < 4; ++z) {
+        const uint32_t sz = v.wsum == 0 ? 0u : div_magic(acc[z], v.wsum, v.wmagic);
+        // scoreForEachNUMANode (score.go:110-124): minimum of the non-zero zone scores
+        const bool take = z < nz && (min_score == 0 || (sz != 0 && sz < min_score));
+        min_score = take ? sz : min_score;
+      }
+      score = min_score;
+    }
+    if constexpr (POD)
+      static_cast<uint8_t*>(Tout)[(size_t)(row0 + j) * a.count + slot] =
+          (uint8_t)(ok != 0 ? score : 128u + B200S_REASON_NRT_ALIGN_POD);
+    else
+      static_cast<uint16_t*>(Tout)[(size_t)(row0 + j) * a.count + slot] = (uint16_t)(score | (ok << 8));
   }
 }
 
@@ -941,6 +1062,55 @@ int nrt2_prepare(b200s_ctx* c) {
       o.guar = v.guar;
       o.mask = v.mask;
     }
+    // quotient-table form: distinct (resource, eff, rq, rv) keys and the rows of both tables in terms of them
+    std::vector<QKey> qkeys;
+    std::vector<RowQ> rowq_c(std::max<size_t>(s->tc_list.size(), 1)), rowq_p(std::max<size_t>(s->tp_list.size(), 1));
+    memset(rowq_c.data(), 0, rowq_c.size() * sizeof(RowQ));
+    memset(rowq_p.data(), 0, rowq_p.size() * sizeof(RowQ));
+    {
+      static const bool q_enabled = []() { const char* e = getenv("B200S_NRT2_Q"); return !(e && e[0] == '0'); }();
+      bool ok = q_enabled && c->nrt_strategy != B200S_NRT_BALANCED_ALLOCATION;
+      std::map<std::array<int32_t, 4>, int> index;
+      std::vector<std::array<uint16_t, 4>> vec_keys(std::max<size_t>(U, 1));
+      for (size_t u = 0; u < U && ok; ++u) {
+        const VecRec& o = recs[u];
+        if (o.wsum > 655) ok = false;
+        for (int r = 0; r < 4 && ok; ++r) {
+          const std::array<int32_t, 4> key = {r, o.eff[r], o.rq[r], o.rv[r]};
+          auto it = index.find(key);
+          if (it == index.end()) {
+            if (qkeys.size() >= 8192) {
+              ok = false;
+              break;
+            }
+            it = index.emplace(key, (int)qkeys.size()).first;
+            qkeys.push_back(QKey{o.eff[r], o.rq[r], o.rv[r], r});
+          }
+          vec_keys[u][r] = (uint16_t)it->second;
+        }
+      }
+      if (ok && qkeys.size() * (size_t)(s->Sc + s->Sp) * 4 > ((size_t)1 << 30)) ok = false;
+      auto fill = [&](std::vector<RowQ>& rows, const std::vector<int32_t>& list) {
+        for (size_t i = 0; i < list.size(); ++i) {
+          const VecRec& o = recs[(size_t)list[i]];
+          RowQ& q = rows[i];
+          for (int r = 0; r < 4; ++r) {
+            q.j[r] = vec_keys[(size_t)list[i]][r];
+            q.w[r] = (uint16_t)o.w[r];
+          }
+          q.wsum = o.wsum;
+          q.wmagic = o.wmagic;
+          q.need = o.need;
+          q.guar = o.guar;
+        }
+      };
+      if (ok) {
+        fill(rowq_c, s->tc_list);
+        fill(rowq_p, s->tp_list);
+      }
+      s->use_q = ok && !qkeys.empty();
+      s->n_qkeys = (int)qkeys.size();
+    }
     std::vector<int32_t> pod_tc(std::max<size_t>(P * C_MAX, 1), -1), pod_tp(std::max<size_t>(P, 1), -1);
     for (size_t p = 0; p < P; ++p) {
       for (int cidx = 0; cidx < C_MAX; ++cidx) {
@@ -961,6 +1131,11 @@ int nrt2_prepare(b200s_ctx* c) {
     B200S_TRY(up(s->d_pod_tp, pod_tp.data(), pod_tp.size() * 4));
     B200S_TRY(up(s->d_tc_list, s->tc_list.data(), s->tc_list.size() * 4));
     B200S_TRY(up(s->d_tp_list, s->tp_list.data(), s->tp_list.size() * 4));
+    if (s->use_q) {
+      B200S_TRY(up(s->qkeys, qkeys.data(), qkeys.size() * sizeof(QKey)));
+      B200S_TRY(up(s->rowq_c, rowq_c.data(), rowq_c.size() * sizeof(RowQ)));
+      B200S_TRY(up(s->rowq_p, rowq_p.data(), rowq_p.size() * sizeof(RowQ)));
+    }
     B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources die at return
     s->prep_pods_serial = s->pods_serial;
     s->prep_cfg = cfg;
@@ -970,6 +1145,9 @@ int nrt2_prepare(b200s_ctx* c) {
   }
   B200S_CUDA_TRY(c, s->Tc.ensure(tc_bytes));
   B200S_CUDA_TRY(c, s->Tp.ensure(tp_bytes));
+  if (s->use_q) B200S_CUDA_TRY(c, s->Q.ensure((size_t)s->n_qkeys * S * 4));
+  if (s->use_q)
+    s->note = wide ? "batched, quotient tables, 64-bit Value() ratios" : "batched, quotient tables";
   return 1;
 }
 
@@ -1008,13 +1186,58 @@ void launch_tables(b200s_ctx* c, Nrt2* s) {
     c->launches += 1;
   }
 }
+
+// Least / MostAllocated through the quotient tables: one pass over (key, slot), then both tables from it.
+void launch_tables_q(b200s_ctx* c, Nrt2* s) {
+  const int S = s->Sc + s->Sp;
+  QArgs qa;
+  qa.filt = s->filt.as<int32_t>();
+  qa.capv = s->capv.as<int32_t>();
+  qa.magic = s->magic.as<uint32_t>();
+  qa.keys = s->qkeys.as<QKey>();
+  qa.K = s->n_qkeys;
+  qa.S = S;
+  qa.most = c->nrt_strategy == B200S_NRT_MOST_ALLOCATED;
+  dim3 qgrid((unsigned)(S / 128), (unsigned)((qa.K + QT - 1) / QT));
+  if (s->wide)
+    nrt2_q_kernel<4, 4, true><<<qgrid, 128, 0, c->stream>>>(qa, s->Q.as<uint32_t>());
+  else
+    nrt2_q_kernel<4, 4, false><<<qgrid, 128, 0, c->stream>>>(qa, s->Q.as<uint32_t>());
+  c->launches += 1;
+  TableQArgs a;
+  a.S = S;
+  if (!s->tc_list.empty() && s->Nc > 0) {
+    a.Q = s->Q.as<uint32_t>();
+    a.nzs = s->nzs.as<uint8_t>();
+    a.nrm = s->nrm.as<uint8_t>();
+    a.rows = s->rowq_c.as<RowQ>();
+    a.nrows = (int)s->tc_list.size();
+    a.count = s->Sc;
+    dim3 grid((unsigned)(s->Sc / 128), (unsigned)((a.nrows + RT - 1) / RT));
+    nrt2_tableq_kernel<false><<<grid, 128, 0, c->stream>>>(a, s->Tc.as<uint16_t>());
+    c->launches += 1;
+  }
+  if (!s->tp_list.empty() && s->Np > 0) {
+    a.Q = s->Q.as<uint32_t>() + s->Sc;
+    a.nzs = s->nzs.as<uint8_t>() + s->Sc;
+    a.nrm = s->nrm.as<uint8_t>() + s->Sc;
+    a.rows = s->rowq_p.as<RowQ>();
+    a.nrows = (int)s->tp_list.size();
+    a.count = s->Sp;
+    dim3 grid((unsigned)(s->Sp / 128), (unsigned)((a.nrows + RT - 1) / RT));
+    nrt2_tableq_kernel<true><<<grid, 128, 0, c->stream>>>(a, s->Tp.as<uint8_t>());
+    c->launches += 1;
+  }
+}
 }  // namespace
 
 // Runs the batched path (nrt2_prepare returned 1; outputs ensured by the caller).
 int nrt2_eval(b200s_ctx* c, int dtype) {
   Nrt2* s = nrt2_get(c);
   PluginOut& o = c->out[B200S_PLUGIN_NRT];
-  if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION)
+  if (s->use_q && c->nrt_strategy != B200S_NRT_BALANCED_ALLOCATION)
+    launch_tables_q(c, s);
+  else if (c->nrt_strategy == B200S_NRT_BALANCED_ALLOCATION)
     launch_tables<1, false>(c, s);  // fractions in float64: no 32-bit ratio to widen
   else if (s->wide)
     launch_tables<0, true>(c, s);

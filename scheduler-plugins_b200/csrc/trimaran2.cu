@@ -49,7 +49,14 @@ __device__ __forceinline__ double go_max(double a, double b) {
   return a > b ? a : b;
 }
 
-// math.Exp, Go's portable implementation (src/math/exp.go; FreeBSD e_exp.c)
+// math.Exp, Go's portable implementation (src/math/exp.go, Copyright (c) 2009 The Go Authors, BSD-style licence),
+// which is a simplified version of FreeBSD's lib/msun/src/e_exp.c; algorithm and constants came with this notice:
+//   ====================================================
+//   Copyright (C) 2004 by Sun Microsystems, Inc. All rights reserved.
+//   Permission to use, copy, modify, and distribute this software is freely granted, provided that this notice
+//   is preserved.
+//   ====================================================
+// Restated here (not copied); full upstream notices in NOTICE.md.
 __device__ __forceinline__ double go_exp(double x) {
   const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10,
                Log2e = 1.44269504088896338700e+00, Overflow = 7.09782712893383973096e+02,
@@ -179,7 +186,9 @@ constexpr double MACHEP = 1.11022302462515654042e-16, MAXLOG = 7.097827128933839
 __device__ double gamma_ratio(double a, double b) { return tgamma(a + b) / (tgamma(a) * tgamma(b)); }
 __device__ double lbeta_neg(double a, double b) { return lgamma(a + b) - lgamma(a) - lgamma(b); }
 
-// Cephes incbet pieces (gonum mathext.RegIncBeta): power series, the two continued fractions
+// Cephes incbet pieces (gonum mathext.RegIncBeta): power series, the two continued fractions.  Restated from the
+// published algorithm -- Cephes Math Library Release 2.3, Copyright 1984, 1995 by Stephen L. Moshier; gonum's port
+// Copyright (c) 2016 The Gonum Authors, BSD-style licence.  Full upstream notices in NOTICE.md.
 __device__ double incb_pseries(double a, double b, double x) {
   const double ai = 1.0 / a;
   double u = (1.0 - b) * x, v = u / (a + 1.0);

@@ -60,6 +60,31 @@ def test_batched_wide_value_ratios(eng, engine_mod, strategy):
     assert np.array_equal(gr, wr) and np.array_equal(gf, wf) and np.array_equal(gs, ws)
 
 
+@pytest.mark.parametrize("strategy", [0, 2])  # MostAllocated, LeastAllocated
+def test_batched_quotient_tables_and_per_vector_tables_agree_with_oracle(eng, engine_mod, strategy):
+    """Least / MostAllocated tables are built from per-(request value, cell) quotient tables when the weight sum keeps
+    100 x sum inside a 16-bit lane (<= 655); larger weights keep the per-vector table kernel.  Both forms, ragged
+    row / slot counts, with and without an upstream mask -- against the oracle."""
+    from oracle import pyoracle_nrt
+
+    E = engine_mod
+    seen = set()
+    for seed, P, N, Z, w in ((41, 130, 700, 4, [1, 1, 1, 1]), (42, 97, 391, 2, [5, 3, 2, 1]), (43, 130, 700, 4, [300, 400, 1, 1]),
+                             (44, 64, 129, 4, [160, 160, 160, 175]), (45, 64, 129, 4, [164, 164, 164, 164])):
+        nodes, pods = synth.gen_nrt(seed, N, P, Z=Z)
+        feas = synth.gen_feasible_words(seed, P, N, E.npad_of(N)) if seed % 2 else None
+        gs, gf, gr = run_nrt(eng, E, nodes, pods, strategy, w, feas, path=E.NRT_PATH_BATCHED)
+        assert eng.nrt_last_path() == E.NRT_PATH_BATCHED, eng.nrt_path_note()
+        want_q = max(sum(w[r] for r in range(4) if (int(m) >> r) & 1) for m in np.unique(pods["req_mask"])) <= 655
+        assert ("quotient tables" in eng.nrt_path_note()) == want_q, (seed, eng.nrt_path_note())
+        seen.add(want_q)
+        ws, wf, wr = pyoracle_nrt.nrt_batch(nodes, pods, strategy, w, feas, pitch=eng.Npad)
+        assert np.array_equal(gr, wr), (seed, np.argwhere(gr != wr)[:5])
+        assert np.array_equal(gf, wf), seed
+        assert np.array_equal(gs, ws), (seed, np.argwhere(gs != ws)[:5])
+    assert seen == {True, False}
+
+
 def test_batched_declines_what_it_cannot_encode(eng, engine_mod):
     """Quantities that do not fit the scaled 32-bit encoding, absurd weights, a Guaranteed pod that names a single
     resource under BalancedAllocation (NaN variance) and LeastNUMANodes all keep the direct kernel -- with the
