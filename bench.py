@@ -572,9 +572,13 @@ def main():
             b, keep = eng.make_batch(len(rows), **pod_columns(cfg, dp, pinned_copy(np.ascontiguousarray(feas_local[rows]))))
             batches.append((b, keep, len(rows)))
 
+        # the host prepares chunk i + 1 (request-vector dictionary, staging) while the device evaluates chunk i: uploads
+        # queue without synchronising; the batches' arrays stay alive and unchanged in `batches`
+        eng.config_async_upload(True)
+
         def step(fetch=False):
             for ci, (b, _keep, n) in enumerate(batches):
-                eng._chk(eng.lib.b200s_pods_upload(eng.ctx, C.byref(b)))  # pod columns of the chunk: tiny H2D
+                eng._chk(eng.lib.b200s_pods_upload(eng.ctx, C.byref(b)))  # pod columns + upstream mask of the chunk
                 eng.P = n
                 eng.eval_combined(0b11111, PROFILE_WEIGHTS, k=1, write_total=False)
                 if fetch:

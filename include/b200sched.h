@@ -390,6 +390,11 @@ int b200s_fetch_topk(b200s_ctx* ctx, b200s_topk_entry* out, size_t bytes); /* [P
  * per-plugin matrix; b200s_fetch_total_feasible still works, b200s_fetch_scores of the individual plugins does not.
  * on = 0 keeps the plugin-by-plugin path for every batch size (parity tests, A/B timing).  Default on. */
 int b200s_config_fused_cycle(b200s_ctx* ctx, int on);
+/* on = 1: b200s_pods_upload queues its copies and returns without synchronising the stream, so the host can prepare
+ * the next pod chunk while the device evaluates this one (a 50k-pod queue goes through the engine in chunks).  The
+ * caller then keeps every column buffer of the batch that is larger than 4 MiB unchanged until the next synchronising
+ * call (any b200s_fetch_*, b200s_score_batch, b200s_schedule_*); smaller columns are staged at the call.  Default 0. */
+int b200s_config_async_upload(b200s_ctx* ctx, int on);
 /* The engine-only profile in ONE call with ONE synchronisation: upload the batch's pod columns (HOST pointers),
  * evaluate the weighted combination, copy the [n_pods][k] winners to topk_out (HOST). */
 int b200s_schedule_batch(b200s_ctx* ctx, const b200s_pod_batch* batch, uint32_t plugin_mask,

@@ -336,6 +336,7 @@ void b200s_shutdown(b200s_ctx* c) {
   c->pod_lo_alt.release();
   c->cycle_scratch.release();
   cycle_graph_free(c);
+  c->pods_stage2.release();
   if (c->small_bounce) cudaFreeHost(c->small_bounce);
   c->norm_params_alt.release();
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
@@ -982,13 +983,20 @@ struct PodUpload {
   std::vector<Item> items;
   void add(DevBuf* d, const void* s, size_t bytes) { items.push_back({d, s, bytes}); }
   int flush(b200s_ctx* c) {
-    constexpr size_t kSmall = 64 * 1024, kAlign = 256;
+    // asynchronous uploads stage more themselves: a copy from the caller's pageable memory would wait for the stream
+    const bool dbl = c->async_upload && !c->hold_upload;
+    const size_t kSmall = dbl ? (size_t)4 << 20 : (size_t)64 * 1024;
+    constexpr size_t kAlign = 256;
     size_t total = 0;
     for (auto& it : items)
       if (it.bytes <= kSmall) total += (it.bytes + kAlign - 1) / kAlign * kAlign;
     // held for the cycle graph: the copy is rounded up to 4 KiB so that its size rarely changes between cycles
     const size_t need = c->hold_upload ? (total + 4095) / 4096 * 4096 : total;
-    if (total > 0) {
+    void* stage = nullptr;
+    if (total > 0 && dbl) {
+      B200S_CUDA_TRY(c, c->pods_stage2.acquire(need, &stage));
+      B200S_CUDA_TRY(c, c->pods_arena.ensure(need));
+    } else if (total > 0) {
       if (need > c->pods_stage_cap) {
         if (c->pods_stage) cudaFreeHost(c->pods_stage);
         c->pods_stage = nullptr;
@@ -997,11 +1005,12 @@ struct PodUpload {
         c->pods_stage_cap = need * 2;
       }
       B200S_CUDA_TRY(c, c->pods_arena.ensure(need));
+      stage = c->pods_stage;
     }
     size_t off = 0;
     for (auto& it : items) {
       if (it.bytes <= kSmall) {
-        memcpy(static_cast<char*>(c->pods_stage) + off, it.s, it.bytes);
+        memcpy(static_cast<char*>(stage) + off, it.s, it.bytes);
         it.d->view(static_cast<char*>(c->pods_arena.p) + off);
         off += (it.bytes + kAlign - 1) / kAlign * kAlign;
       } else {
@@ -1012,10 +1021,11 @@ struct PodUpload {
     c->held_bytes = 0;
     if (total > 0 && c->hold_upload) {  // b200s_schedule_batch: the copy is the first node of the cycle graph
       c->held_dst = c->pods_arena.p;
-      c->held_src = c->pods_stage;
+      c->held_src = stage;
       c->held_bytes = need;
     } else if (total > 0) {
-      B200S_CUDA_TRY(c, cudaMemcpyAsync(c->pods_arena.p, c->pods_stage, total, cudaMemcpyHostToDevice, c->stream));
+      B200S_CUDA_TRY(c, cudaMemcpyAsync(c->pods_arena.p, stage, total, cudaMemcpyHostToDevice, c->stream));
+      if (dbl) B200S_CUDA_TRY(c, c->pods_stage2.commit(c->stream));
     }
     return B200S_OK;
   }
@@ -1111,7 +1121,7 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   B200S_TRY(up.flush(c));
   B200S_CUDA_TRY(c, cudaEventRecord(c->ev_inputs, c->stream));  // the batch's columns are queued up to here
   // Inputs may be pinned (truly async copies): the caller may reuse them after we return.
-  if (!c->defer_sync) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (!c->defer_sync && !c->async_upload) B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (auto& o : c->out) o.valid = false;
   c->total_valid = c->topk_valid = c->feas_valid = false;
   c->pods_valid = true;
@@ -1309,6 +1319,13 @@ static int score_batch_chunked(b200s_ctx* c, b200s_plugin plugin, const b200s_po
     B200S_CUDA_TRY(c, cudaEventRecord(c->ev_d2h, c->d2h_stream));
   }
   return rc;
+}
+
+int b200s_config_async_upload(b200s_ctx* c, int on) {
+  if (!c) return B200S_ERR_INVALID;
+  Guard g(c);
+  c->async_upload = on != 0;
+  return B200S_OK;
 }
 
 int b200s_config_fused_cycle(b200s_ctx* c, int on) {

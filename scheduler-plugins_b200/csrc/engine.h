@@ -50,6 +50,48 @@ struct DevBuf {
   }
 };
 
+// Double-buffered pinned staging for host->device uploads that must not synchronise the stream: acquire() hands out the
+// other buffer (waiting only until the copies queued from it two uploads ago have run), commit() marks the copies queued.
+struct PinStage {
+  void* p[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  int cur = 0;
+  cudaError_t acquire(size_t bytes, void** out) {
+    cur ^= 1;
+    cudaError_t e = cudaSuccess;
+    if (used[cur]) e = cudaEventSynchronize(ev[cur]);
+    if (e != cudaSuccess) return e;
+    if (!ev[cur]) e = cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    if (bytes > cap[cur]) {
+      if (p[cur]) cudaFreeHost(p[cur]);
+      p[cur] = nullptr;
+      cap[cur] = 0;
+      e = cudaHostAlloc(&p[cur], bytes + bytes / 4 + 4096, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      cap[cur] = bytes + bytes / 4 + 4096;
+    }
+    *out = p[cur];
+    return cudaSuccess;
+  }
+  cudaError_t commit(cudaStream_t st) {
+    used[cur] = true;
+    return cudaEventRecord(ev[cur], st);
+  }
+  void release() {
+    for (int i = 0; i < 2; ++i) {
+      if (p[i]) cudaFreeHost(p[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      p[i] = nullptr;
+      ev[i] = nullptr;
+      cap[i] = 0;
+      used[i] = false;
+    }
+  }
+};
+
 struct PluginOut {
   DevBuf scores;   // [P][Npad] int64 or u8
   DevBuf feas;     // [P][Npad/64] u64 (own filter AND upstream mask)
@@ -195,6 +237,8 @@ struct b200s_ctx {
   b200s::DevBuf pods_arena;
   void* pods_stage = nullptr;
   size_t pods_stage_cap = 0;
+  bool async_upload = false;    // b200s_config_async_upload: b200s_pods_upload queues and returns
+  b200s::PinStage pods_stage2;  // ... through this double-buffered staging block
   bool has_feasible = false;
   b200s::DevBuf feasible_in;  // [P][Npad/64]
   // eval_combined chains the filters: each plugin's "upstream" set is what the previous filters left

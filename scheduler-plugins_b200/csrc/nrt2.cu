@@ -31,6 +31,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <type_traits>
 
 #include "engine.h"
 
@@ -135,6 +136,7 @@ struct Nrt2 {
   uint64_t prep_gm[4] = {0, 0, 0, 0}, prep_gv[4] = {0, 0, 0, 0};
   bool prep_ok = false;
   DevBuf vecrec, d_pod_vec, d_pod_tc, d_pod_tp, d_tc_list, d_tp_list;
+  PinStage stage;  // pinned staging of the per-batch uploads below
   // quotient-table form of the table kernels (Least / MostAllocated): distinct (resource, request value) keys
   bool use_q = false;
   int n_qkeys = 0;
@@ -147,6 +149,7 @@ struct Nrt2 {
     for (DevBuf* b : {&stats_part, &slot, &list, &tile_n0, &tile_c0, &filt, &capv, &magic, &nzs, &nrm, &vecrec, &d_pod_vec, &d_pod_tc, &d_pod_tp,
                       &d_tc_list, &d_tp_list, &Tc, &Tp, &qkeys, &rowq_c, &rowq_p, &Q})
       b->release();
+    stage.release();
   }
 };
 
@@ -741,7 +744,19 @@ __global__ void __launch_bounds__(TILE, 4) nrt2_expand_kernel(ExpandArgs a, OutT
     m.flags = (uint8_t)((a.flags[p] & 3u) | (a.qos[p] == B200S_QOS_GUARANTEED ? 4u : 0u));
     m.n_init = (uint8_t)n_init;
     m.steps = (uint8_t)steps;
-    m.first = (uint8_t)min(n_init + 1, steps);
+    // containers that see the zones as the snapshot has them: the init containers, the first app container, and every
+    // further app container as long as its predecessors took nothing (a Burstable / BestEffort pod's NUMA-affine
+    // requests are not subtracted, numaresources.go:137-142 -- for most of them the state machine never starts)
+    int first = min(n_init + 1, steps);
+    while (first < steps) {
+      const int32_t u = a.pod_vec[(size_t)p * (C_MAX + 1) + first - 1];
+      if (u >= 0) {
+        const int4 sb = reinterpret_cast<const int4*>(a.vecs + u)[1];
+        if ((sb.x | sb.y | sb.z | sb.w) != 0) break;
+      }
+      ++first;
+    }
+    m.first = (uint8_t)first;
     m.tpoff = (uint32_t)max(a.pod_tp[p], 0) * (uint32_t)a.Sp;
     m.inv_steps = (65536u + (uint32_t)max(steps, 1) - 1u) / (uint32_t)max(steps, 1);
     m.pad = 0;
@@ -774,19 +789,26 @@ __global__ void __launch_bounds__(TILE, 4) nrt2_expand_kernel(ExpandArgs a, OutT
       const int steps = m.steps, first = m.first;
       // every container's table entry at once (independent loads): score in the low byte, zones it fits on the
       // node as the snapshot has it in bits 8..
-      uint32_t e[C_MAX];
-#pragma unroll
-      for (int s = 0; s < C_MAX; ++s) e[s] = s < steps ? (uint32_t)tc[s_tcoff[pp][s]] : 0u;
       // init containers and the FIRST app container see the unmodified zones (init containers do not subtract,
       // :43-55): their verdict is the stored fit mask
       uint32_t sum = 0, ok = 0, fail = 0;
+      auto gather = [&](auto cm) {  // most pods have <= 4 containers: half the predicated work (steps is CTA-uniform)
+        constexpr int CM = decltype(cm)::value;
+        uint32_t e[CM];
 #pragma unroll
-      for (int s = 0; s < C_MAX; ++s) {
-        sum += e[s] & 0xFFu;
-        const bool look = s < first;
-        ok = look ? e[s] >> 8 : ok;
-        fail |= (look && e[s] < 256u) ? 1u << s : 0u;
-      }
+        for (int s = 0; s < CM; ++s) e[s] = s < steps ? (uint32_t)tc[s_tcoff[pp][s]] : 0u;
+#pragma unroll
+        for (int s = 0; s < CM; ++s) {
+          sum += e[s] & 0xFFu;
+          const bool look = s < first;
+          ok = look ? e[s] >> 8 : ok;
+          fail |= (look && e[s] < 256u) ? 1u << s : 0u;
+        }
+      };
+      if (steps <= 4)
+        gather(std::integral_constant<int, 4>());
+      else
+        gather(std::integral_constant<int, C_MAX>());
       uint32_t reason = fail ? s_code[pp][__ffs(fail) - 1] : 0u;
       if (steps > first) {  // further app containers: the first-fit state machine with subtraction (:57-76)
         int32_t zs[Z][R];
@@ -1070,13 +1092,19 @@ int nrt2_prepare(b200s_ctx* c) {
     {
       static const bool q_enabled = []() { const char* e = getenv("B200S_NRT2_Q"); return !(e && e[0] == '0'); }();
       bool ok = q_enabled && c->nrt_strategy != B200S_NRT_BALANCED_ALLOCATION;
-      std::map<std::array<int32_t, 4>, int> index;
+      std::map<std::array<int32_t, 4>, int> index;  // a few hundred keys at most (8192 cap)
+      std::array<int32_t, 4> last_key[4] = {{-1, 0, 0, 0}, {-1, 0, 0, 0}, {-1, 0, 0, 0}, {-1, 0, 0, 0}};
+      int last_id[4] = {0, 0, 0, 0};
       std::vector<std::array<uint16_t, 4>> vec_keys(std::max<size_t>(U, 1));
       for (size_t u = 0; u < U && ok; ++u) {
         const VecRec& o = recs[u];
         if (o.wsum > 655) ok = false;
         for (int r = 0; r < 4 && ok; ++r) {
           const std::array<int32_t, 4> key = {r, o.eff[r], o.rq[r], o.rv[r]};
+          if (key == last_key[r]) {  // consecutive vectors often repeat a value
+            vec_keys[u][r] = (uint16_t)last_id[r];
+            continue;
+          }
           auto it = index.find(key);
           if (it == index.end()) {
             if (qkeys.size() >= 8192) {
@@ -1087,6 +1115,8 @@ int nrt2_prepare(b200s_ctx* c) {
             qkeys.push_back(QKey{o.eff[r], o.rq[r], o.rv[r], r});
           }
           vec_keys[u][r] = (uint16_t)it->second;
+          last_key[r] = key;
+          last_id[r] = it->second;
         }
       }
       if (ok && qkeys.size() * (size_t)(s->Sc + s->Sp) * 4 > ((size_t)1 << 30)) ok = false;
@@ -1120,9 +1150,22 @@ int nrt2_prepare(b200s_ctx* c) {
       const int32_t u = s->pod_vec[p * (C_MAX + 1) + C_MAX];
       if (u >= 0) pod_tp[p] = s->tp_of[(size_t)u];
     }
+    // through a double-buffered pinned block: no stream synchronisation, so the host prepares pod chunk i + 1 while
+    // the device works on chunk i
+    const size_t stage_need = 256 * 12 + recs.size() * sizeof(VecRec) + (s->pod_vec.size() + pod_tc.size() + pod_tp.size() +
+                              s->tc_list.size() + s->tp_list.size()) * 4 + qkeys.size() * sizeof(QKey) +
+                              (rowq_c.size() + rowq_p.size()) * sizeof(RowQ);
+    void* stage_base = nullptr;
+    B200S_CUDA_TRY(c, s->stage.acquire(stage_need, &stage_base));
+    size_t stage_off = 0;
     auto up = [&](DevBuf& d, const void* src, size_t bytes) -> int {
       B200S_CUDA_TRY(c, d.ensure(std::max<size_t>(bytes, 16)));
-      if (bytes) B200S_CUDA_TRY(c, cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+      if (bytes) {
+        char* st = static_cast<char*>(stage_base) + stage_off;
+        memcpy(st, src, bytes);
+        stage_off += (bytes + 255) / 256 * 256;
+        B200S_CUDA_TRY(c, cudaMemcpyAsync(d.p, st, bytes, cudaMemcpyHostToDevice, c->stream));
+      }
       return B200S_OK;
     };
     B200S_TRY(up(s->vecrec, recs.data(), recs.size() * sizeof(VecRec)));
@@ -1136,7 +1179,7 @@ int nrt2_prepare(b200s_ctx* c) {
       B200S_TRY(up(s->rowq_c, rowq_c.data(), rowq_c.size() * sizeof(RowQ)));
       B200S_TRY(up(s->rowq_p, rowq_p.data(), rowq_p.size() * sizeof(RowQ)));
     }
-    B200S_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pageable sources die at return
+    B200S_CUDA_TRY(c, s->stage.commit(c->stream));
     s->prep_pods_serial = s->pods_serial;
     s->prep_cfg = cfg;
     memcpy(s->prep_gm, gm, sizeof(gm));

@@ -45,7 +45,7 @@ EXPORTS = [
     "b200s_device_scores", "b200s_device_feasible", "b200s_eval_combined", "b200s_fetch_topk",
     "b200s_fetch_total", "b200s_fetch_total_feasible", "b200s_score_batch", "b200s_alloc_pinned",
     "b200s_free_pinned", "b200s_npad", "b200s_set_profiling", "b200s_kernel_time", "b200s_debug_div_check",
-    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import", "b200s_config_fused_cycle",
+    "b200s_config_nrt_path", "b200s_nrt_last_path", "b200s_nrt_path_note", "b200s_phase_time", "b200s_comm_peer_export", "b200s_comm_peer_import", "b200s_config_fused_cycle", "b200s_config_async_upload",
     "b200s_schedule_batch", "b200s_schedule_sequence",
 ]
 
@@ -502,6 +502,10 @@ class Engine:
         self._chk(self.lib.b200s_eval_combined(self.ctx, C.c_uint32(plugin_mask), _ptr(w), C.c_int32(k),
                                                C.c_int(1 if write_total else 0)))
         self._k = k
+
+    def config_async_upload(self, on: bool):
+        """pods_upload queues and returns (keep the batch's arrays alive and unchanged until the next fetch)"""
+        self._chk(self.lib.b200s_config_async_upload(self.ctx, C.c_int(1 if on else 0)))
 
     def config_fused_cycle(self, on):
         """False / 0: plugin-by-plugin for every batch size; True / 1: fused cycle, b200s_schedule_batch as one graph

@@ -9,8 +9,8 @@ for f in ('bench_c4',):
     d=json.loads(open(f'gpurun_out/r24/{f}.json').read().strip().splitlines()[-1])
     print(f, d['ms_per_step'], d.get('parity_checked'), d.get('per_plugin_kernel_ms'), d['roofline'])
 PY
-B200S_NRT2_Q=0 timeout 300 python bench.py --config c4 --steps 20 --warmup 3 > $O/bench_c4_noq.json 2> $O/bench_c4_noq.err; python - <<'PY'
+timeout 300 python bench.py --config c5 --steps 2 --warmup 1 > $O/bench_c5.json 2> $O/bench_c5.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r24/bench_c4_noq.json').read().strip().splitlines()[-1])
-print('noq', d['ms_per_step'], d.get('parity_checked'))
+d=json.loads(open('gpurun_out/r24/bench_c5.json').read().strip().splitlines()[-1])
+print('c5', d['ms_per_step'], d.get('parity_checked'), d.get('parity_errors'), d['roofline'].get('per_plugin_kernel_ms'), d['roofline'].get('phase_ms_per_step'))
 PY
