@@ -133,6 +133,77 @@ combine_topk_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words,
   }
 }
 
+// k = 1 without the total matrix and with weights that keep the sum in 32 bits (the usual profile): a pure read
+// stream.  16 nodes per thread and step -- one 16-byte load per plugin matrix, all in flight together -- and a running
+// (score, node) maximum instead of the sorted list; a thread visits its nodes in ascending order, so `>` keeps the
+// lowest node among equals, and the block reduction uses the same (score desc, node asc) order as the general kernel.
+__global__ void __launch_bounds__(256)
+combine_top1_kernel(PluginPtrs pl, const uint64_t* __restrict__ feas, int words, int N, int Npad, int node_off, int chunk,
+                    int P, b200s_topk_entry* __restrict__ out) {
+  const int p = blockIdx.x, t = threadIdx.x;
+  const int n_begin = blockIdx.y * chunk, n_end = min(Npad, n_begin + chunk);
+  int32_t w[B200S_PLUGIN_COUNT];
+#pragma unroll
+  for (int j = 0; j < B200S_PLUGIN_COUNT; ++j) w[j] = j < pl.n ? (int32_t)pl.w[j] : 0;
+  int32_t best = -1, bestn = INT32_MAX;  // sums are >= 0
+  const size_t rowoff = (size_t)p * Npad;
+  const uint16_t* f16 = reinterpret_cast<const uint16_t*>(feas + (size_t)p * words);
+#pragma unroll 2
+  for (int n16 = n_begin + t * 16; n16 < n_end; n16 += 256 * 16) {
+    uint4 v[B200S_PLUGIN_COUNT];
+#pragma unroll
+    for (int j = 0; j < B200S_PLUGIN_COUNT; ++j)
+      v[j] = j < pl.n ? __ldcs(reinterpret_cast<const uint4*>(pl.s[j] + rowoff + n16)) : make_uint4(0, 0, 0, 0);
+    uint32_t fb = f16[n16 >> 4];
+    if (n16 + 16 > N) fb &= N > n16 ? (1u << (N - n16)) - 1u : 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int e = q * 4 + b;
+        int32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < B200S_PLUGIN_COUNT; ++j) {
+          const uint32_t word = q == 0 ? v[j].x : (q == 1 ? v[j].y : (q == 2 ? v[j].z : v[j].w));
+          sum += w[j] * (int32_t)((word >> (8 * b)) & 255u);
+        }
+        const bool take = ((fb >> e) & 1u) && sum > best;
+        best = take ? sum : best;
+        bestn = take ? n16 + e : bestn;
+      }
+    }
+  }
+  int64_t s = best < 0 ? INT64_MIN : (int64_t)best;
+  int32_t n = best < 0 ? INT32_MAX : node_off + bestn;
+  for (int o = 16; o; o >>= 1) {
+    const int64_t os = __shfl_xor_sync(0xffffffffu, s, o);
+    const int32_t on = __shfl_xor_sync(0xffffffffu, n, o);
+    if (better(os, on, s, n)) {
+      s = os;
+      n = on;
+    }
+  }
+  __shared__ int64_t ss[8];
+  __shared__ int32_t sn[8];
+  if ((t & 31) == 0) {
+    ss[t >> 5] = s;
+    sn[t >> 5] = n;
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int i = 1; i < 8; ++i)
+      if (better(ss[i], sn[i], s, n)) {
+        s = ss[i];
+        n = sn[i];
+      }
+    b200s_topk_entry e;
+    e.score = n == INT32_MAX ? 0 : s;
+    e.node = n == INT32_MAX ? -1 : n;
+    e.pad = 0;
+    out[(size_t)blockIdx.y * P + p] = e;
+  }
+}
+
 // Fold the gathered [world][P][k] winners: one thread per pod, k rounds of arg-max.
 __global__ void fold_topk_kernel(const b200s_topk_entry* __restrict__ all, int world, int P, int k,
                                  b200s_topk_entry* __restrict__ out) {
@@ -263,7 +334,18 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
   dim3 grid(P, S);
   {
   KernelTimer kt(c, B200S_PLUGIN_COUNT + B200S_PHASE_COMBINE);  // weighted sum + per-pod top-k + slice fold
-  if (k == 1)
+  bool small_w = true;  // sum_j w_j * 255 stays below 2^31 and no weight is negative
+  {
+    int64_t wsum = 0;
+    for (int j = 0; j < pl.n; ++j) {
+      if (pl.w[j] < 0 || pl.w[j] > (1 << 20)) small_w = false;
+      wsum += pl.w[j] < 0 ? 0 : pl.w[j];
+    }
+    if (wsum * 255 >= ((int64_t)1 << 31)) small_w = false;
+  }
+  if (k == 1 && !tot && small_w)
+    combine_top1_kernel<<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, chunk, P, stage1);
+  else if (k == 1)
     combine_topk_kernel<1><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);
   else if (k <= 4)
     combine_topk_kernel<4><<<grid, 256, 0, c->stream>>>(pl, c->total_feas.as<uint64_t>(), words, N, Npad, c->node_off, k, chunk, P, tot, stage1);

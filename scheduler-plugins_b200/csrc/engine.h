@@ -237,6 +237,7 @@ struct b200s_ctx {
   b200s::DevBuf pods_arena;
   void* pods_stage = nullptr;
   size_t pods_stage_cap = 0;
+  bool netoh_attr_set = false;  // netoh_fast4_kernel's dynamic shared-memory limit raised on this device
   bool async_upload = false;    // b200s_config_async_upload: b200s_pods_upload queues and returns
   b200s::PinStage pods_stage2;  // ... through this double-buffered staging block
   bool has_feasible = false;

@@ -313,6 +313,140 @@ netoh_fast_kernel(Topo t, const int32_t* __restrict__ pair_id, int NQ, const int
   }
 }
 
+// The same two passes with the pods' pair tables staged in shared memory and FOUR consecutive nodes per thread: the
+// table lookups leave L2, the per-eval byte stores become one 32-bit store per thread (reason codes, u8 scores) or two
+// 16-byte stores (int64 scores), the feasibility words are assembled nibble by nibble.  PASS 2 stages the NORMALISED
+// score of every pair instead of its cost (the normalisation depends on (pod, cost) only).  Needs PT x NQ x 12 bytes of
+// shared memory; larger label-pair dictionaries keep netoh_fast_kernel.
+template <int PASS, class OutT, int PT>
+__global__ void __launch_bounds__(256)
+netoh_fast4_kernel(Topo t, const int32_t* __restrict__ pair_id, int NQ, const int64_t* __restrict__ pair_cost,
+                   const uint32_t* __restrict__ pair_sv, int node_off, const uint8_t* __restrict__ equal,
+                   const int32_t* __restrict__ dep_off, const b200s_netoh_dep* __restrict__ deps,
+                   const uint16_t* __restrict__ region, const uint16_t* __restrict__ zone,
+                   const uint64_t* __restrict__ upstream, int words, int N, int Npad, int P, bool apply_filter,
+                   uint64_t* __restrict__ feas, uint8_t* __restrict__ reasons, int64_t* __restrict__ lo,
+                   int64_t* __restrict__ hi, const NormParam* __restrict__ params, OutT* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  int64_t* s_val = reinterpret_cast<int64_t*>(dyn);                        // [PT][NQ] cost (PASS 1) / normalised score (PASS 2)
+  uint32_t* s_sv = reinterpret_cast<uint32_t*>(dyn + (size_t)PT * NQ * 8);  // [PT][NQ] satisfied | violated << 16 (PASS 1)
+  __shared__ uint32_t bm[PT][32];  // hosted-node bitmap of this CTA's 1024 nodes, per pod of the tile
+  __shared__ long long s_lo[PT], s_hi[PT];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ncta = blockIdx.x * 1024;
+  const int p0 = blockIdx.y * PT, pend = min(p0 + PT, P);
+  for (int i = tid; i < PT * 32; i += 256) bm[i / 32][i % 32] = 0;
+  if (PASS == 1)
+    for (int i = tid; i < PT; i += 256) {
+      s_lo[i] = INT64_MAX;
+      s_hi[i] = INT64_MIN;
+    }
+  for (int i = tid; i < (pend - p0) * NQ; i += 256) {
+    const int pp = i / NQ;
+    const size_t k = (size_t)p0 * NQ + i;
+    const int64_t cost = pair_cost[k];
+    if (PASS == 1) {
+      s_val[i] = cost;
+      s_sv[i] = pair_sv[k];
+    } else {
+      s_val[i] = netoh_norm_one(params[p0 + pp], cost);
+    }
+  }
+  __syncthreads();
+  for (int p = p0; p < pend; ++p) {
+    if (equal[p]) continue;
+    const int d0 = dep_off[p], d1 = dep_off[p + 1];
+    for (int i = d0 + tid; i < d1; i += 256) {
+      const int local = deps[i].host_node - node_off - ncta;
+      if (local >= 0 && local < 1024) atomicOr(&bm[p - p0][local >> 5], 1u << (local & 31));
+    }
+  }
+  __syncthreads();
+  const int n4 = ncta + tid * 4;
+  const bool active = n4 < Npad;  // Npad is a multiple of 128: uniform over the warp
+  int q[4] = {0, 0, 0, 0};
+  if (active) {
+    const int4 qq = *reinterpret_cast<const int4*>(pair_id + n4);
+    q[0] = qq.x, q[1] = qq.y, q[2] = qq.z, q[3] = qq.w;
+  }
+  uint8_t* feas8 = reinterpret_cast<uint8_t*>(feas);
+  const size_t row_bytes = (size_t)words * 8;
+  for (int p = p0; p < pend && active; ++p) {
+    const int pp = p - p0;
+    const bool eq = equal[p] != 0;
+    const uint32_t hb = eq ? 0u : (bm[pp][tid >> 3] >> ((tid & 7) * 4)) & 15u;
+    int64_t val[4];
+    uint32_t sv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      val[e] = eq ? (PASS == 1 ? 0 : s_val[pp * NQ + q[e]]) : s_val[pp * NQ + q[e]];
+      sv[e] = (PASS == 1 && !eq) ? s_sv[pp * NQ + q[e]] : 0u;
+    }
+    if (hb) {  // a dependency is hosted on one of these nodes: evaluate it directly
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!((hb >> e) & 1u) || n4 + e >= N) continue;
+        int64_t s1 = 0, w1 = 0, c1 = 0;
+        eval_node(t, node_off + n4 + e, region[n4 + e], zone[n4 + e], deps + dep_off[p], dep_off[p + 1] - dep_off[p], s1, w1, c1);
+        val[e] = PASS == 1 ? c1 : netoh_norm_one(params[p], c1);
+        sv[e] = (uint32_t)s1 | ((uint32_t)w1 << 16);
+      }
+    }
+    if (PASS == 1) {
+      const uint32_t up = upstream ? (uint32_t)(upstream[(size_t)p * words + (n4 >> 6)] >> (n4 & 63)) & 15u : 15u;
+      uint32_t nib = 0, r4 = 0;
+      int64_t mn = INT64_MAX, mx = INT64_MIN;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool v = n4 + e < N;
+        const bool pass = v && (eq || !((sv[e] >> 16) > (sv[e] & 0xffffu)));  // networkoverhead.go:349-357
+        const bool f = (apply_filter ? pass : v) && ((up >> e) & 1u);
+        nib |= (f ? 1u : 0u) << e;
+        const uint32_t code = !v ? 0u : (!pass ? (uint32_t)B200S_REASON_NETOH_VIOLATED : (f ? (uint32_t)B200S_REASON_OK : (uint32_t)B200S_REASON_UPSTREAM));
+        r4 |= code << (8 * e);
+        mn = f && val[e] < mn ? val[e] : mn;
+        mx = f && val[e] > mx ? val[e] : mx;
+      }
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, nib, 1);
+      if (!(lane & 1)) feas8[(size_t)p * row_bytes + (n4 >> 3)] = (uint8_t)(nib | (other << 4));
+      *reinterpret_cast<uint32_t*>(reasons + (size_t)p * Npad + n4) = r4;
+      if (__any_sync(0xffffffffu, nib != 0)) {
+        for (int o = 16; o; o >>= 1) {
+          const int64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+          mn = a < mn ? a : mn;
+          mx = b > mx ? b : mx;
+        }
+        if (lane == 0) {
+          atomicMin(&s_lo[pp], (long long)mn);
+          atomicMax(&s_hi[pp], (long long)mx);
+        }
+      }
+    } else {
+      const uint32_t fn = ((uint32_t)feas8[(size_t)p * row_bytes + (n4 >> 3)] >> (n4 & 4)) & 15u;
+      int64_t o4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o4[e] = ((fn >> e) & 1u) ? val[e] : 0;
+      OutT* orow = out + (size_t)p * Npad + n4;
+      if constexpr (sizeof(OutT) == 1) {
+        st_stream_u32(orow, ((uint32_t)o4[0] & 255u) | (((uint32_t)o4[1] & 255u) << 8) | (((uint32_t)o4[2] & 255u) << 16) |
+                                (((uint32_t)o4[3] & 255u) << 24));
+      } else {
+        st_stream_v2(reinterpret_cast<int64_t*>(orow), o4[0], o4[1]);
+        st_stream_v2(reinterpret_cast<int64_t*>(orow) + 2, o4[2], o4[3]);
+      }
+    }
+  }
+  if (PASS == 1) {
+    __syncthreads();
+    for (int i = tid; i < pend - p0; i += 256) {
+      if (s_lo[i] != INT64_MAX || s_hi[i] != INT64_MIN) {
+        atomicMin(reinterpret_cast<long long*>(lo) + p0 + i, s_lo[i]);
+        atomicMax(reinterpret_cast<long long*>(hi) + p0 + i, s_hi[i]);
+      }
+    }
+  }
+}
+
 int netoh_eval_fast(b200s_ctx* c, int dtype) {
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64, NQ = c->netoh_NQ;
   PluginOut& o = c->out[B200S_PLUGIN_NETWORK_OVERHEAD];
@@ -332,7 +466,20 @@ int netoh_eval_fast(b200s_ctx* c, int dtype) {
   c->launches += 2;
   B200S_CUDA_TRY(c, cudaGetLastError());
   constexpr int PT = 32;
+  // pair tables in shared memory + 4 nodes per thread when they fit (two CTAs per SM)
+  const size_t dyn = (size_t)PT * NQ * 12;
+  static const bool fast4_enabled = []() { const char* e = getenv("B200S_NETOH_FAST4"); return !(e && e[0] == '0'); }();
+  const bool fast4 = fast4_enabled && dyn <= 96 * 1024;
+  if (fast4) {
+    if (!c->netoh_attr_set) {  // per device
+      B200S_CUDA_TRY(c, cudaFuncSetAttribute(netoh_fast4_kernel<1, uint8_t, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      B200S_CUDA_TRY(c, cudaFuncSetAttribute(netoh_fast4_kernel<2, uint8_t, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      B200S_CUDA_TRY(c, cudaFuncSetAttribute(netoh_fast4_kernel<2, int64_t, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      c->netoh_attr_set = true;
+    }
+  }
   dim3 grid((Npad + 511) / 512, (P + PT - 1) / PT);
+  dim3 grid4((Npad + 1023) / 1024, (P + PT - 1) / PT);
 #define NETOH_FAST_ARGS(outp)                                                                                          \
   t, c->netoh_pair_id.as<int32_t>(), NQ, c->netoh_pair_cost.as<int64_t>(), c->netoh_pair_sv.as<uint32_t>(), c->node_off, \
       c->netoh_equal.as<uint8_t>(), c->netoh_dep_off.as<int32_t>(), c->netoh_deps.as<b200s_netoh_dep>(),                 \
@@ -341,14 +488,21 @@ int netoh_eval_fast(b200s_ctx* c, int dtype) {
       c->norm_params.as<NormParam>(), outp
   {
     KernelTimer kt(c, B200S_PLUGIN_NETWORK_OVERHEAD);
-    netoh_fast_kernel<1, uint8_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS((uint8_t*)nullptr));
+    if (fast4)
+      netoh_fast4_kernel<1, uint8_t, PT><<<grid4, 256, dyn, c->stream>>>(NETOH_FAST_ARGS((uint8_t*)nullptr));
+    else
+      netoh_fast_kernel<1, uint8_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS((uint8_t*)nullptr));
     c->launches++;
     B200S_CUDA_TRY(c, cudaGetLastError());
   }
   B200S_TRY(comm_allreduce_minmax(c, lo_buf, hi_buf, P));
   netoh_params_kernel<<<(P + 255) / 256, 256, 0, c->stream>>>(lo_buf, hi_buf, P, c->norm_params.as<NormParam>());
   c->launches++;
-  if (dtype == B200S_OUT_I64)
+  if (fast4 && dtype == B200S_OUT_I64)
+    netoh_fast4_kernel<2, int64_t, PT><<<grid4, 256, dyn, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<int64_t>()));
+  else if (fast4)
+    netoh_fast4_kernel<2, uint8_t, PT><<<grid4, 256, dyn, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<uint8_t>()));
+  else if (dtype == B200S_OUT_I64)
     netoh_fast_kernel<2, int64_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<int64_t>()));
   else
     netoh_fast_kernel<2, uint8_t, PT><<<grid, 256, 0, c->stream>>>(NETOH_FAST_ARGS(o.scores.as<uint8_t>()));

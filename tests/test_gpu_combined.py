@@ -89,6 +89,18 @@ def test_combined_matches_oracle(eng, engine_mod, mask, k):
         got = [(int(e["score"]), int(e["node"])) for e in got_topk[p]]
         assert got == want_topk[p], (p, got, want_topk[p])
     assert any(r[0][1] >= 0 for r in want_topk)
+    # winners only (no total matrix): k = 1 with small weights is the 16-nodes-per-thread read-stream kernel, weights
+    # beyond 32-bit sums keep the general one -- same winners either way
+    eng.eval_combined(mask, weights, k=k, write_total=False)
+    got_topk = eng.fetch_topk()
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in got_topk[p]] == want_topk[p], p
+    big = [w << 21 for w in weights]
+    _, _, want_big = oracle_combined(d, P, N, eng.Npad, feas, big, k, mask)
+    eng.eval_combined(mask, big, k=k, write_total=False)
+    got_topk = eng.fetch_topk()
+    for p in range(P):
+        assert [(int(e["score"]), int(e["node"])) for e in got_topk[p]] == want_big[p], p
 
 
 def test_combined_without_total_matrix_and_no_upstream_mask(eng, engine_mod):

@@ -309,6 +309,25 @@ def test_network_overhead_matches_oracle(eng, engine_mod, oracle, P, N, masked):
     assert np.array_equal(eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD, E.OUT_U8).astype(np.int64), ws)
 
 
+@pytest.mark.parametrize("regions,zones_per_region", [(2, 3), (20, 16)])
+def test_network_overhead_small_and_large_pair_dictionaries(eng, engine_mod, oracle, regions, zones_per_region):
+    """The pair tables of a pod tile live in shared memory when the (region, zone) dictionary is small (4 nodes per
+    thread, packed stores); 320 zones exceed it and keep the global-table kernel.  Ragged N, hosted nodes, masks."""
+    E = engine_mod
+    P, N = 70, 5000 + 37
+    net = synth.gen_netoh(synth.BASE_SEED + 11, N, P, n_regions=regions, zones_per_region=zones_per_region)
+    netoh_setup(eng, E, net, N)
+    feas = synth.gen_feasible_words(synth.BASE_SEED + 11, P, N, eng.Npad)
+    eng.pods_upload(P, feasible=feas, netoh=net)
+    ws, wf, wr = oracle.netoh_batch(net["zone_cost"], net["region_cost"], net["region_all"], net["zone_all"],
+                                    net["score_equally"], net["dep_offset"], net["deps"], feas, pitch=eng.Npad)
+    for dt in (E.OUT_I64, E.OUT_U8):
+        eng.eval(E.PLUGIN_NETWORK_OVERHEAD, dt)
+        assert np.array_equal(eng.fetch_feasible(E.PLUGIN_NETWORK_OVERHEAD), wf)
+        assert np.array_equal(eng.fetch_reasons(E.PLUGIN_NETWORK_OVERHEAD), wr)
+        assert np.array_equal(eng.fetch_scores(E.PLUGIN_NETWORK_OVERHEAD, dt).astype(np.int64), ws)
+
+
 def test_network_overhead_generic_normalize(eng, engine_mod, oracle):
     """Huge costs: the float64 NormalizeScore formula verbatim (networkoverhead.go:406-410)."""
     E = engine_mod
