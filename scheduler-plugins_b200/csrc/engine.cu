@@ -337,6 +337,10 @@ void b200s_shutdown(b200s_ctx* c) {
   c->cycle_scratch.release();
   cycle_graph_free(c);
   c->pods_stage2.release();
+  c->feasible_alt.release();
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  for (cudaEvent_t e : {c->ev_mark[0], c->ev_mark[1], c->ev_copied})
+    if (e) cudaEventDestroy(e);
   if (c->small_bounce) cudaFreeHost(c->small_bounce);
   c->norm_params_alt.release();
   DevBuf* bufs[] = {&c->alloc_cols,      &c->alloc_raw,        &c->alloc_sorted_raw, &c->alloc_order,
@@ -1013,6 +1017,14 @@ struct PodUpload {
         memcpy(static_cast<char*>(stage) + off, it.s, it.bytes);
         it.d->view(static_cast<char*>(c->pods_arena.p) + off);
         off += (it.bytes + kAlign - 1) / kAlign * kAlign;
+      } else if (dbl && it.d == &c->feasible_in && c->h2d_stream) {
+        // the buffer the batch before the previous one used: free once everything queued before the previous upload ran
+        std::swap(c->feasible_in, c->feasible_alt);
+        B200S_CUDA_TRY(c, c->feasible_in.ensure(it.bytes));
+        B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_mark[(c->upload_seq - 1) & 1], 0));
+        B200S_CUDA_TRY(c, cudaMemcpyAsync(c->feasible_in.p, it.s, it.bytes, cudaMemcpyHostToDevice, c->h2d_stream));
+        B200S_CUDA_TRY(c, cudaEventRecord(c->ev_copied, c->h2d_stream));
+        B200S_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
       } else {
         B200S_CUDA_TRY(c, it.d->ensure(it.bytes));
         B200S_CUDA_TRY(c, cudaMemcpyAsync(it.d->p, it.s, it.bytes, cudaMemcpyHostToDevice, c->stream));
@@ -1039,6 +1051,15 @@ static int pods_upload_locked(b200s_ctx* c, const b200s_pod_batch* b) {
   int P = b->n_pods;
   c->pods_valid = false;
   c->P = P;
+  if (c->async_upload && !c->hold_upload) {  // marks "everything queued for the earlier batches" on the engine stream
+    if (!c->h2d_stream) {
+      B200S_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&c->ev_mark[0], &c->ev_mark[1], &c->ev_copied})
+        B200S_CUDA_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    c->upload_seq++;
+    B200S_CUDA_TRY(c, cudaEventRecord(c->ev_mark[c->upload_seq & 1], c->stream));
+  }
   size_t words = (size_t)(c->Npad / 64);
   PodUpload up;
   c->has_feasible = b->feasible != nullptr;

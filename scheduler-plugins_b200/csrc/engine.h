@@ -240,6 +240,12 @@ struct b200s_ctx {
   bool netoh_attr_set = false;  // netoh_fast4_kernel's dynamic shared-memory limit raised on this device
   bool async_upload = false;    // b200s_config_async_upload: b200s_pods_upload queues and returns
   b200s::PinStage pods_stage2;  // ... through this double-buffered staging block
+  // ... and the upstream mask (the one large column) travels on its own stream into the buffer the batch before the
+  // previous one used, so that the copy of chunk i + 1 overlaps the kernels of chunk i
+  cudaStream_t h2d_stream = nullptr;
+  cudaEvent_t ev_mark[2] = {nullptr, nullptr}, ev_copied = nullptr;
+  uint64_t upload_seq = 0;
+  b200s::DevBuf feasible_alt;
   bool has_feasible = false;
   b200s::DevBuf feasible_in;  // [P][Npad/64]
   // eval_combined chains the filters: each plugin's "upstream" set is what the previous filters left

@@ -45,6 +45,41 @@ def test_allocatable_matches_oracle(eng, engine_mod, oracle, P, N, mode, masked)
     assert np.array_equal(got8.astype(np.int64), want)
 
 
+def test_async_upload_of_consecutive_pod_chunks(eng, engine_mod, oracle):
+    """b200s_config_async_upload: pod chunks are queued back to back without synchronising -- small columns through the
+    double-buffered staging block, the upstream mask (> 4 MiB here) on its own stream into alternating buffers.  Every
+    chunk must be evaluated with ITS mask (NormalizeScore depends on it)."""
+    E = engine_mod
+    P, N = 640, 60_000  # 640 x 60 032 / 8 = 4.8 MB of mask per chunk
+    seed = synth.BASE_SEED + 3
+    nodes = synth.gen_nodes(seed, N)
+    cols = setup_alloc(eng, E, nodes, 1)
+    masks = [synth.gen_feasible_words(seed + i, P, N, eng.Npad) for i in range(5)]
+    pinned = []
+    for m in masks:
+        buf = eng.pinned(m.nbytes)
+        v = buf.view(np.uint64, m.shape)
+        v[:] = m
+        pinned.append((buf, v))
+    eng.config_async_upload(True)
+    try:
+        outs = []
+        for i, (_, v) in enumerate(pinned):
+            eng.pods_upload(P, feasible=v)
+            eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+            if i % 2 == 1 or i == len(pinned) - 1:  # chunks 0 and 2 are overtaken by the next upload before any fetch
+                outs.append((i, eng.fetch_scores(E.PLUGIN_ALLOCATABLE, E.OUT_U8)))
+        for i, got in outs:
+            want = oracle.alloc_batch(cols, W_DEFAULT, 1, P, masks[i], pitch=eng.Npad)
+            assert np.array_equal(got.astype(np.int64), want), i
+    finally:
+        eng.config_async_upload(False)
+    eng.pods_upload(P, feasible=masks[0])
+    eng.eval(E.PLUGIN_ALLOCATABLE, E.OUT_U8)
+    want = oracle.alloc_batch(cols, W_DEFAULT, 1, P, masks[0], pitch=eng.Npad)
+    assert np.array_equal(eng.fetch_scores(E.PLUGIN_ALLOCATABLE, E.OUT_U8).astype(np.int64), want)
+
+
 def test_allocatable_golden_through_cuda(eng, engine_mod):
     """The reference's own table (allocatable_test.go:114-221) through the CUDA path."""
     import json

@@ -1,7 +1,7 @@
 # pinned double-buffered staging (no per-chunk stream syncs) + async pod upload: parity + c5 / c4 timing
 set -u
 O=gpurun_out/r25; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py tests/test_gpu_combined.py tests/test_gpu_fuzz.py tests/test_gpu_snapshot_patch.py tests/test_gpu_integration_scenarios.py -q -m gpu > $O/tests.log 2>&1; echo "pytest rc=$?" >> $O/tests.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_combined.py tests/test_gpu_full_size.py -q -m gpu > $O/tests.log 2>&1; echo "pytest rc=$?" >> $O/tests.log
 tail -5 $O/tests.log
 for cfg in c5; do
 timeout 300 python bench.py --config $cfg --steps 3 --warmup 1 > $O/bench_$cfg.json 2> $O/bench_$cfg.err
