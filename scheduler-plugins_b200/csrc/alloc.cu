@@ -52,9 +52,14 @@ __device__ __forceinline__ NormParam make_norm_param(int64_t lo, int64_t hi);
 
 // One warp per pod.  lo = raw of the first feasible node in ascending sorted order, hi = last.
 // Single-GPU: also emits the pod's NormParam (no all-reduce in between, one launch less per step).
+// The scan from each end is bounded: behind a chain of filters a pod's feasible set can be sparse or EMPTY (a
+// Guaranteed pod that fits no NUMA zone anywhere), and walking the whole sorted order with dependent gathers costs
+// milliseconds per pod.  After kScanRounds x 32 entries the warp switches to one coalesced pass over the pod's
+// feasibility words and takes the exact min / max of the raw scores of the set bits -- the same two values.
+constexpr int kScanRounds = 16;
 __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, const int32_t* __restrict__ order,
-                                    const uint64_t* __restrict__ feasible, int words, int N, int P,
-                                    int64_t* __restrict__ lo, int64_t* __restrict__ hi,
+                                    const int64_t* __restrict__ raw, const uint64_t* __restrict__ feasible, int words, int N,
+                                    int P, int64_t* __restrict__ lo, int64_t* __restrict__ hi,
                                     NormParam* __restrict__ params_out) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -66,7 +71,9 @@ __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, cons
       vlo = sorted_raw[0];
       vhi = sorted_raw[N - 1];
     } else {
-      for (int base = 0; base < N; base += 32) {
+      bool found_lo = false, found_hi = false;
+      const int span = min(N, 32 * kScanRounds);
+      for (int base = 0; base < span; base += 32) {
         int i = base + lane;
         bool f = false;
         if (i < N) {
@@ -76,11 +83,12 @@ __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, cons
         unsigned b = __ballot_sync(0xffffffffu, f);
         if (b) {
           vlo = sorted_raw[base + __ffs(b) - 1];
+          found_lo = true;
           break;
         }
       }
-      {
-        for (int top = N - 1; top >= 0; top -= 32) {
+      if (found_lo) {  // an empty or sparse row goes straight to the full pass
+        for (int top = N - 1; top > N - 1 - span; top -= 32) {
           int i = top - lane;
           bool f = false;
           if (i >= 0) {
@@ -90,9 +98,32 @@ __global__ void alloc_minmax_kernel(const int64_t* __restrict__ sorted_raw, cons
           unsigned b = __ballot_sync(0xffffffffu, f);
           if (b) {
             vhi = sorted_raw[top - (__ffs(b) - 1)];
+            found_hi = true;
             break;
           }
         }
+      }
+      if (!found_lo || !found_hi) {
+        int64_t mn = INT64_MAX, mx = -INT64_MAX;
+        for (int w = lane; w < words; w += 32) {
+          uint64_t bits = row[w];
+          while (bits) {
+            const int n = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (n < N) {
+              const int64_t r = raw[n];
+              mn = r < mn ? r : mn;
+              mx = r > mx ? r : mx;
+            }
+          }
+        }
+        for (int o = 16; o; o >>= 1) {
+          const int64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+          mn = a < mn ? a : mn;
+          mx = b > mx ? b : mx;
+        }
+        vlo = mn;
+        vhi = mx;
       }
     }
   }
@@ -364,8 +395,8 @@ int alloc_eval(b200s_ctx* c, int dtype) {
     const int threads = 128, warps_per_block = threads / 32;
     int64_t* lo = c->pod_lo.as<int64_t>() + 2 * (size_t)a;
     alloc_minmax_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads, 0, c->stream>>>(
-        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas ? feas + (size_t)a * words : nullptr, words, N,
-        n, lo, lo + n, sharded ? nullptr : c->norm_params.as<NormParam>() + a);
+        c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), c->alloc_raw.as<int64_t>(),
+        feas ? feas + (size_t)a * words : nullptr, words, N, n, lo, lo + n, sharded ? nullptr : c->norm_params.as<NormParam>() + a);
     c->launches++;
   };
   auto launch_norm = [&](int a, int n) {
@@ -415,7 +446,8 @@ int alloc_eval(b200s_ctx* c, int dtype) {
     {
       const int threads = 128, warps_per_block = threads / 32;
       alloc_minmax_kernel<<<(P + warps_per_block - 1) / warps_per_block, threads, 0, cs>>>(
-          c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), feas, words, N, P, lo, lo + P, nullptr);
+          c->alloc_sorted_raw.as<int64_t>(), c->alloc_order.as<int32_t>(), c->alloc_raw.as<int64_t>(), feas, words, N, P, lo,
+          lo + P, nullptr);
       c->launches++;
     }
     B200S_TRY(comm_allreduce_minmax_on(c, cs, lo, lo + P, P));

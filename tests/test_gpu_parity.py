@@ -125,6 +125,39 @@ def test_allocatable_edge_feasibility(eng, engine_mod, oracle):
     assert not got[0].any() and not got[2].any()
 
 
+def test_allocatable_sparse_and_empty_feasible_sets_far_from_the_ends(eng, engine_mod, oracle):
+    """Behind a chain of filters a pod's feasible set can be empty or a handful of nodes in the MIDDLE of the sorted
+    order: the bounded scan from the two ends (512 entries each) gives up and the warp takes the exact min / max over
+    the feasibility words instead -- same NormalizeScore."""
+    E = engine_mod
+    N, P = 9000, 12
+    nodes = synth.gen_nodes(17, N)
+    rng = np.random.default_rng(17)
+    for mode in (0, 1):
+        cols = setup_alloc(eng, E, nodes, mode)
+        raw_order = np.argsort(nodes["alloc_cpu_milli"].astype(np.float64) * (1 << 20) + nodes["alloc_mem_bytes"], kind="stable")
+        feas_b = np.zeros((P, N), dtype=bool)
+        feas_b[1, raw_order[N // 2]] = True                      # one node in the middle
+        feas_b[2, raw_order[N // 2 - 40:N // 2 + 40:7]] = True   # a few around the middle
+        feas_b[3, raw_order[600]] = feas_b[3, raw_order[N - 700]] = True   # just beyond both scan windows
+        feas_b[4, raw_order[3]] = feas_b[4, raw_order[N // 3]] = True      # low end found by the scan, high end not
+        feas_b[5, raw_order[N // 3]] = feas_b[5, raw_order[N - 2]] = True  # the other way round
+        feas_b[6] = rng.random(N) < 0.002
+        feas_b[7] = True
+        feas_b[8, raw_order[511]] = feas_b[8, raw_order[N - 512]] = True   # last entries of the scan windows
+        feas_b[9, raw_order[512]] = feas_b[9, raw_order[N - 513]] = True   # first entries beyond them
+        feas_b[10] = rng.random(N) < 0.5
+        # pods 0 and 11: nothing feasible
+        feas = E.pack_bits(feas_b, eng.Npad)
+        eng.pods_upload(P, feasible=feas)
+        for dt in (E.OUT_I64, E.OUT_U8):
+            eng.eval(E.PLUGIN_ALLOCATABLE, dt)
+            got = eng.fetch_scores(E.PLUGIN_ALLOCATABLE, dt).astype(np.int64)
+            want = oracle.alloc_batch(cols, W_DEFAULT, mode, P, feas, pitch=eng.Npad)
+            assert np.array_equal(got, want), (mode, dt, np.argwhere(got != want)[:5])
+        assert not got[0].any() and not got[11].any()
+
+
 def test_allocatable_generic_int64_path(eng, engine_mod, oracle):
     """Huge weights / wrapping ranges take the exact generic path (Go wraps, allocatable.go:126,163)."""
     E = engine_mod
