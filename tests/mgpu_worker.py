@@ -67,6 +67,19 @@ def main():
     got_topk = eng.fetch_topk()
     for p in range(P):
         assert [(int(e["score"]), int(e["node"])) for e in got_topk[p]] == want_topk[p], (rank, p)
+    # --- chunked b200s_score_batch on UNEVEN shards (this N gives the ranks different Npad): the batch is large enough
+    # for the pod-chunk pipeline, every chunk is one min/max exchange, so chunked-or-not and the chunk count must come
+    # from rank-invariant values -- ranks that disagreed would mismatch the exchanges (hang or wrong normalisation)
+    P2 = 13_000
+    feas2_full = synth.gen_feasible_words(seed + 1, P2, N, E.npad_of(N))
+    feas2 = E.pack_bits(E.unpack_bits(feas2_full, N)[:, off:off + cnt], E.npad_of(cnt))
+    batch2, _keep2 = eng.make_batch(P2, feasible=feas2)
+    out2 = np.empty((P2, eng.Npad), dtype=np.int64)
+    assert P2 * E.npad_of(-(-N // world)) * 8 >= (96 << 20)  # the chunked path (engine.cu: >= 2 x 48 MiB of scores)
+    eng.score_batch(E.PLUGIN_ALLOCATABLE, batch2, E.OUT_I64, out2)
+    want2 = orc.alloc_batch([d["nodes"]["alloc_cpu_milli"], d["nodes"]["alloc_mem_bytes"]], [1 << 20, 1], 1, P2, feas2_full,
+                            pitch=E.npad_of(N))
+    assert np.array_equal(out2[:, :cnt], want2[:, off:off + cnt]), f"rank {rank}: chunked sharded score_batch differs"
     # --- Peaks: NormalizeScore's min/max over the feasible set crosses the shards (one all-reduce between the passes)
     nodes = d["nodes"]
     tri, t2 = synth.gen_trimaran(seed, nodes), synth.gen_trimaran2(seed, nodes, P)
