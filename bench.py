@@ -560,7 +560,7 @@ def main():
     feas_pin = pinned_copy(feas_local) if feas_local is not None else None
     plugins = {"c2": [E.PLUGIN_ALLOCATABLE], "c3": [E.PLUGIN_TLP, E.PLUGIN_LVRB], "c4": [E.PLUGIN_NRT],
                "c5": [E.PLUGIN_NRT, E.PLUGIN_NETWORK_OVERHEAD, E.PLUGIN_ALLOCATABLE, E.PLUGIN_TLP, E.PLUGIN_LVRB]}[cfg]
-    dom = {"c2": (E.PLUGIN_ALLOCATABLE, "alloc_norm_kernel<int64>"), "c3": (E.PLUGIN_LVRB, "lvrb_kernel<int64>"),
+    dom = {"c2": (E.PLUGIN_ALLOCATABLE, "alloc_norm_kernel<int64>"), "c3": (E.PLUGIN_LVRB, "lvrb_kernel<u8> over the distinct (cpu, mem) keys + expand_rows_kernel<int64>"),
            "c4": (E.PLUGIN_NRT, "nrt2_q_kernel + nrt2_tableq_kernel x2 + nrt2_expand_kernel<int64>"),
            "c5": (E.PLUGIN_NRT, "nrt2_q_kernel + nrt2_tableq_kernel x2 + nrt2_expand_kernel<u8>")}[cfg]
     topk_rows = {}  # c5: chunk index -> fetched [chunk][1] winners of the last step
