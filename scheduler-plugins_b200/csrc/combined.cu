@@ -261,7 +261,7 @@ int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, in
   const int P = c->P, N = c->N, Npad = c->Npad, words = Npad / 64;
   c->total_valid = c->topk_valid = c->feas_valid = false;
   c->mask_override = nullptr;
-  if (cycle_applies(c, mask, k, write_total)) {  // a handful of pods on one GPU: the whole cycle as ONE kernel
+  if (cycle_applies(c, mask, k, write_total)) {  // a handful of pods on one GPU: the whole cycle in two launches (cycle.cu)
     for (auto& o : c->out) o.valid = false;
     return cycle_eval(c, mask, weights, k);
   }

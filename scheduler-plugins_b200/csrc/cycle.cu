@@ -1,4 +1,4 @@
-// The scheduling cycle as ONE kernel: all enabled plugins, chained filters, NormalizeScore, weighted sum and the
+// The scheduling cycle in TWO launches (one graph launch): all enabled plugins, chained filters, NormalizeScore, weighted sum and the
 // per-pod top-k for a handful of pods (the real scheduler's shape is P = 1) over all nodes of the shard.
 //
 // combined.cu evaluates a profile plugin by plugin (13 launches for the five plugins at P = 1: each plugin writes its

@@ -347,7 +347,7 @@ int peaks_eval(b200s_ctx* c, int dtype);
 int lowrisk_eval(b200s_ctx* c, int dtype);
 int combined_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, int write_total);
 int alloc_prepare(b200s_ctx* c);  // raw scores + sorted order of the snapshot (cached per snapshot / args)
-// cycle.cu: the whole cycle as one cooperative kernel (small P, single GPU)
+// cycle.cu: the whole cycle in two launches -- one graph launch from b200s_schedule_batch (small P, single GPU)
 bool cycle_applies(b200s_ctx* c, uint32_t mask, int k, int write_total, bool any_p = false);
 int cycle_eval(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k);
 int cycle_graph_run(b200s_ctx* c, uint32_t mask, const int64_t* weights, int k, b200s_topk_entry* host_out);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Where does a P = 1 cycle (all five plugins + top-1, 50k nodes) spend its time?  Wall-clock p50 of the pieces of
-b200s_schedule_batch, and the cooperative kernel's own duration (CUDA events)."""
+b200s_schedule_batch, and the two cycle kernels' own duration (CUDA events)."""
 import ctypes as C
 import json
 import os
