@@ -54,6 +54,14 @@ int main(void) {
   CHECK(b200s_snapshot_commit(ctx));
   CHECK(b200s_score_batch(ctx, B200S_PLUGIN_ALLOCATABLE, &batch, B200S_OUT_U8, scores, NULL, NULL));
   for (int n = 0; n < 4; ++n) printf("node %d: %d\n", n, scores[n]); /* 100, 0, 41, 0 */
+  /* an engine-only profile does not need the row at all: upload, the whole cycle (two kernels, one graph launch), the
+   * winner back -- one call, one synchronisation */
+  int64_t profile[B200S_PLUGIN_COUNT];
+  memset(profile, 0, sizeof(profile));
+  profile[B200S_PLUGIN_ALLOCATABLE] = 1;
+  b200s_topk_entry winner;
+  CHECK(b200s_schedule_batch(ctx, &batch, 1u << B200S_PLUGIN_ALLOCATABLE, profile, 1, &winner));
+  printf("winner: node %d, score %lld\n", (int)winner.node, (long long)winner.score); /* node 0, score 100 */
   free(feasible);
   free(scores);
   b200s_shutdown(ctx);
