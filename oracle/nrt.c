@@ -459,6 +459,15 @@ void orc_nrt_subtract_from_numas(int64_t* avail, const uint8_t* zmask, int Z, in
 
 /* Test entry point for numaNodesRequired (least_numa.go:159-208): the zone bitmask that can host the request with the
  * fewest zones, and whether it is a minimum-distance combination.  Returns the zone count, 0 = cannot fit. */
+/* onlyNonNUMAResources (pluginhelpers.go:163-173) on zone resource masks: 1 iff no zone lists any requested resource */
+int orc_nrt_only_non_numa(const uint8_t* zone_res_mask, int n_zones, uint8_t req_mask, int R) {
+  zones_t zs;
+  memset(&zs, 0, sizeof(zs));
+  zs.nz = n_zones;
+  for (int z = 0; z < n_zones && z < Z_MAX; ++z) zs.zmask[z] = zone_res_mask[z];
+  return only_non_numa(&zs, req_mask, R);
+}
+
 int orc_nrt_numa_nodes_required(const orc_nrt_node* nd, const uint8_t* res_flags, int R, int qos, uint8_t req_mask,
                                 const int64_t* req, uint32_t* mask_out, int* is_min) {
   zones_t zs;

@@ -165,6 +165,7 @@ int orc_nrt_filter(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t
 int64_t orc_nrt_score(const orc_nrt_node* nd, const orc_nrt_pod* pod, const uint8_t* res_flags, int R, int strategy,
                       const int64_t* weights);
 int64_t orc_nrt_normalize_least_numa(int count, int is_min, int max_numa);
+int orc_nrt_only_non_numa(const uint8_t* zone_res_mask, int n_zones, uint8_t req_mask, int R);
 int orc_nrt_numa_nodes_required(const orc_nrt_node* nd, const uint8_t* res_flags, int R, int qos, uint8_t req_mask,
                                 const int64_t* req, uint32_t* mask_out, int* is_min);
 float orc_nrt_min_avg_distance(const int32_t* cost, int n, const int* combos, int n_combos, int k);

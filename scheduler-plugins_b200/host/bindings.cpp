@@ -222,6 +222,9 @@ PYBIND11_MODULE(_b200host, m) {
     auto ids = NumaNodesRequired((QOS)qos, CreateNUMANodeList(nrt), resources, &is_min);
     return py::make_tuple(ids, is_min);
   });
+  m.def("only_non_numa_resources", [](const NodeResourceTopology& nrt, const ResourceList& resources) {
+    return OnlyNonNUMAResources(CreateNUMANodeList(nrt), resources);
+  });
   m.def("scalar_filter", [](const Pod& pod, const NodeInfo& ni, const NodeResourceTopology& nrt) { return ScalarFilter(pod, ni, nrt); });
   m.def("scalar_score", [](const Pod& pod, const NodeResourceTopology& nrt, int strategy, const std::map<std::string, int64_t>& w) {
     return ScalarScore(pod, nrt, strategy, w);

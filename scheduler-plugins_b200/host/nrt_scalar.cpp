@@ -174,7 +174,9 @@ float NodesAvgDistance(const NUMANodeList& numa_nodes, const std::vector<int>& n
   return (float)accu / (float)(nodes.size() * nodes.size());
 }
 
-bool OnlyNonNUMAResources(const NUMANodeList& numa_nodes, const ResourceList& resources) {  // least_numa.go:102-114
+}  // namespace
+
+bool OnlyNonNUMAResources(const NUMANodeList& numa_nodes, const ResourceList& resources) {  // pluginhelpers.go:163-173
   for (const auto& [res, q] : resources) {
     (void)q;
     for (const auto& numa : numa_nodes)
@@ -182,6 +184,8 @@ bool OnlyNonNUMAResources(const NUMANodeList& numa_nodes, const ResourceList& re
   }
   return true;
 }
+
+namespace {
 
 // subtractFromNUMAs: numaresources.go:184-215 -- `nodes` are NUMA ids used as LIST indices, exactly as the reference
 void SubtractFromNUMAs(const ResourceList& resources, NUMANodeList& numa_nodes, const std::vector<int>& nodes) {

@@ -30,6 +30,7 @@ int64_t ScalarScore(const Pod& pod, const NodeResourceTopology& nrt, int strateg
 
 // numaNodesRequired (least_numa.go:159-174): NUMA ids of the smallest fitting combination (empty = cannot fit) and
 // whether its average distance is the minimum for that size
+bool OnlyNonNUMAResources(const NUMANodeList& numa_nodes, const ResourceList& resources);  // pluginhelpers.go:163-173
 std::vector<int> NumaNodesRequired(QOS qos, const NUMANodeList& numa_nodes, const ResourceList& resources, bool* is_min_distance);
 
 }  // namespace b200host

@@ -238,6 +238,23 @@ def test_numa_nodes_required_all_vectors_through_the_host_scalar_path(H, case):
     assert is_min == case["expected_min_distance"]
 
 
+def _only_non_numa():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "only_non_numa.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _only_non_numa()["cases"], ids=lambda c: c["name"])
+def test_only_non_numa_resources_vectors(H, case):
+    """TestOnlyNonNUMAResources (pluginhelpers_test.go:28-106) through the host's scalar helper."""
+    zones = [dict(z, costs={}) for z in _only_non_numa()["zones"]]
+    assert H.only_non_numa_resources(_nrt_of(H, zones), H.resource_list(case["resources"])) == case["expected"]
+
+
 def test_scalar_filter_and_score_do_not_depend_on_zone_list_order(H):
     """Filter picks the LOWEST NUMA id (filter.go:154) and the Least/Most/Balanced scores take a minimum over zones
     (score.go:110-124): listing the zones in another order must not change either.  Checks the scalar path against

@@ -92,3 +92,31 @@ def test_numa_nodes_required_vectors(oracle, case):
     assert k == len(case["expected_bits"])
     assert out_mask.value == sum(1 << b for b in case["expected_bits"])
     assert bool(is_min.value) == case["expected_min_distance"]
+
+
+# ------------------------------------------------------------------ TestOnlyNonNUMAResources (pluginhelpers_test.go:28-106)
+def _only_non_numa():
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "only_non_numa.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _only_non_numa()["cases"], ids=lambda c: c["name"])
+def test_only_non_numa_resources_vectors(oracle, case):
+    """onlyNonNUMAResources on the dense encoding: a resource slot per name that occurs in the zones or the request, the
+    zones' resource masks, the request mask -- true iff no zone lists any requested resource."""
+    g = _only_non_numa()
+    names = sorted({r for z in g["zones"] for r in z["resources"]} | set(case["resources"]))
+    assert len(names) <= 8
+    zmask = (C.c_uint8 * 8)()
+    for z, zone in enumerate(g["zones"]):
+        for r, n in enumerate(names):
+            if n in zone["resources"]:
+                zmask[z] |= 1 << r
+    req_mask = sum(1 << r for r, n in enumerate(names) if n in case["resources"])
+    got = oracle.lib().orc_nrt_only_non_numa(zmask, C.c_int(len(g["zones"])), C.c_uint8(req_mask), C.c_int(len(names)))
+    assert bool(got) == case["expected"]
